@@ -1,0 +1,164 @@
+/*
+ * seq_engine.h - C ABI of the B200-native batched Lindblad / Schroedinger integrator.
+ *
+ * This is the drop-in boundary for ONE hot path of sequencing-dev/sequencing: the time
+ * evolution that `CompiledPulseSequence.run()` hands to a third-party solver at
+ *     sequencing/sequencing/basic.py:504-512   qutip.mesolve(H, init_state, tlist, c_ops, e_ops, options)
+ *     sequencing/sequencing/basic.py:481-485   qutip.Options(): max_step = dt, store_states = True
+ *     sequencing/sequencing/basic.py:500       qutip.QobjEvo(H, tlist=times)   (only_final_state)
+ *     sequencing/sequencing/basic.py:560-567   qutip.propagator(H, times, c_op_list=c_ops, ...)
+ *     sequencing/sequencing/main.py:316-322    U*psi / U*rho*U^dag between Sequence segments
+ *     sequencing/sequencing/main.py:333-335    qutip.expect(op, states)
+ * The reference has no FFI of its own (pure Python calling QuTiP), so each entry point cites
+ * the Python call it replaces.  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no torch / C++ types.  All matrices are complex128 stored as
+ *    interleaved (re, im) doubles, row-major.
+ *  - unless SEQ_FLAG_HOST_POINTERS is set, every data pointer is a DEVICE pointer owned by the
+ *    caller; the engine never frees or retains them.  Work is enqueued on the engine's stream;
+ *    the caller synchronises that stream before reading outputs.
+ *  - with SEQ_FLAG_HOST_POINTERS every data pointer is a HOST pointer; the engine stages the
+ *    inputs to the device, solves, copies the outputs back and synchronises before returning.
+ *  - every function returns 0 (SEQ_OK) on success, a negative SEQ_ERR_* code otherwise;
+ *    seq_engine_last_error() gives the message.  Per-trajectory integration failures are
+ *    reported in `status[b]` (the call itself still returns SEQ_OK): the Python host raises the
+ *    same-meaning exception QuTiP raises ("ODE integration error ... increase nsteps").
+ *  - one handle per device/stream; calls on one handle are not concurrent.
+ */
+#ifndef SEQ_ENGINE_H
+#define SEQ_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEQ_ENGINE_ABI_VERSION 1
+
+/* return codes */
+#define SEQ_OK 0
+#define SEQ_ERR_INVALID (-1)      /* malformed descriptor                        */
+#define SEQ_ERR_CUDA (-2)         /* CUDA runtime error (message in last_error)  */
+#define SEQ_ERR_UNSUPPORTED (-3)  /* shape / option outside what the kernels cover */
+#define SEQ_ERR_NOMEM (-4)
+
+/* per-trajectory status words */
+#define SEQ_STATUS_OK 0
+#define SEQ_STATUS_MAX_STEPS 1    /* more than `nsteps` internal steps in one output interval */
+#define SEQ_STATUS_NONFINITE 2    /* NaN/Inf in the state or error estimate                    */
+#define SEQ_STATUS_STEP_UNDERFLOW 3
+
+/* flags */
+#define SEQ_FLAG_KET 0x1u             /* state is a ket [N]; Schroedinger evolution (qutip.sesolve) */
+#define SEQ_FLAG_NORMALIZE 0x2u       /* kets: renormalise at every output (Options.normalize_output) */
+#define SEQ_FLAG_STORE_STATES 0x4u    /* write every output state to `states` (Options.store_states) */
+#define SEQ_FLAG_EXPECT_COMPLEX 0x8u  /* `expect` is complex128 (non-Hermitian e_ops)               */
+#define SEQ_FLAG_HOST_POINTERS 0x10u  /* all data pointers are host pointers (end-to-end call)      */
+
+/* kernel selection (0 = let the engine choose by N) */
+#define SEQ_METHOD_AUTO 0
+#define SEQ_METHOD_GENERIC 1   /* FP64-FMA, one CTA per trajectory, any N                    */
+#define SEQ_METHOD_DMMA 2      /* FP64 tensor-core (DMMA.8x8x4) tiles, rho resident in smem  */
+#define SEQ_METHOD_SMALL 3     /* N <= 8: several trajectories per CTA, state in registers   */
+#define SEQ_METHOD_DMMA_STREAM 4 /* DMMA with operands streamed through smem (N too big to stay resident) */
+
+typedef struct seq_engine seq_engine;
+
+/*
+ * One batched solve.  B trajectories share the operators and differ in their coefficient
+ * tables and initial states: one trajectory = one (sequence x initial state x sweep value),
+ * i.e. one `seq.run()` of the reference's sweep loops (calibration.py:120-125, 452-466).
+ *
+ *   H(t)      = H0 + sum_k coeff[b,k](t) * Hk[k]                      (basic.py:225-239)
+ *   d rho/dt  = -i[H, rho] + sum_j (L_j rho L_j^dag - 1/2 {L_j^dag L_j, rho})
+ *               with L_j in Lc (constant) and sqrt(rate[b,j](t)) * Ltd[j] (CTerm, basic.py:241-247)
+ *   d psi/dt  = -i H(t) psi                                           (SEQ_FLAG_KET)
+ *
+ * coeff / rate tables are sampled on the uniform grid t0 + i*dt, i < n_t, and interpolated by
+ * the natural cubic spline QuTiP 4.x applies to array coefficients; `rate` holds conj(c)*c of
+ * the collapse coefficient at the knots.  Outputs are produced at the samples out_idx[0..n_out)
+ * (ascending; integration starts at out_idx[0] and stops at out_idx[n_out-1]).
+ */
+typedef struct seq_solve_desc {
+  uint32_t size;   /* = sizeof(seq_solve_desc) */
+  uint32_t flags;  /* SEQ_FLAG_* */
+  int32_t N;       /* Hilbert-space dimension */
+  int32_t B;       /* trajectories */
+  int32_t n_t;     /* samples per coefficient table */
+  int32_t n_ch;    /* time-dependent Hamiltonian channels */
+  int32_t n_c;     /* constant collapse operators */
+  int32_t n_ctd;   /* time-dependent collapse operators */
+  int32_t n_e;     /* expectation operators */
+  int32_t n_out;   /* output samples */
+  int32_t nsteps;  /* max internal steps per output interval (Options.nsteps, default 1000) */
+  int32_t method;  /* SEQ_METHOD_* */
+  double t0, dt;   /* coefficient grid */
+  double atol, rtol;                  /* Options.atol / rtol (1e-8 / 1e-6) */
+  double max_step, first_step, min_step; /* Options.*; 0 = unset */
+
+  const void* H0;             /* c128 [N,N], or [B,N,N] when H0_batch_stride != 0 */
+  int64_t H0_batch_stride;    /* complex elements between trajectories (0 = shared) */
+  const void* Hk;             /* c128 [n_ch,N,N] */
+  const double* coeff;        /* f64 [B,n_ch,n_t] */
+  int64_t coeff_batch_stride; /* doubles between trajectories; 0 = one table shared by all */
+  const double* coeff_scale;  /* optional f64 [B,n_ch]: per-trajectory multiplier (amplitude sweeps) */
+  const void* Lc;             /* c128 [n_c,N,N] */
+  const void* Ltd;            /* c128 [n_ctd,N,N] */
+  const double* rate;         /* f64 [B,n_ctd,n_t] */
+  int64_t rate_batch_stride;  /* doubles between trajectories; 0 = shared */
+  const void* state0;         /* c128 [B,N,N] (density matrices) or [B,N] (kets) */
+  const void* E;              /* c128 [n_e,N,N] */
+  const int32_t* out_idx;     /* i32 [n_out] */
+
+  void* expect;        /* f64 [B,n_e,n_out], or c128 with SEQ_FLAG_EXPECT_COMPLEX; may be NULL if n_e == 0 */
+  void* final_state;   /* c128 [B,N,N] / [B,N] */
+  void* states;        /* c128 [B,n_out,N,N] / [B,n_out,N]; required with SEQ_FLAG_STORE_STATES */
+  int32_t* status;     /* i32 [B] */
+  int32_t* stats;      /* i32 [B,4]: accepted steps, rejected steps, RHS evaluations, reserved */
+} seq_solve_desc;
+
+/* Library / ABI identification. */
+int seq_engine_abi_version(void);
+const char* seq_engine_build_info(void);
+
+/* Create an engine bound to CUDA device `device` and stream `stream` (a cudaStream_t, NULL =
+ * the legacy default stream).  Replaces: constructing the solver state inside qutip.mesolve. */
+int seq_engine_create(int device, void* stream, seq_engine** out);
+int seq_engine_destroy(seq_engine* eng);
+const char* seq_engine_last_error(const seq_engine* eng);
+
+/* Bytes of device scratch a solve of this shape needs (the engine allocates and caches it). */
+int64_t seq_engine_workspace_bytes(const seq_engine* eng, const seq_solve_desc* desc);
+
+/* The hot path.  Replaces qutip.mesolve / qutip.sesolve at basic.py:504-512. */
+int seq_engine_solve(seq_engine* eng, const seq_solve_desc* desc);
+
+/* Method the engine would pick for this descriptor (SEQ_METHOD_*), without running it. */
+int seq_engine_select_method(const seq_engine* eng, const seq_solve_desc* desc);
+
+/* Number of kernel launches issued by the last seq_engine_solve on this handle, and the
+ * duration in milliseconds of its integration kernel measured with CUDA events on the
+ * engine's stream (valid after the stream is synchronised). */
+int seq_engine_last_launch_count(const seq_engine* eng);
+float seq_engine_last_kernel_ms(seq_engine* eng);
+
+/* Natural-cubic-spline second derivatives M[s,:] of n_series tables y[s,0..n_t) on a uniform
+ * grid (device pointers).  Replaces qutip's _prep_cubic_spline (QobjEvo array coefficients). */
+int seq_engine_spline_prep(seq_engine* eng, const double* y, double* M, int64_t n_series, int32_t n_t, double dt);
+
+/* states[b] <- U states[b] U^dag (density matrices) or U states[b] (kets); U is c128 [N,N]
+ * shared by the batch (device pointers).  Replaces main.py:316-322. */
+int seq_engine_apply_unitary(seq_engine* eng, const void* U, void* states, int32_t N, int32_t B, int is_ket);
+
+/* out[b,e] = Tr(E[e] states[b]) or <psi_b|E[e]|psi_b>, complex128 (device pointers).
+ * Replaces qutip.expect(op, states) at main.py:333-335. */
+int seq_engine_expect(seq_engine* eng, const void* E, const void* states, void* out, int32_t N, int32_t B,
+                      int32_t n_e, int is_ket);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEQ_ENGINE_H */

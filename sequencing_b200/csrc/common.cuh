@@ -1,0 +1,138 @@
+// Shared device helpers: complex arithmetic on double2, the Dormand-Prince 5(4) tableau, the
+// natural-cubic-spline evaluation QuTiP 4.x applies to array coefficients, block reductions,
+// and the kernel parameter block.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/seq_engine.h"
+
+namespace seq {
+
+typedef double2 cplx;
+
+__host__ __device__ __forceinline__ cplx cmake(double r, double i) { cplx z; z.x = r; z.y = i; return z; }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return cmake(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return cmake(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx cconj(cplx a) { return cmake(a.x, -a.y); }
+__device__ __forceinline__ cplx cscale(double s, cplx a) { return cmake(s * a.x, s * a.y); }
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return cmake(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// acc += a*b
+__device__ __forceinline__ void cfma(cplx& acc, cplx a, cplx b) {
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+// acc += a*conj(b)
+__device__ __forceinline__ void cfma_conj(cplx& acc, cplx a, cplx b) {
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(a.y, b.x, acc.y); acc.y = fma(-a.x, b.y, acc.y);
+}
+__device__ __forceinline__ double cabs2(cplx a) { return a.x * a.x + a.y * a.y; }
+
+// ---- Dormand-Prince 5(4), FSAL.  c: nodes, a: stage matrix, b: 5th-order weights (== a7j),
+// e: b - b_hat (error weights).
+#define DP_C2 (1.0 / 5.0)
+#define DP_C3 (3.0 / 10.0)
+#define DP_C4 (4.0 / 5.0)
+#define DP_C5 (8.0 / 9.0)
+#define DP_A21 (1.0 / 5.0)
+#define DP_A31 (3.0 / 40.0)
+#define DP_A32 (9.0 / 40.0)
+#define DP_A41 (44.0 / 45.0)
+#define DP_A42 (-56.0 / 15.0)
+#define DP_A43 (32.0 / 9.0)
+#define DP_A51 (19372.0 / 6561.0)
+#define DP_A52 (-25360.0 / 2187.0)
+#define DP_A53 (64448.0 / 6561.0)
+#define DP_A54 (-212.0 / 729.0)
+#define DP_A61 (9017.0 / 3168.0)
+#define DP_A62 (-355.0 / 33.0)
+#define DP_A63 (46732.0 / 5247.0)
+#define DP_A64 (49.0 / 176.0)
+#define DP_A65 (-5103.0 / 18656.0)
+#define DP_B1 (35.0 / 384.0)
+#define DP_B3 (500.0 / 1113.0)
+#define DP_B4 (125.0 / 192.0)
+#define DP_B5 (-2187.0 / 6784.0)
+#define DP_B6 (11.0 / 84.0)
+#define DP_E1 (71.0 / 57600.0)
+#define DP_E3 (-71.0 / 16695.0)
+#define DP_E4 (71.0 / 1920.0)
+#define DP_E5 (-17253.0 / 339200.0)
+#define DP_E6 (22.0 / 525.0)
+#define DP_E7 (-1.0 / 40.0)
+
+// step-size controller (same constants as scipy's RK45 / Hairer's DOPRI5)
+#define SEQ_SAFETY 0.9
+#define SEQ_MIN_FACTOR 0.2
+#define SEQ_MAX_FACTOR 10.0
+
+// ---- kernel parameter block (device pointers into caller buffers + engine scratch)
+struct SolveParams {
+  int N, B, n_t, n_g, n_ch, n_c, n_ctd, n_e, n_out, nsteps;
+  unsigned flags;
+  double t0, dt, atol, rtol, max_step, first_step, min_step;
+  const cplx* G0;           // [N,N] (or per trajectory): H0 - (i/2) sum_const L^dag L   (kets: H0)
+  long long G0_bstride;
+  const cplx* Gk;           // [n_g,N,N]: H_k (k < n_ch), then -(i/2) L^dag L of time-dependent collapse ops
+  const double2* tab;       // packed spline tables (y_i, M_i dt^2/6): [B or 1][n_g][n_t]
+  long long tab_bstride_c;  // elements between trajectories for the coeff part (0 = shared)
+  long long tab_bstride_r;  // same for the rate part
+  const double2* tab_rate;  // base of the rate tables ([B or 1][n_ctd][n_t]) inside the packed buffer
+  const double* coeff_scale;  // optional [B,n_ch]
+  const cplx* L;            // [n_c + n_ctd, N, N]
+  const cplx* state0;
+  const cplx* E;
+  const int* out_idx;
+  void* expect;
+  cplx* final_state;
+  cplx* states;
+  int* status;
+  int* stats;
+  cplx* ws;                 // per-trajectory scratch
+  long long ws_stride;      // complex elements per trajectory
+};
+
+// Natural cubic spline on a uniform grid, packed table entries (y_i, m_i) with m_i = M_i dt^2/6.
+// Restates qutip/cy/inter.pyx::_spline_float_cte_second: clamp outside the grid,
+// value = te*(m_p te^2 + y_p - m_p) + tb*(m_{p+1} tb^2 + y_{p+1} - m_{p+1}).
+__device__ __forceinline__ double spline_eval(const double2* __restrict__ tab, int n_t, double t0, double dt, double t) {
+  double x = (t - t0) / dt;
+  if (x <= 0.0) return tab[0].x;
+  if (x >= (double)(n_t - 1)) return tab[n_t - 1].x;
+  int p = (int)x;
+  double tb = x - (double)p;
+  double te = 1.0 - tb;
+  double2 a = tab[p];
+  double2 b = tab[p + 1];
+  return te * (a.y * te * te + (a.x - a.y)) + tb * (b.y * tb * tb + (b.x - b.y));
+}
+
+// ---- block-wide sum; `scratch` holds >= 33 doubles.  Result is returned to every thread.
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect scratch reuse
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double s = (lane < nw) ? scratch[lane] : 0.0;
+    s = warp_sum(s);
+    if (lane == 0) scratch[32] = s;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+__device__ __forceinline__ cplx block_sum_c(cplx v, double* scratch) {
+  double r = block_sum(v.x, scratch);
+  double i = block_sum(v.y, scratch);
+  return cmake(r, i);
+}
+
+}  // namespace seq

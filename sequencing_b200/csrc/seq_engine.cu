@@ -1,0 +1,616 @@
+// C-ABI implementation of include/seq_engine.h: descriptor validation, device scratch
+// management, the preparation kernels (effective-Hamiltonian assembly, natural-cubic-spline
+// second derivatives) and dispatch to the integration kernels.
+//
+// Build (see __graft_entry__.build):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC \
+//        -o sequencing_b200/_seq_engine.so sequencing_b200/csrc/seq_engine.cu
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernel_generic.cuh"
+#include "kernel_dmma.cuh"
+#include "kernel_small.cuh"
+
+using namespace seq;
+
+// ------------------------------------------------------------------------------------------
+// engine object
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t cap = 0;
+};
+
+struct seq_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  DevBuf ws, gbuf, tab, cprime, stage_in, stage_out;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  int launches = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+};
+
+static int fail(seq_engine* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf;
+  return code;
+}
+
+#define CUDA_TRY(eng, call)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return fail(eng, SEQ_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+static int reserve(seq_engine* e, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return SEQ_OK;
+  if (b.ptr) {
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    CUDA_TRY(e, cudaFree(b.ptr));
+    b.ptr = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + bytes / 8 + 256;
+  cudaError_t rc = cudaMalloc(&b.ptr, want);
+  if (rc != cudaSuccess) {
+    b.ptr = nullptr;
+    return fail(e, SEQ_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(rc));
+  }
+  b.cap = want;
+  return SEQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// preparation kernels
+// ------------------------------------------------------------------------------------------
+// K = sum_{l in [l0,l1)} L_l^dag L_l  (naive; operators are built once per solve)
+__device__ __forceinline__ cplx ldagl_elem(const cplx* __restrict__ L, int N, int a, int b) {
+  cplx acc = cmake(0, 0);
+  for (int k = 0; k < N; k++) {
+    cplx x = L[k * N + a], y = L[k * N + b];
+    // conj(x) * y
+    acc.x = fma(x.x, y.x, acc.x); acc.x = fma(x.y, y.y, acc.x);
+    acc.y = fma(x.x, y.y, acc.y); acc.y = fma(-x.y, y.x, acc.y);
+  }
+  return acc;
+}
+
+// G0[b] = H0[b] - (i/2) sum_const L^dag L ; grid.y = number of G0 matrices (1 or B)
+__global__ void prep_G0_kernel(const cplx* __restrict__ H0, long long h0_stride, const cplx* __restrict__ Lc, int n_c,
+                               int N, cplx* __restrict__ G0, int ket) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int m = blockIdx.y;
+  if (idx >= N * N) return;
+  cplx g = H0[(long long)m * h0_stride + idx];
+  if (!ket) {
+    int a = idx / N, b = idx - a * N;
+    cplx s = cmake(0, 0);
+    for (int l = 0; l < n_c; l++) {
+      cplx v = ldagl_elem(Lc + (long long)l * N * N, N, a, b);
+      s.x += v.x; s.y += v.y;
+    }
+    // -(i/2) s = (s.y/2, -s.x/2)
+    g.x += 0.5 * s.y;
+    g.y -= 0.5 * s.x;
+  }
+  G0[(long long)m * N * N + idx] = g;
+}
+
+// Gk[m] = Hk[m] (m < n_ch) ; Gk[n_ch+j] = -(i/2) Ltd_j^dag Ltd_j
+__global__ void prep_Gk_kernel(const cplx* __restrict__ Hk, int n_ch, const cplx* __restrict__ Ltd, int n_ctd, int N,
+                               cplx* __restrict__ Gk) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int m = blockIdx.y;
+  if (idx >= N * N) return;
+  cplx g;
+  if (m < n_ch) {
+    g = Hk[(long long)m * N * N + idx];
+  } else {
+    int a = idx / N, b = idx - a * N;
+    cplx v = ldagl_elem(Ltd + (long long)(m - n_ch) * N * N, N, a, b);
+    g = cmake(0.5 * v.y, -0.5 * v.x);
+  }
+  Gk[(long long)m * N * N + idx] = g;
+}
+
+// Thomas factors of the (1,4,1) system, shared by every series: cp[i] for i in 1..n_t-2
+__global__ void spline_cprime_kernel(double* cp, int n_t) {
+  if (blockIdx.x || threadIdx.x) return;
+  double c = 0.0;
+  for (int i = 1; i <= n_t - 2; i++) {
+    c = 1.0 / (4.0 - c);
+    cp[i] = c;
+  }
+}
+
+// One thread per series: m solves m[i-1] + 4 m[i] + m[i+1] = y[i+1] - 2 y[i] + y[i-1], m[0]=m[n-1]=0
+// (m = M dt^2/6 of QuTiP's _prep_cubic_spline).  Output is packed (y, m) per sample.
+__global__ void spline_series_kernel(const double* __restrict__ y, double2* __restrict__ out, const double* __restrict__ cp,
+                                     long long n_series, int n_t) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_series) return;
+  const double* ys = y + s * n_t;
+  double2* o = out + s * n_t;
+  if (n_t < 3) {
+    for (int i = 0; i < n_t; i++) o[i] = make_double2(ys[i], 0.0);
+    return;
+  }
+  double dprev = 0.0;
+  double ym = ys[0], yc = ys[1];
+  o[0] = make_double2(ym, 0.0);
+  for (int i = 1; i <= n_t - 2; i++) {
+    double yp = ys[i + 1];
+    double rhs = yp - 2.0 * yc + ym;
+    double d = (rhs - dprev) * cp[i];
+    o[i] = make_double2(yc, d);
+    dprev = d;
+    ym = yc;
+    yc = yp;
+  }
+  o[n_t - 1] = make_double2(yc, 0.0);
+  double mnext = 0.0;
+  for (int i = n_t - 2; i >= 1; i--) {
+    double2 v = o[i];
+    double m = v.y - cp[i] * mnext;
+    o[i] = make_double2(v.x, m);
+    mnext = m;
+  }
+}
+
+// unpack helper for seq_engine_spline_prep: M[i] = m[i] * 6 / dt^2
+__global__ void spline_unpack_kernel(const double2* __restrict__ packed, double* __restrict__ M, long long n, double scale) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) M[i] = packed[i].y * scale;
+}
+
+// states[b] <- U states[b] U^dag  /  U psi_b   (one CTA per trajectory; scratch T in global)
+__global__ void apply_unitary_kernel(const cplx* __restrict__ U, cplx* __restrict__ states, cplx* __restrict__ scratch,
+                                     int N, int is_ket) {
+  int b = blockIdx.x;
+  if (is_ket) {
+    cplx* psi = states + (long long)b * N;
+    cplx* T = scratch + (long long)b * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      cplx acc = cmake(0, 0);
+      for (int k = 0; k < N; k++) cfma(acc, U[i * N + k], psi[k]);
+      T[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) psi[i] = T[i];
+    return;
+  }
+  cplx* rho = states + (long long)b * N * N;
+  cplx* T = scratch + (long long)b * N * N;
+  for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
+    int i = idx / N, j = idx - i * N;
+    cplx acc = cmake(0, 0);
+    for (int k = 0; k < N; k++) cfma(acc, U[i * N + k], rho[k * N + j]);
+    T[idx] = acc;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
+    int i = idx / N, j = idx - i * N;
+    cplx acc = cmake(0, 0);
+    for (int k = 0; k < N; k++) cfma_conj(acc, T[i * N + k], U[j * N + k]);
+    rho[idx] = acc;
+  }
+}
+
+__global__ void expect_kernel(const cplx* __restrict__ E, const cplx* __restrict__ states, cplx* __restrict__ out, int N,
+                              int n_e, int is_ket) {
+  __shared__ double red[34];
+  int b = blockIdx.x, e = blockIdx.y;
+  const cplx* Em = E + (long long)e * N * N;
+  cplx acc = cmake(0, 0);
+  if (is_ket) {
+    const cplx* psi = states + (long long)b * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      cplx row = cmake(0, 0);
+      for (int k = 0; k < N; k++) cfma(row, Em[i * N + k], psi[k]);
+      cfma_conj(acc, row, psi[i]);
+    }
+  } else {
+    const cplx* rho = states + (long long)b * N * N;
+    for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
+      int i = idx / N, j = idx - i * N;
+      cfma(acc, Em[idx], rho[j * N + i]);
+    }
+  }
+  acc = block_sum_c(acc, red);
+  if (threadIdx.x == 0) out[(long long)b * n_e + e] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// descriptor checks and method selection
+// ------------------------------------------------------------------------------------------
+static int validate(seq_engine* e, const seq_solve_desc* d) {
+  if (!d) return fail(e, SEQ_ERR_INVALID, "descriptor is NULL");
+  if (d->size != sizeof(seq_solve_desc))
+    return fail(e, SEQ_ERR_INVALID, "descriptor size %u != %zu (ABI mismatch)", d->size, sizeof(seq_solve_desc));
+  if (d->N < 1 || d->B < 0 || d->n_t < 1 || d->n_out < 1)
+    return fail(e, SEQ_ERR_INVALID, "bad shape N=%d B=%d n_t=%d n_out=%d", d->N, d->B, d->n_t, d->n_out);
+  if (d->n_ch < 0 || d->n_c < 0 || d->n_ctd < 0 || d->n_e < 0)
+    return fail(e, SEQ_ERR_INVALID, "negative operator count");
+  if (!(d->dt > 0)) return fail(e, SEQ_ERR_INVALID, "dt must be positive");
+  if (!(d->atol > 0) || !(d->rtol >= 0)) return fail(e, SEQ_ERR_INVALID, "bad tolerances atol=%g rtol=%g", d->atol, d->rtol);
+  if (d->nsteps < 1) return fail(e, SEQ_ERR_INVALID, "nsteps must be >= 1");
+  if (d->B == 0) return SEQ_OK;
+  if (!d->H0 || !d->state0 || !d->final_state || !d->status || !d->stats || !d->out_idx)
+    return fail(e, SEQ_ERR_INVALID, "required pointer is NULL (H0/state0/final_state/status/stats/out_idx)");
+  if (d->n_ch > 0 && (!d->Hk || !d->coeff)) return fail(e, SEQ_ERR_INVALID, "n_ch > 0 but Hk/coeff is NULL");
+  if (d->n_c > 0 && !d->Lc) return fail(e, SEQ_ERR_INVALID, "n_c > 0 but Lc is NULL");
+  if (d->n_ctd > 0 && (!d->Ltd || !d->rate)) return fail(e, SEQ_ERR_INVALID, "n_ctd > 0 but Ltd/rate is NULL");
+  if (d->n_e > 0 && (!d->E || !d->expect)) return fail(e, SEQ_ERR_INVALID, "n_e > 0 but E/expect is NULL");
+  if ((d->flags & SEQ_FLAG_STORE_STATES) && !d->states)
+    return fail(e, SEQ_ERR_INVALID, "SEQ_FLAG_STORE_STATES set but states is NULL");
+  if ((d->flags & SEQ_FLAG_KET) && (d->n_c + d->n_ctd) > 0)
+    return fail(e, SEQ_ERR_INVALID, "kets cannot be evolved with collapse operators (convert to a density matrix)");
+  if (d->n_ch + d->n_ctd > 64) return fail(e, SEQ_ERR_UNSUPPORTED, "more than 64 time-dependent terms");
+  return SEQ_OK;
+}
+
+static int pick_method(const seq_engine* e, const seq_solve_desc* d) {
+  if (d->method != SEQ_METHOD_AUTO) return d->method;
+  const bool ket = d->flags & SEQ_FLAG_KET;
+  if (!ket && small_supported(d->N, d->n_ch + d->n_ctd, d->n_c + d->n_ctd)) return SEQ_METHOD_SMALL;
+  if (!ket && d->H0_batch_stride == 0 && dmma_supported(d->N, e ? e->max_smem_optin : 232448)) return SEQ_METHOD_DMMA;
+  return SEQ_METHOD_GENERIC;
+}
+
+static size_t state_elems(const seq_solve_desc* d) {
+  return (d->flags & SEQ_FLAG_KET) ? (size_t)d->N : (size_t)d->N * d->N;
+}
+
+static size_t ws_elems_per_traj(const seq_solve_desc* d, int method) {
+  size_t N2 = (size_t)d->N * d->N, NN = state_elems(d);
+  if (method == SEQ_METHOD_GENERIC) return 2 * N2 + 9 * NN;
+  if (method == SEQ_METHOD_DMMA) return dmma_ws_elems(d->N);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int seq_engine_abi_version(void) { return SEQ_ENGINE_ABI_VERSION; }
+
+const char* seq_engine_build_info(void) {
+  return "seq_engine abi=1 arch=sm_100a kernels=generic(fma),dmma(8x8x4 resident),small(registers) built " __DATE__;
+}
+
+int seq_engine_create(int device, void* stream, seq_engine** out) {
+  if (!out) return SEQ_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t rc = cudaGetDeviceCount(&count);
+  if (rc != cudaSuccess || device < 0 || device >= count) return SEQ_ERR_CUDA;
+  seq_engine* e = new seq_engine();
+  e->device = device;
+  e->stream = (cudaStream_t)stream;
+  if (cudaSetDevice(device) != cudaSuccess) { delete e; return SEQ_ERR_CUDA; }
+  cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if (cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) { delete e; return SEQ_ERR_CUDA; }
+  *out = e;
+  return SEQ_OK;
+}
+
+int seq_engine_destroy(seq_engine* e) {
+  if (!e) return SEQ_OK;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  DevBuf* bufs[] = {&e->ws, &e->gbuf, &e->tab, &e->cprime, &e->stage_in, &e->stage_out};
+  for (DevBuf* b : bufs) if (b->ptr) cudaFree(b->ptr);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  delete e;
+  return SEQ_OK;
+}
+
+const char* seq_engine_last_error(const seq_engine* e) { return e ? e->err.c_str() : "engine is NULL"; }
+
+int seq_engine_select_method(const seq_engine* e, const seq_solve_desc* d) {
+  if (!d) return SEQ_ERR_INVALID;
+  return pick_method(e, d);
+}
+
+int64_t seq_engine_workspace_bytes(const seq_engine* e, const seq_solve_desc* d) {
+  if (!d || d->size != sizeof(seq_solve_desc)) return SEQ_ERR_INVALID;
+  int method = pick_method(e, d);
+  size_t N2 = (size_t)d->N * d->N;
+  int n_g = d->n_ch + d->n_ctd;
+  size_t nG0 = d->H0_batch_stride ? (size_t)d->B : 1;
+  size_t bytes = ws_elems_per_traj(d, method) * (size_t)d->B * sizeof(cplx);
+  bytes += (nG0 + n_g) * N2 * sizeof(cplx);
+  size_t series_c = (size_t)(d->coeff_batch_stride ? d->B : 1) * d->n_ch;
+  size_t series_r = (size_t)(d->rate_batch_stride ? d->B : 1) * d->n_ctd;
+  bytes += (series_c + series_r) * (size_t)d->n_t * sizeof(double2) + (size_t)d->n_t * sizeof(double);
+  return (int64_t)bytes;
+}
+
+int seq_engine_last_launch_count(const seq_engine* e) { return e ? e->launches : 0; }
+
+float seq_engine_last_kernel_ms(seq_engine* e) {
+  if (!e || !e->timed) return -1.0f;
+  if (cudaEventSynchronize(e->ev1) != cudaSuccess) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+static int spline_prep_packed(seq_engine* e, const double* y, double2* packed, long long n_series, int n_t) {
+  if (n_series == 0) return SEQ_OK;
+  int rc = reserve(e, e->cprime, (size_t)n_t * sizeof(double));
+  if (rc) return rc;
+  spline_cprime_kernel<<<1, 32, 0, e->stream>>>((double*)e->cprime.ptr, n_t);
+  e->launches++;
+  int threads = 128;
+  long long blocks = (n_series + threads - 1) / threads;
+  spline_series_kernel<<<(unsigned)blocks, threads, 0, e->stream>>>(y, packed, (const double*)e->cprime.ptr, n_series, n_t);
+  e->launches++;
+  CUDA_TRY(e, cudaGetLastError());
+  return SEQ_OK;
+}
+
+int seq_engine_spline_prep(seq_engine* e, const double* y, double* M, int64_t n_series, int32_t n_t, double dt) {
+  if (!e) return SEQ_ERR_INVALID;
+  if (!y || !M || n_series < 0 || n_t < 1 || !(dt > 0)) return fail(e, SEQ_ERR_INVALID, "bad spline_prep arguments");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  e->launches = 0;
+  size_t n = (size_t)n_series * n_t;
+  if (n == 0) return SEQ_OK;
+  int rc = reserve(e, e->tab, n * sizeof(double2));
+  if (rc) return rc;
+  rc = spline_prep_packed(e, y, (double2*)e->tab.ptr, n_series, n_t);
+  if (rc) return rc;
+  spline_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>((const double2*)e->tab.ptr, M, (long long)n, 6.0 / (dt * dt));
+  e->launches++;
+  CUDA_TRY(e, cudaGetLastError());
+  return SEQ_OK;
+}
+
+static int solve_device(seq_engine* e, const seq_solve_desc* d) {
+  const int N = d->N, B = d->B;
+  const size_t N2 = (size_t)N * N;
+  const int n_g = d->n_ch + d->n_ctd;
+  const bool ket = d->flags & SEQ_FLAG_KET;
+  const int method = pick_method(e, d);
+  if (method == SEQ_METHOD_DMMA && (ket || !dmma_supported(N, e->max_smem_optin) || d->H0_batch_stride))
+    return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_DMMA does not cover N=%d ket=%d h0_stride=%lld", N, (int)ket, (long long)d->H0_batch_stride);
+  if (method == SEQ_METHOD_SMALL && (ket || !small_supported(N, n_g, d->n_c + d->n_ctd)))
+    return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_SMALL does not cover N=%d ket=%d", N, (int)ket);
+  if (method != SEQ_METHOD_GENERIC && method != SEQ_METHOD_DMMA && method != SEQ_METHOD_SMALL)
+    return fail(e, SEQ_ERR_UNSUPPORTED, "method %d is not implemented", method);
+
+  // ---- scratch
+  const size_t nG0 = d->H0_batch_stride ? (size_t)B : 1;
+  int rc = reserve(e, e->gbuf, (nG0 + n_g) * N2 * sizeof(cplx));
+  if (rc) return rc;
+  const size_t ws_per = ws_elems_per_traj(d, method);
+  rc = reserve(e, e->ws, ws_per * (size_t)B * sizeof(cplx) + 256);
+  if (rc) return rc;
+  const long long series_c = (long long)(d->coeff_batch_stride ? B : 1) * d->n_ch;
+  const long long series_r = (long long)(d->rate_batch_stride ? B : 1) * d->n_ctd;
+  rc = reserve(e, e->tab, (size_t)(series_c + series_r) * d->n_t * sizeof(double2) + 256);
+  if (rc) return rc;
+  if (d->coeff_batch_stride && d->coeff_batch_stride != (int64_t)d->n_ch * d->n_t)
+    return fail(e, SEQ_ERR_UNSUPPORTED, "coeff_batch_stride must be 0 or n_ch*n_t");
+  if (d->rate_batch_stride && d->rate_batch_stride != (int64_t)d->n_ctd * d->n_t)
+    return fail(e, SEQ_ERR_UNSUPPORTED, "rate_batch_stride must be 0 or n_ctd*n_t");
+
+  cplx* G0 = (cplx*)e->gbuf.ptr;
+  cplx* Gk = G0 + nG0 * N2;
+  double2* tabc = (double2*)e->tab.ptr;
+  double2* tabr = tabc + (size_t)series_c * d->n_t;
+
+  // ---- preparation
+  {
+    dim3 grid((unsigned)((N2 + 127) / 128), (unsigned)nG0);
+    prep_G0_kernel<<<grid, 128, 0, e->stream>>>((const cplx*)d->H0, d->H0_batch_stride, (const cplx*)d->Lc, d->n_c, N, G0, ket ? 1 : 0);
+    e->launches++;
+    if (n_g > 0) {
+      dim3 gk((unsigned)((N2 + 127) / 128), (unsigned)n_g);
+      prep_Gk_kernel<<<gk, 128, 0, e->stream>>>((const cplx*)d->Hk, d->n_ch, (const cplx*)d->Ltd, d->n_ctd, N, Gk);
+      e->launches++;
+    }
+    rc = spline_prep_packed(e, d->coeff, tabc, series_c, d->n_t);
+    if (rc) return rc;
+    rc = spline_prep_packed(e, d->rate, tabr, series_r, d->n_t);
+    if (rc) return rc;
+  }
+
+  // collapse operators must be contiguous [n_c + n_ctd, N, N] for the kernels: if both kinds
+  // are present, pack them behind the G matrices
+  const cplx* Lall = (const cplx*)d->Lc;
+  if (d->n_ctd > 0) {
+    if (d->n_c == 0) {
+      Lall = (const cplx*)d->Ltd;
+    } else {
+      size_t need = (nG0 + n_g + d->n_c + d->n_ctd) * N2 * sizeof(cplx);
+      // gbuf may move: re-reserve before the prep launches would be cleaner, but reserve() syncs the stream first
+      if (need > e->gbuf.cap) return fail(e, SEQ_ERR_UNSUPPORTED, "internal: gbuf too small for packed collapse operators");
+      cplx* dst = Gk + (size_t)n_g * N2;
+      CUDA_TRY(e, cudaMemcpyAsync(dst, d->Lc, (size_t)d->n_c * N2 * sizeof(cplx), cudaMemcpyDeviceToDevice, e->stream));
+      CUDA_TRY(e, cudaMemcpyAsync(dst + (size_t)d->n_c * N2, d->Ltd, (size_t)d->n_ctd * N2 * sizeof(cplx), cudaMemcpyDeviceToDevice, e->stream));
+      Lall = dst;
+    }
+  }
+
+  SolveParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.B = B; p.n_t = d->n_t; p.n_g = n_g; p.n_ch = d->n_ch; p.n_c = d->n_c; p.n_ctd = d->n_ctd;
+  p.n_e = d->n_e; p.n_out = d->n_out; p.nsteps = d->nsteps; p.flags = d->flags;
+  p.t0 = d->t0; p.dt = d->dt; p.atol = d->atol; p.rtol = d->rtol;
+  p.max_step = d->max_step; p.first_step = d->first_step; p.min_step = d->min_step;
+  p.G0 = G0; p.G0_bstride = d->H0_batch_stride ? (long long)N2 : 0;
+  p.Gk = Gk;
+  p.tab = tabc; p.tab_rate = tabr;
+  p.tab_bstride_c = d->coeff_batch_stride ? (long long)d->n_ch * d->n_t : 0;
+  p.tab_bstride_r = d->rate_batch_stride ? (long long)d->n_ctd * d->n_t : 0;
+  p.coeff_scale = d->coeff_scale;
+  p.L = Lall;
+  p.state0 = (const cplx*)d->state0; p.E = (const cplx*)d->E; p.out_idx = d->out_idx;
+  p.expect = d->expect; p.final_state = (cplx*)d->final_state; p.states = (cplx*)d->states;
+  p.status = d->status; p.stats = d->stats;
+  p.ws = (cplx*)e->ws.ptr; p.ws_stride = (long long)ws_per;
+
+  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  if (method == SEQ_METHOD_GENERIC) {
+    size_t elems = ket ? (size_t)N : N2;
+    int threads = (int)((elems + 31) / 32 * 32);
+    if (threads < 32) threads = 32;
+    if (threads > 256) threads = 256;
+    size_t smem = (34 + 64) * sizeof(double);
+    if (ket) solve_generic_kernel<true><<<B, threads, smem, e->stream>>>(p);
+    else solve_generic_kernel<false><<<B, threads, smem, e->stream>>>(p);
+    e->launches++;
+  } else if (method == SEQ_METHOD_DMMA) {
+    rc = launch_dmma(p, e->sm_count, e->max_smem_optin, e->stream);
+    if (rc) return fail(e, rc, "DMMA kernel launch configuration failed for N=%d", N);
+    e->launches++;
+  } else {
+    rc = launch_small(p, e->sm_count, e->stream);
+    if (rc) return fail(e, rc, "small-N kernel launch configuration failed for N=%d", N);
+    e->launches++;
+  }
+  CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  e->timed = true;
+  CUDA_TRY(e, cudaGetLastError());
+  return SEQ_OK;
+}
+
+// end-to-end call on host buffers: stage in, solve, stage out, synchronise
+static int solve_host(seq_engine* e, const seq_solve_desc* d) {
+  const size_t N2 = (size_t)d->N * d->N, NN = state_elems(d), B = d->B;
+  const size_t cz = sizeof(cplx);
+  struct Seg { const void* src; size_t bytes; size_t off; };
+  std::vector<Seg> in;
+  size_t off = 0;
+  auto add_in = [&](const void* src, size_t bytes) -> size_t {
+    size_t o = off;
+    if (src && bytes) { in.push_back({src, bytes, o}); off += (bytes + 255) / 256 * 256; }
+    return o;
+  };
+  size_t oH0 = add_in(d->H0, (d->H0_batch_stride ? B : 1) * N2 * cz);
+  size_t oHk = add_in(d->Hk, (size_t)d->n_ch * N2 * cz);
+  size_t oco = add_in(d->coeff, (d->coeff_batch_stride ? B : 1) * (size_t)d->n_ch * d->n_t * sizeof(double));
+  size_t ocs = add_in(d->coeff_scale, B * (size_t)d->n_ch * sizeof(double));
+  size_t oLc = add_in(d->Lc, (size_t)d->n_c * N2 * cz);
+  size_t oLt = add_in(d->Ltd, (size_t)d->n_ctd * N2 * cz);
+  size_t ora = add_in(d->rate, (d->rate_batch_stride ? B : 1) * (size_t)d->n_ctd * d->n_t * sizeof(double));
+  size_t os0 = add_in(d->state0, B * NN * cz);
+  size_t oE = add_in(d->E, (size_t)d->n_e * N2 * cz);
+  size_t ooi = add_in(d->out_idx, (size_t)d->n_out * sizeof(int32_t));
+  int rc = reserve(e, e->stage_in, off + 256);
+  if (rc) return rc;
+  char* din = (char*)e->stage_in.ptr;
+  for (const Seg& s : in) CUDA_TRY(e, cudaMemcpyAsync(din + s.off, s.src, s.bytes, cudaMemcpyHostToDevice, e->stream));
+
+  const size_t esz = (d->flags & SEQ_FLAG_EXPECT_COMPLEX) ? cz : sizeof(double);
+  size_t b_exp = B * (size_t)d->n_e * d->n_out * esz;
+  size_t b_fin = B * NN * cz;
+  size_t b_sts = (d->flags & SEQ_FLAG_STORE_STATES) ? B * (size_t)d->n_out * NN * cz : 0;
+  size_t b_status = B * sizeof(int32_t), b_stats = B * 4 * sizeof(int32_t);
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  size_t o_exp = 0, o_fin = o_exp + up(b_exp), o_sts = o_fin + up(b_fin), o_status = o_sts + up(b_sts), o_stats = o_status + up(b_status);
+  rc = reserve(e, e->stage_out, o_stats + up(b_stats) + 256);
+  if (rc) return rc;
+  char* dout = (char*)e->stage_out.ptr;
+
+  seq_solve_desc dd = *d;
+  dd.flags &= ~SEQ_FLAG_HOST_POINTERS;
+  dd.H0 = d->H0 ? din + oH0 : nullptr;
+  dd.Hk = d->Hk && d->n_ch ? din + oHk : nullptr;
+  dd.coeff = d->coeff && d->n_ch ? (const double*)(din + oco) : nullptr;
+  dd.coeff_scale = d->coeff_scale && d->n_ch ? (const double*)(din + ocs) : nullptr;
+  dd.Lc = d->Lc && d->n_c ? din + oLc : nullptr;
+  dd.Ltd = d->Ltd && d->n_ctd ? din + oLt : nullptr;
+  dd.rate = d->rate && d->n_ctd ? (const double*)(din + ora) : nullptr;
+  dd.state0 = din + os0;
+  dd.E = d->E && d->n_e ? din + oE : nullptr;
+  dd.out_idx = (const int32_t*)(din + ooi);
+  dd.expect = d->n_e ? dout + o_exp : nullptr;
+  dd.final_state = dout + o_fin;
+  dd.states = b_sts ? dout + o_sts : nullptr;
+  dd.status = (int32_t*)(dout + o_status);
+  dd.stats = (int32_t*)(dout + o_stats);
+  rc = solve_device(e, &dd);
+  if (rc) return rc;
+  if (b_exp) CUDA_TRY(e, cudaMemcpyAsync(d->expect, dout + o_exp, b_exp, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(d->final_state, dout + o_fin, b_fin, cudaMemcpyDeviceToHost, e->stream));
+  if (b_sts) CUDA_TRY(e, cudaMemcpyAsync(d->states, dout + o_sts, b_sts, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(d->status, dout + o_status, b_status, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(d->stats, dout + o_stats, b_stats, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  return SEQ_OK;
+}
+
+int seq_engine_solve(seq_engine* e, const seq_solve_desc* d) {
+  if (!e) return SEQ_ERR_INVALID;
+  int rc = validate(e, d);
+  if (rc) return rc;
+  e->launches = 0;
+  e->timed = false;
+  if (d->B == 0) return SEQ_OK;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  // gbuf must also hold the packed collapse operators when both kinds are present
+  if (d->n_c > 0 && d->n_ctd > 0) {
+    size_t N2 = (size_t)d->N * d->N;
+    size_t nG0 = d->H0_batch_stride ? (size_t)d->B : 1;
+    rc = reserve(e, e->gbuf, (nG0 + d->n_ch + d->n_ctd + d->n_c + d->n_ctd) * N2 * sizeof(cplx));
+    if (rc) return rc;
+  }
+  if (d->flags & SEQ_FLAG_HOST_POINTERS) return solve_host(e, d);
+  return solve_device(e, d);
+}
+
+int seq_engine_apply_unitary(seq_engine* e, const void* U, void* states, int32_t N, int32_t B, int is_ket) {
+  if (!e) return SEQ_ERR_INVALID;
+  if (!U || !states || N < 1 || B < 0) return fail(e, SEQ_ERR_INVALID, "bad apply_unitary arguments");
+  e->launches = 0;
+  if (B == 0) return SEQ_OK;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  size_t per = is_ket ? (size_t)N : (size_t)N * N;
+  int rc = reserve(e, e->ws, per * B * sizeof(cplx));
+  if (rc) return rc;
+  int threads = (int)((per + 31) / 32 * 32);
+  if (threads > 256) threads = 256;
+  apply_unitary_kernel<<<B, threads, 0, e->stream>>>((const cplx*)U, (cplx*)states, (cplx*)e->ws.ptr, N, is_ket);
+  e->launches++;
+  CUDA_TRY(e, cudaGetLastError());
+  return SEQ_OK;
+}
+
+int seq_engine_expect(seq_engine* e, const void* E, const void* states, void* out, int32_t N, int32_t B, int32_t n_e,
+                      int is_ket) {
+  if (!e) return SEQ_ERR_INVALID;
+  if (!E || !states || !out || N < 1 || B < 0 || n_e < 0) return fail(e, SEQ_ERR_INVALID, "bad expect arguments");
+  e->launches = 0;
+  if (B == 0 || n_e == 0) return SEQ_OK;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  size_t per = is_ket ? (size_t)N : (size_t)N * N;
+  int threads = (int)((per + 31) / 32 * 32);
+  if (threads > 256) threads = 256;
+  dim3 grid(B, n_e);
+  expect_kernel<<<grid, threads, 0, e->stream>>>((const cplx*)E, (const cplx*)states, (cplx*)out, N, n_e, is_ket);
+  e->launches++;
+  CUDA_TRY(e, cudaGetLastError());
+  return SEQ_OK;
+}
+
+}  // extern "C"

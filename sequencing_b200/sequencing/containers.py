@@ -1,0 +1,240 @@
+"""Sequence containers: ``PulseSequence``, ``Sequence`` and ``SequenceResult``.
+
+Callers of the hot path (reference ``sequencing/sequencing/main.py``): ``PulseSequence.run``
+compiles and runs one pulse block (``:67-136``); ``Sequence.run`` walks a list of pulse blocks,
+bare Operations and instantaneous unitaries, handing the final state of each segment to the
+next (``:250-340``) - segments are sequentially dependent, so batching is across independent
+sequences, not within one.
+"""
+import copy
+
+import numpy as np
+
+from .. import qobj as qt
+from .compiled import CompiledPulseSequence
+from .ops import (
+    DelayChannelsOperation,
+    DelayOperation,
+    Operation,
+    SyncOperation,
+    ValidatedList,
+    delay_channels,
+    get_sequence,
+)
+
+try:  # progress bars are cosmetic
+    from tqdm import tqdm
+except Exception:  # pragma: no cover
+    def tqdm(iterable, **kwargs):
+        return iterable
+
+
+class PulseSequence(ValidatedList):
+    """List of Operation / Sync / Delay / DelayChannels items, compiled lazily."""
+
+    VALID_TYPES = (Operation, SyncOperation, DelayOperation, DelayChannelsOperation)
+
+    def __init__(self, system=None, t0=0, items=None):
+        self.system = None
+        self.t0 = None
+        super().__init__(items)
+        self.set_system(system=system, t0=t0)
+
+    def set_system(self, system=None, t0=0):
+        self.system = system
+        self.t0 = t0
+        self.clear()
+
+    def compile(self):
+        """Replay the items into a fresh ``CompiledPulseSequence`` starting at ``self.t0``."""
+        seq = CompiledPulseSequence(system=self.system, t0=self.t0)
+        for item in self:
+            item = self._validate(item)
+            if isinstance(item, Operation):
+                seq.add_operation(item)
+            elif isinstance(item, SyncOperation):
+                seq.sync()
+            elif isinstance(item, DelayOperation):
+                seq.delay(item.length, sync_before=item.sync_before, sync_after=item.sync_after)
+            else:
+                delay_channels(item.channels, item.length, seq=seq)
+        return seq
+
+    @property
+    def times(self):
+        return self.compile().times
+
+    @property
+    def channels(self):
+        return self.compile().channels
+
+    def run(self, init_state, c_ops=None, e_ops=None, options=None, only_final_state=False, progress_bar=None):
+        return self.compile().run(init_state, c_ops=c_ops, e_ops=e_ops, options=options,
+                                  only_final_state=only_final_state, progress_bar=progress_bar)
+
+    def propagator(self, c_ops=None, options=None, unitary_mode="batch", parallel=False, progress_bar=None):
+        if all(isinstance(op, SyncOperation) for op in self):
+            return [self.system.I()]
+        return self.compile().propagator(c_ops=c_ops, options=options, unitary_mode=unitary_mode, parallel=parallel)
+
+    def plot_coefficients(self, subplots=True, plot_imag=False, step=False):
+        return self.compile().plot_coefficients(subplots=subplots, plot_imag=plot_imag, step=step)
+
+
+class Sequence(ValidatedList):
+    """PulseSequences, Operations and instantaneous unitaries applied in series."""
+
+    VALID_TYPES = (qt.Qobj, Operation, PulseSequence)
+
+    def __init__(self, system, operations=None):
+        self.system = system
+        self.pulse_sequence = get_sequence(system)
+        self._t = 0
+        super().__init__(operations)
+
+    def _validate(self, item):
+        item = super()._validate(item)
+        if item is self.pulse_sequence:
+            # appending the global sequence: keep a snapshot and start a new one
+            item = copy.deepcopy(item)
+            self.reset_pulse_sequence()
+        elif len(self.pulse_sequence):
+            self.capture()
+        return item
+
+    def reset_pulse_sequence(self):
+        self.pulse_sequence = get_sequence(self.system)
+
+    def capture(self):
+        """Append the global pulse sequence if anything was captured into it."""
+        if len(self.pulse_sequence):
+            self.append(self.pulse_sequence)
+
+    def _segment(self, item):
+        """Compile one pulsed item (PulseSequence or Operation) at the current sequence time."""
+        if isinstance(item, PulseSequence):
+            if item.system != self.system:
+                raise ValueError("All operations must have the same system.")
+            item.t0 = self._t
+            seq = item.compile()
+        else:
+            seq = CompiledPulseSequence(self.system, t0=self._t)
+            seq.add_operation(item)
+        seq.sync()
+        return seq
+
+    def run(self, init_state, e_ops=None, options=None, full_evolution=True, progress_bar=False):
+        self.capture()
+        wrap = tqdm if progress_bar else (lambda it, **kw: it)
+        e_ops = e_ops or []
+        self._t = 0
+        times = [self._t]
+        states = [init_state]
+        for item in wrap(self):
+            item = self._validate(item)
+            if isinstance(item, qt.Qobj):
+                state = states[-1]
+                state = item * state if state.isket else item * state * item.dag()
+                new_states, new_times = [state], [times[-1]]
+            else:
+                seq = self._segment(item)
+                result = seq.run(states[-1], options=options, only_final_state=(not full_evolution))
+                keep = slice(None) if full_evolution else slice(-1, None)
+                new_states, new_times = result.states[keep], list(result.times[keep])
+                self._t = seq._t
+            states.extend(new_states)
+            times.extend(new_times)
+        times = np.array(times)
+        order = np.argsort(times, kind="stable")
+        times = times[order]
+        states = [states[i] for i in order]
+        expect = [qt.expect(op, states) for op in e_ops]
+        return SequenceResult(times=times, states=states, expect=expect,
+                              num_collapse=len(self.system.c_ops(clean=True)))
+
+    def propagator(self, c_ops=None, options=None, unitary_mode="batch", parallel=False, progress_bar=False):
+        self.capture()
+        wrap = tqdm if progress_bar else (lambda it, **kw: it)
+        c_ops = c_ops or []
+        self._t = 0
+        props = [self.system.I()]
+        for item in wrap(self):
+            item = self._validate(item)
+            if isinstance(item, qt.Qobj):
+                props.append(item * props[-1])
+                continue
+            seq = self._segment(item)
+            step = seq.propagator(c_ops=c_ops, options=options, unitary_mode=unitary_mode, parallel=parallel)[-1]
+            self._t = seq._t
+            props.append(step * props[-1])
+        return props
+
+    def plot_coefficients(self, subplots=True, sharex=True, sharey=True):
+        import matplotlib.pyplot as plt
+
+        self._t = 0
+        traces = {}
+        marks = []
+        for item in self:
+            item = self._validate(item)
+            if isinstance(item, qt.Qobj):
+                marks.append(self._t)
+                continue
+            seq = self._segment(item)
+            seg_times = seq.times
+            self._t = seg_times.max()
+            for name, info in seq.channels.items():
+                if "coeffs" not in info:
+                    continue
+                ts, cs = traces.get(name, (np.zeros(0), np.zeros(0)))
+                traces[name] = (np.concatenate([ts, seg_times]), np.concatenate([cs, info["coeffs"]]))
+        names = [n for n in traces if n != "delay"]
+        if not names:
+            raise ValueError("There are no channels with coefficients to plot.")
+        if subplots:
+            fig, axes = plt.subplots(len(names), sharex=sharex, sharey=sharey)
+            axes = np.atleast_1d(axes)
+        else:
+            fig, ax = plt.subplots(1, 1)
+            axes = [ax] * len(names)
+        for name, ax in zip(names, axes):
+            ax.plot(*traces[name], label=name)
+            ax.legend(loc=0)
+            ax.grid(True)
+        for ax in (axes if subplots else axes[:1]):
+            for t in marks:
+                ax.axvline(t, ls="--", lw=1.5, color="k", alpha=0.25)
+        fig.suptitle("Hamiltonian coefficients")
+        axes[-1].set_xlabel("Time")
+        return (fig, axes) if subplots else (fig, axes[0])
+
+
+class SequenceResult(object):
+    """``qutip.solver.Result``-like record for a ``Sequence``."""
+
+    def __init__(self, times=None, states=None, expect=None, num_collapse=0):
+        self.times = np.array([]) if times is None else times
+        self.expect = [] if expect is None else expect
+        self.states = [] if states is None else states
+        self.num_collapse = num_collapse
+        self.solver = "sequencing.Sequence"
+
+    @property
+    def num_expect(self):
+        return len(self.expect)
+
+    def __str__(self):
+        lines = ["SequenceResult", "-" * 14]
+        if self.times is not None and len(self.times) > 0:
+            lines.append(f"Number of times: {len(self.times)}")
+        if self.states is not None and len(self.states) > 0:
+            lines.append("states = True")
+        if self.expect is not None and len(self.expect) > 0:
+            lines.append(f"expect = True, num_expect = {self.num_expect}")
+        lines.append(f"num_collapse = {self.num_collapse}")
+        return "\n".join(lines)
+
+    __repr__ = __str__
+
+
+_global_pulse_sequence = PulseSequence()

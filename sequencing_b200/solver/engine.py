@@ -1,0 +1,284 @@
+"""Device staging + calls into the C ABI.  PyTorch is plumbing only (HBM buffers, streams)."""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import EngineUnavailable, SolveDesc
+
+
+@dataclass
+class BatchProblem:
+    """B trajectories sharing operators (host numpy arrays, complex128 / float64).
+
+    One trajectory = one (sequence x initial state x sweep value): what one ``seq.run()`` of the
+    reference's sweep loops integrates (``calibration.py:120-125``).
+    """
+
+    H0: np.ndarray                      # [N,N] or [B,N,N]
+    Hk: np.ndarray                      # [n_ch,N,N]
+    coeff: np.ndarray                   # [B,n_ch,n_t] or [1,n_ch,n_t] (shared)
+    state0: np.ndarray                  # [B,N,N] or [B,N] (kets)
+    t0: float
+    dt: float
+    out_idx: np.ndarray                 # [n_out] int32
+    Lc: Optional[np.ndarray] = None     # [n_c,N,N]
+    Ltd: Optional[np.ndarray] = None    # [n_ctd,N,N]
+    rate: Optional[np.ndarray] = None   # [B,n_ctd,n_t] or [1,...]
+    E: Optional[np.ndarray] = None      # [n_e,N,N]
+    coeff_scale: Optional[np.ndarray] = None  # [B,n_ch]
+    is_ket: bool = False
+    normalize: bool = True
+    store_states: bool = False
+    expect_complex: bool = False
+    atol: float = 1e-8
+    rtol: float = 1e-6
+    max_step: float = 0.0
+    first_step: float = 0.0
+    min_step: float = 0.0
+    nsteps: int = 1000
+    method: int = _lib.METHOD_AUTO
+
+    @property
+    def N(self):
+        return int(self.Hk.shape[-1]) if self.Hk is not None and self.Hk.size else int(self.H0.shape[-1])
+
+    @property
+    def B(self):
+        return int(self.state0.shape[0])
+
+
+@dataclass
+class BatchOutput:
+    expect: np.ndarray          # [B,n_e,n_out] float64 or complex128
+    final_state: np.ndarray     # [B,N,N] / [B,N]
+    states: Optional[np.ndarray]
+    status: np.ndarray          # [B] int32
+    stats: np.ndarray           # [B,4] int32
+    kernel_ms: float = -1.0
+    launches: int = 0
+    method: str = "auto"
+
+
+def _c128(a, shape_tail):
+    a = np.ascontiguousarray(a, dtype=np.complex128)
+    return a.reshape((-1,) + tuple(shape_tail)) if a.size else a.reshape((0,) + tuple(shape_tail))
+
+
+class Engine:
+    """One C-ABI engine handle bound to one CUDA device (and torch's current stream on it)."""
+
+    _instances = {}
+
+    def __init__(self, device_index: int = 0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise EngineUnavailable("no CUDA device: sequencing_b200 integrates on B200 only (no CPU fallback)")
+        self.lib = _lib.load()
+        self.torch = torch
+        self.device = torch.device("cuda", device_index)
+        with torch.cuda.device(self.device):
+            self.stream = torch.cuda.current_stream(self.device)
+            handle = C.c_void_p()
+            rc = self.lib.seq_engine_create(device_index, C.c_void_p(self.stream.cuda_stream), C.byref(handle))
+        if rc != 0:
+            raise EngineUnavailable(f"seq_engine_create failed with code {rc}")
+        self.handle = handle
+        self.last_kernel_ms = -1.0
+        self.last_launches = 0
+        self.total_launches = 0
+
+    @classmethod
+    def get(cls, device_index: Optional[int] = None) -> "Engine":
+        import torch
+
+        if not torch.cuda.is_available():
+            raise EngineUnavailable("no CUDA device: sequencing_b200 integrates on B200 only (no CPU fallback)")
+        if device_index is None:
+            device_index = torch.cuda.current_device()
+        if device_index not in cls._instances:
+            cls._instances[device_index] = cls(device_index)
+        return cls._instances[device_index]
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.seq_engine_last_error(self.handle)
+            raise RuntimeError(f"seq_engine error {rc}: {msg.decode() if msg else ''}")
+
+    # -- descriptor assembly ---------------------------------------------------------------
+    def _desc(self, bp: BatchProblem, ptr, host: bool) -> SolveDesc:
+        N, B = bp.N, bp.B
+        d = SolveDesc()
+        d.size = C.sizeof(SolveDesc)
+        flags = 0
+        if bp.is_ket:
+            flags |= _lib.FLAG_KET
+            if bp.normalize:
+                flags |= _lib.FLAG_NORMALIZE
+        if bp.store_states:
+            flags |= _lib.FLAG_STORE_STATES
+        if bp.expect_complex:
+            flags |= _lib.FLAG_EXPECT_COMPLEX
+        if host:
+            flags |= _lib.FLAG_HOST_POINTERS
+        d.flags = flags
+        d.N, d.B = N, B
+        d.n_t = int(bp.coeff.shape[-1]) if bp.coeff is not None and bp.coeff.size else int(self._n_t(bp))
+        d.n_ch = int(bp.Hk.shape[0]) if bp.Hk is not None else 0
+        d.n_c = int(bp.Lc.shape[0]) if bp.Lc is not None else 0
+        d.n_ctd = int(bp.Ltd.shape[0]) if bp.Ltd is not None else 0
+        d.n_e = int(bp.E.shape[0]) if bp.E is not None else 0
+        d.n_out = int(len(bp.out_idx))
+        d.nsteps = int(bp.nsteps)
+        d.method = int(bp.method)
+        d.t0, d.dt = float(bp.t0), float(bp.dt)
+        d.atol, d.rtol = float(bp.atol), float(bp.rtol)
+        d.max_step, d.first_step, d.min_step = float(bp.max_step), float(bp.first_step), float(bp.min_step)
+        d.H0 = ptr["H0"]
+        d.H0_batch_stride = N * N if (bp.H0.ndim == 3 and bp.H0.shape[0] == B and B > 1) else 0
+        d.Hk = ptr.get("Hk")
+        d.coeff = ptr.get("coeff")
+        d.coeff_batch_stride = d.n_ch * d.n_t if (d.n_ch and bp.coeff.shape[0] == B and B > 1) else 0
+        d.coeff_scale = ptr.get("coeff_scale")
+        d.Lc = ptr.get("Lc")
+        d.Ltd = ptr.get("Ltd")
+        d.rate = ptr.get("rate")
+        d.rate_batch_stride = d.n_ctd * d.n_t if (d.n_ctd and bp.rate.shape[0] == B and B > 1) else 0
+        d.state0 = ptr["state0"]
+        d.E = ptr.get("E")
+        d.out_idx = ptr["out_idx"]
+        d.expect = ptr.get("expect")
+        d.final_state = ptr["final_state"]
+        d.states = ptr.get("states")
+        d.status = ptr["status"]
+        d.stats = ptr["stats"]
+        return d
+
+    @staticmethod
+    def _n_t(bp):
+        if bp.rate is not None and bp.rate.size:
+            return bp.rate.shape[-1]
+        return int(np.max(bp.out_idx)) + 1
+
+    def _host_arrays(self, bp: BatchProblem):
+        N, B = bp.N, bp.B
+        arrs = {"H0": _c128(bp.H0, (N, N))}
+        if bp.Hk is not None and bp.Hk.shape[0]:
+            arrs["Hk"] = _c128(bp.Hk, (N, N))
+            arrs["coeff"] = np.ascontiguousarray(bp.coeff, dtype=np.float64)
+            if bp.coeff_scale is not None:
+                arrs["coeff_scale"] = np.ascontiguousarray(bp.coeff_scale, dtype=np.float64)
+        if bp.Lc is not None and bp.Lc.shape[0]:
+            arrs["Lc"] = _c128(bp.Lc, (N, N))
+        if bp.Ltd is not None and bp.Ltd.shape[0]:
+            arrs["Ltd"] = _c128(bp.Ltd, (N, N))
+            arrs["rate"] = np.ascontiguousarray(bp.rate, dtype=np.float64)
+        arrs["state0"] = np.ascontiguousarray(bp.state0, dtype=np.complex128)
+        if bp.E is not None and bp.E.shape[0]:
+            arrs["E"] = _c128(bp.E, (N, N))
+        arrs["out_idx"] = np.ascontiguousarray(bp.out_idx, dtype=np.int32)
+        return arrs
+
+    def _out_shapes(self, bp: BatchProblem):
+        N, B = bp.N, bp.B
+        n_e = int(bp.E.shape[0]) if bp.E is not None else 0
+        n_out = len(bp.out_idx)
+        st = (N,) if bp.is_ket else (N, N)
+        shapes = {
+            "expect": ((B, n_e, n_out), np.complex128 if bp.expect_complex else np.float64),
+            "final_state": ((B,) + st, np.complex128),
+            "status": ((B,), np.int32),
+            "stats": ((B, 4), np.int32),
+        }
+        if bp.store_states:
+            shapes["states"] = ((B, n_out) + st, np.complex128)
+        return shapes
+
+    # -- solves ----------------------------------------------------------------------------
+    def solve(self, bp: BatchProblem) -> BatchOutput:
+        """Public host-buffer solve: numpy in, numpy out; H2D/D2H staging via pinned memory."""
+        dev = self.solve_device(self.to_device(bp), bp)
+        out = {k: v.cpu().numpy() for k, v in dev["out"].items()}
+        return self._finish(bp, out)
+
+    def to_device(self, bp: BatchProblem):
+        torch = self.torch
+        tens = {}
+        for name, arr in self._host_arrays(bp).items():
+            t = torch.from_numpy(arr)
+            tens[name] = t.pin_memory().to(self.device, non_blocking=True) if t.numel() else t.to(self.device)
+        return tens
+
+    def solve_device(self, tens, bp: BatchProblem):
+        """Inputs already resident in HBM (torch tensors); outputs stay on the device."""
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            outs = {}
+            for name, (shape, dt) in self._out_shapes(bp).items():
+                tdt = {np.float64: torch.float64, np.complex128: torch.complex128, np.int32: torch.int32}[dt]
+                outs[name] = torch.empty(shape, dtype=tdt, device=self.device)
+            ptr = {k: (v.data_ptr() if v.numel() else None) for k, v in tens.items()}
+            ptr.update({k: (v.data_ptr() if v.numel() else None) for k, v in outs.items()})
+            desc = self._desc(bp, ptr, host=False)
+            self._check(self.lib.seq_engine_solve(self.handle, C.byref(desc)))
+            self.last_launches = self.lib.seq_engine_last_launch_count(self.handle)
+            self.total_launches += self.last_launches
+            self._last_method = self.lib.seq_engine_select_method(self.handle, C.byref(desc))
+        return {"out": outs, "in": tens}
+
+    def solve_host_abi(self, bp: BatchProblem) -> BatchOutput:
+        """The reference-facing C-ABI call on HOST buffers (SEQ_FLAG_HOST_POINTERS): the engine
+        itself stages host->device, integrates, and copies results back before returning."""
+        arrs = self._host_arrays(bp)
+        outs = {name: np.empty(shape, dtype=dt) for name, (shape, dt) in self._out_shapes(bp).items()}
+        ptr = {k: (v.ctypes.data if v.size else None) for k, v in arrs.items()}
+        ptr.update({k: (v.ctypes.data if v.size else None) for k, v in outs.items()})
+        desc = self._desc(bp, ptr, host=True)
+        self._check(self.lib.seq_engine_solve(self.handle, C.byref(desc)))
+        self.last_launches = self.lib.seq_engine_last_launch_count(self.handle)
+        self.total_launches += self.last_launches
+        self._last_method = self.lib.seq_engine_select_method(self.handle, C.byref(desc))
+        return self._finish(bp, outs)
+
+    def _finish(self, bp, out) -> BatchOutput:
+        self.last_kernel_ms = float(self.lib.seq_engine_last_kernel_ms(self.handle))
+        return BatchOutput(
+            expect=out["expect"], final_state=out["final_state"], states=out.get("states"),
+            status=out["status"], stats=out["stats"], kernel_ms=self.last_kernel_ms,
+            launches=self.last_launches, method=_lib.METHOD_NAMES.get(getattr(self, "_last_method", 0), "?"),
+        )
+
+    def kernel_ms(self) -> float:
+        return float(self.lib.seq_engine_last_kernel_ms(self.handle))
+
+    # -- auxiliary entry points --------------------------------------------------------------
+    def spline_prep(self, y: np.ndarray, dt: float) -> np.ndarray:
+        torch = self.torch
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        n_t = y.shape[-1]
+        ty = torch.from_numpy(y.reshape(-1, n_t)).to(self.device)
+        tm = torch.empty_like(ty)
+        self._check(self.lib.seq_engine_spline_prep(self.handle, ty.data_ptr(), tm.data_ptr(), ty.shape[0], n_t, float(dt)))
+        return tm.cpu().numpy().reshape(y.shape)
+
+    def apply_unitary(self, U: np.ndarray, states: np.ndarray, is_ket: bool) -> np.ndarray:
+        torch = self.torch
+        N = U.shape[0]
+        tu = torch.from_numpy(np.ascontiguousarray(U, dtype=np.complex128)).to(self.device)
+        ts = torch.from_numpy(np.ascontiguousarray(states, dtype=np.complex128)).to(self.device)
+        B = ts.shape[0]
+        self._check(self.lib.seq_engine_apply_unitary(self.handle, tu.data_ptr(), ts.data_ptr(), N, B, int(is_ket)))
+        return ts.cpu().numpy()
+
+    def expect(self, E: np.ndarray, states: np.ndarray, is_ket: bool) -> np.ndarray:
+        torch = self.torch
+        N = E.shape[-1]
+        te = torch.from_numpy(_c128(E, (N, N))).to(self.device)
+        ts = torch.from_numpy(np.ascontiguousarray(states, dtype=np.complex128)).to(self.device)
+        B, n_e = ts.shape[0], te.shape[0]
+        out = torch.empty((B, n_e), dtype=torch.complex128, device=self.device)
+        self._check(self.lib.seq_engine_expect(self.handle, te.data_ptr(), ts.data_ptr(), out.data_ptr(), N, B, n_e, int(is_ket)))
+        return out.cpu().numpy()

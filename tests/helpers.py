@@ -1,0 +1,121 @@
+"""Shared test helpers: oracle adapters and canonical synthetic problems."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import qutip4_oracle as orc  # noqa: E402
+from sequencing_b200.solver.engine import BatchOutput, BatchProblem  # noqa: E402
+
+
+def oracle_options(bp: BatchProblem, **over):
+    kw = dict(atol=bp.atol, rtol=bp.rtol, nsteps=bp.nsteps, first_step=bp.first_step, min_step=bp.min_step,
+              max_step=bp.max_step, store_states=bp.store_states, normalize_output=bp.normalize)
+    kw.update(over)
+    return orc.Options(**kw)
+
+
+def oracle_inputs(bp: BatchProblem, b: int):
+    """Trajectory ``b`` of a BatchProblem in the oracle's list format."""
+    n_t = bp.coeff.shape[-1] if bp.coeff is not None and bp.coeff.size else (bp.rate.shape[-1] if bp.rate is not None and bp.rate.size else int(bp.out_idx.max()) + 1)
+    grid = bp.t0 + bp.dt * np.arange(n_t)
+    H0 = bp.H0[b] if bp.H0.ndim == 3 else bp.H0
+    H = [H0]
+    n_ch = bp.Hk.shape[0] if bp.Hk is not None else 0
+    for k in range(n_ch):
+        c = bp.coeff[b if bp.coeff.shape[0] > 1 else 0, k]
+        if bp.coeff_scale is not None:
+            c = c * bp.coeff_scale[b, k]
+        H.append((bp.Hk[k], c))
+    c_ops = [L for L in (bp.Lc if bp.Lc is not None else [])]
+    n_ctd = bp.Ltd.shape[0] if bp.Ltd is not None else 0
+    for j in range(n_ctd):
+        r = bp.rate[b if bp.rate.shape[0] > 1 else 0, j]
+        c_ops.append((bp.Ltd[j], np.sqrt(r)))
+    e_ops = [E for E in (bp.E if bp.E is not None else [])]
+    tlist = grid[bp.out_idx]
+    return H, bp.state0[b], tlist, c_ops, e_ops, grid
+
+
+def oracle_solve(bp: BatchProblem, b: int, truth=False, **opt_over):
+    H, s0, tlist, c_ops, e_ops, grid = oracle_inputs(bp, b)
+    if truth:
+        return orc.truth_solve(H, s0, tlist, c_ops, e_ops, coeff_tlist=grid)
+    return orc.mesolve(H, s0, tlist, c_ops, e_ops, oracle_options(bp, **opt_over), coeff_tlist=grid)
+
+
+class OracleEngine:
+    """Engine look-alike that integrates each trajectory with the CPU oracle (tests only)."""
+
+    def __init__(self):
+        self.calls = 0
+        self.batch_sizes = []
+
+    def solve(self, bp: BatchProblem) -> BatchOutput:
+        self.calls += 1
+        B, N = bp.B, bp.N
+        self.batch_sizes.append(B)
+        n_e = bp.E.shape[0] if bp.E is not None else 0
+        n_out = len(bp.out_idx)
+        st = (N,) if bp.is_ket else (N, N)
+        expect = np.zeros((B, n_e, n_out), dtype=complex if bp.expect_complex else float)
+        final = np.zeros((B,) + st, dtype=complex)
+        states = np.zeros((B, n_out) + st, dtype=complex) if bp.store_states else None
+        for b in range(B):
+            r = oracle_solve(bp, b, store_states=True)
+            for m in range(n_e):
+                expect[b, m] = r.expect[m] if bp.expect_complex else np.real(r.expect[m])
+            final[b] = r.final_state.reshape(st)
+            if states is not None:
+                states[b] = np.stack([s.reshape(st) for s in r.states])
+        return BatchOutput(expect=expect, final_state=final, states=states, status=np.zeros(B, np.int32),
+                           stats=np.zeros((B, 4), np.int32), method="oracle")
+
+    solve_host_abi = solve
+
+
+def trace_distance(a, b):
+    return orc.trace_distance(a, b)
+
+
+# ---- canonical synthetic problems ----------------------------------------------------------
+def random_problem(N, B, n_t, n_ch=2, n_c=2, n_ctd=0, n_e=2, seed=0, ket=False, dt=1.0, hscale=0.5, **kw):
+    """Seeded random dense problem (Hermitian H terms, random collapse ops, smooth coefficients)."""
+    rng = np.random.default_rng(seed)
+
+    def herm():
+        a = rng.normal(size=(N, N)) + 1j * rng.normal(size=(N, N))
+        return hscale * (a + a.conj().T) / (2 * np.sqrt(N))
+
+    H0 = herm()
+    Hk = np.stack([herm() for _ in range(n_ch)]) if n_ch else np.zeros((0, N, N), complex)
+    ts = np.arange(n_t) * dt
+    coeff = np.zeros((B, n_ch, n_t))
+    for b in range(B):
+        for k in range(n_ch):
+            f = rng.uniform(0.02, 0.08) / dt
+            coeff[b, k] = rng.uniform(0.5, 1.5) * np.sin(2 * np.pi * f * ts + rng.uniform(0, 6.28)) * np.exp(-((ts - ts.mean()) / (0.35 * max(ts[-1], dt))) ** 2)
+    Lc = np.stack([0.15 * (rng.normal(size=(N, N)) + 1j * rng.normal(size=(N, N))) / np.sqrt(N) for _ in range(n_c)]) if n_c else np.zeros((0, N, N), complex)
+    Ltd = np.stack([0.15 * (rng.normal(size=(N, N)) + 1j * rng.normal(size=(N, N))) / np.sqrt(N) for _ in range(n_ctd)]) if n_ctd else np.zeros((0, N, N), complex)
+    rate = np.zeros((B, n_ctd, n_t))
+    for b in range(B):
+        for j in range(n_ctd):
+            rate[b, j] = rng.uniform(0.2, 1.0) * (1 + np.cos(2 * np.pi * ts / max(ts[-1], dt) + rng.uniform(0, 6.28))) / 2
+    if ket:
+        psi = rng.normal(size=(B, N)) + 1j * rng.normal(size=(B, N))
+        state0 = psi / np.linalg.norm(psi, axis=1, keepdims=True)
+    else:
+        state0 = np.zeros((B, N, N), complex)
+        for b in range(B):
+            a = rng.normal(size=(N, N)) + 1j * rng.normal(size=(N, N))
+            rho = a @ a.conj().T
+            state0[b] = rho / np.trace(rho).real
+    E = np.stack([herm() for _ in range(n_e)]) if n_e else np.zeros((0, N, N), complex)
+    args = dict(H0=H0, Hk=Hk, coeff=coeff, state0=state0, t0=0.0, dt=dt, out_idx=np.arange(n_t, dtype=np.int32),
+                Lc=Lc, Ltd=Ltd, rate=rate, E=E, is_ket=ket, max_step=dt)
+    args.update(kw)
+    return BatchProblem(**args)
