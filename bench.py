@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched Lindblad integration (``CompiledPulseSequence.run`` ->
+``mesolve``) on the configuration BASELINE.json's metric is quoted on.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3]
+
+One "step" = one pass of the engine over one batch of synthetic sweep trajectories
+(C2: transmon(3) (x) cavity(15), number-selective pi pulse, 32x32 amplitude x detuning sweep:
+N=45, n_t=1000, n_ch=2, n_c=4, B=1024 per GPU).  With N GPUs every rank integrates its own
+1024-trajectory shard (independent units -> weak scaling, no data-path collective) and the
+expectation traces + final states are gathered with NCCL inside the timed step.
+
+Prints ONE JSON line (rank 0).  ``value`` = trajectories/s with inputs resident in HBM;
+``e2e`` = the same through the C-ABI call on HOST (pinned) buffers, H2D/D2H inside the timed
+region; ``roofline`` = algorithmic FP64 flops of the integration kernel / its CUDA-event
+duration against the measured DMMA peak; ``cpu_baseline`` = the CPU oracle (QuTiP-4.x
+restatement: sparse Liouvillian + ZVODE) timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "batched mesolve trajectories/sec at Hilbert dim N; % of FP64-DMMA/HBM roofline"
+UNIT = "trajectories/s"
+FP64_DMMA_PEAK_TFLOPS = 37.0  # measured on this pool's B200 by tools/fp64_peak.cu (profiles/r01_fp64_peak.json)
+
+
+def build_workload(name):
+    from sequencing_b200 import workloads as w
+
+    if name == "c2":
+        bp = w.c2_selective(32, 32)
+        desc = "C2 transmon(3)x cavity(15) selective pi pulse, 32x32 amp x detuning sweep"
+    elif name == "c1":
+        bp = w.c1_rabi(65536)
+        desc = "C1 transmon(3) Rabi amplitude sweep, T1/T2 collapse ops"
+    elif name == "c3":
+        bp = w.c3_drag(4096)
+        desc = "C3 transmon(4) DRAG sweep x 6 cardinal states"
+    elif name == "c2small":
+        bp = w.c2_selective(4, 4, sigma=25)
+        desc = "C2-small (smoke) transmon(3)x cavity(15), 4x4 sweep, n_t=100"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return bp, desc
+
+
+def shape_of(bp):
+    return dict(N=bp.N, B=bp.B, n_t=int(bp.coeff.shape[-1]), n_ch=int(bp.Hk.shape[0]),
+                n_c=int(bp.Lc.shape[0] + bp.Ltd.shape[0]), n_e=int(bp.E.shape[0]))
+
+
+def algorithmic(bp, stats):
+    """F_rhs = 8 N^3 (1 + 2 n_c) per RHS evaluation; bytes per trajectory =
+    8 n_ch n_t + 16 N^2 + 8 n_e n_t + 16 N^2."""
+    s = shape_of(bp)
+    f_rhs = 8.0 * s["N"] ** 3 * (1 + 2 * s["n_c"])
+    rhs_evals = float(np.sum(stats[:, 2]))
+    bytes_traj = 8.0 * s["n_ch"] * s["n_t"] + 32.0 * s["N"] ** 2 + 8.0 * s["n_e"] * s["n_t"]
+    return f_rhs * rhs_evals, bytes_traj * s["B"], f_rhs
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if x > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline leg and --impl reference)
+# ------------------------------------------------------------------------------------------
+_ORACLE_BP = None
+
+
+def _oracle_init(workload):
+    global _ORACLE_BP
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    os.environ.setdefault("MKL_NUM_THREADS", "1")
+    _ORACLE_BP, _ = build_workload(workload)
+
+
+def _oracle_one(b):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import oracle_solve
+
+    r = oracle_solve(_ORACLE_BP, int(b) % _ORACLE_BP.B)
+    return float(np.real(r.expect[0][-1])) if r.expect else 0.0
+
+
+class OraclePool:
+    """The reference's CPU path (restated: oracle/qutip4_oracle.py) over all host cores,
+    one trajectory per task (= qutip.parallel_map over sweep points)."""
+
+    def __init__(self, workload, cores=None):
+        import multiprocessing as mp
+
+        self.cores = cores or os.cpu_count() or 1
+        ctx = mp.get_context("spawn")
+        self.pool = ctx.Pool(self.cores, initializer=_oracle_init, initargs=(workload,))
+
+    def run(self, n_traj, offset=0):
+        t = time.perf_counter()
+        self.pool.map(_oracle_one, range(offset, offset + n_traj), chunksize=1)
+        return time.perf_counter() - t
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    bp, desc = build_workload(args.workload)
+    pool = OraclePool(args.workload)
+    sample = max(pool.cores * 2, 16)
+    for w in range(args.warmup):
+        pool.run(min(pool.cores, sample))
+    times = [pool.run(sample, offset=k * sample) for k in range(args.steps)]
+    pool.close()
+    total = sum(times)
+    value = sample * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
+        "config": {"workload": desc, **shape_of(bp), "sample_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": pool.cores, "kind": "port",
+                         "sample": f"{sample} trajectories/step of the same workload, one per task over {pool.cores} processes "
+                                   "(QuTiP-4.x restatement: CSR Liouvillian SpMV + scipy ZVODE-Adams, atol 1e-8 rtol 1e-6 max_step dt)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from sequencing_b200.solver import Engine
+
+    bp, desc = build_workload(args.workload)   # every rank integrates its own shard of this size (weak scaling)
+    if world > 1:
+        # rank-dependent sweep values: scale the amplitudes a little so shards are distinct units
+        bp.coeff = bp.coeff * (1.0 + 1e-3 * rank)
+    eng = Engine.get(local)
+    dev = torch.device("cuda", local)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def gather(outs):
+        if world == 1:
+            return
+        for key in ("expect", "final_state"):
+            t = outs[key]
+            buf = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(buf, t)
+
+    # ---- device-resident value -----------------------------------------------------------
+    tens = eng.to_device(bp)
+    torch.cuda.synchronize()
+    kernel_ms, step_ms, launches = [], [], 0
+    for w in range(args.warmup):
+        res = eng.solve_device(tens, bp)
+        gather(res["out"])
+        torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush_buf.fill_(k)            # L2 flush between timed iterations (outside the events)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = eng.solve_device(tens, bp)
+        gather(res["out"])
+        e1.record()
+        torch.cuda.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        kernel_ms.append(eng.kernel_ms())
+        launches += eng.last_launches
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    stats = res["out"]["stats"].cpu().numpy()
+    status = res["out"]["status"].cpu().numpy()
+    assert np.all(status == 0), "integration failed for some trajectories"
+    t_dev = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    total_ms = float(t_dev.item())
+    value = bp.B * world * args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end through the C ABI on pinned host buffers ---------------------------------
+    host = eng._host_arrays(bp)
+    pinned = {}
+    for name, arr in host.items():
+        t = torch.from_numpy(arr).pin_memory() if arr.size else torch.from_numpy(arr)
+        pinned[name] = t
+    import copy
+    bp_h = copy.copy(bp)
+    for name in ("H0", "Hk", "coeff", "Lc", "Ltd", "rate", "state0", "E", "out_idx"):
+        if name in pinned:
+            setattr(bp_h, name, pinned[name].numpy())
+    h2d = sum(int(v.numel() * v.element_size()) for v in pinned.values())
+    eng.solve_host_abi(bp_h)  # warm the staging buffers
+    barrier()
+    e2e_t = []
+    for k in range(max(1, min(args.steps, 3))):
+        flush_buf.fill_(k)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out_h = eng.solve_host_abi(bp_h)   # returns after D2H + stream sync
+        e2e_t.append(time.perf_counter() - t0)
+        launches += eng.last_launches
+    d2h = int(out_h.expect.nbytes + out_h.final_state.nbytes + out_h.status.nbytes + out_h.stats.nbytes)
+    t_e2e = torch.tensor([sum(e2e_t)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = bp.B * world * len(e2e_t) / float(t_e2e.item())
+
+    if rank == 0:
+        flops, bytes_alg, f_rhs = algorithmic(bp, stats)
+        k_ms = float(np.mean(kernel_ms))
+        achieved = flops / (k_ms * 1e-3) / 1e12
+        s = shape_of(bp)
+        roof = {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                "frac": achieved / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
+                "kernel": f"solve_{out_h.method}_kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (total_ms / args.steps),
+                "flops_per_rhs": f_rhs, "rhs_evals_per_launch": float(np.sum(stats[:, 2])),
+                "peak_source": "FP64 DMMA.8x8x4 issue-rate microbenchmark tools/fp64_peak.cu on this pool's B200 "
+                               "(MEASURED_PEAKS.json has no FP64 entry): 36.99 TFLOP/s sustained",
+                "hbm_algorithmic_GBps": bytes_alg / (k_ms * 1e-3) / 1e9}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            pool = OraclePool(args.workload)
+            n = max(pool.cores * 4, 32)
+            pool.run(pool.cores)
+            t_cpu = pool.run(n)
+            pool.close()
+            cpu = {"value": n / t_cpu, "unit": UNIT, "cores": pool.cores, "kind": "port",
+                   "sample": f"{n} of the {bp.B} trajectories, one per task over {pool.cores} processes "
+                             "(oracle/qutip4_oracle.py: CSR Liouvillian + scipy ZVODE-Adams, reference options)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "c128 (f64)", "data": "synthetic",
+            "config": {"workload": desc, **s, "B_per_gpu": bp.B, "atol": bp.atol, "rtol": bp.rtol, "max_step": bp.max_step,
+                       "parallelism": f"batch-sharded x{world}", "l2": "256 MiB L2 flush between timed steps; per-step scratch 300 MB > L2",
+                       "method": out_h.method, "steps_accepted_mean": float(stats[:, 0].mean()), "steps_rejected_mean": float(stats[:, 1].mean())},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "wall_s_timed_region": wall,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

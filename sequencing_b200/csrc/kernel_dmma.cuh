@@ -1,8 +1,535 @@
-// placeholder until the DMMA kernel lands
+// SEQ_METHOD_DMMA: batched Lindblad integrator on the FP64 tensor cores (DMMA.8x8x4), rho resident.
+//
+// One CTA integrates one trajectory over the whole time span (Dormand-Prince 5(4), FSAL,
+// CTA-uniform adaptive step control, fused spline evaluation and expectation reduction).
+//
+// Data layout
+//  * N is padded to NP = 8*NT.  Matrices in shared memory are PLANAR (re plane, im plane), row
+//    major with leading dimension LD = NP + 4 doubles: LD = 4 (mod 8) makes the A-fragment loads
+//    (8 rows x 4 cols) and the B-fragment loads (4 rows x 8 cols) of mma.m8n8k4 bank-conflict free.
+//  * shared memory holds four such matrices: Y (the RK stage state), T (scratch: -iGY, then L_l Y),
+//    X0 (G(t), later odd L_l) and X1 (even L_l).  L_l are streamed from L2 with cp.async, double
+//    buffered behind the products of the previous operator.
+//  * each warp owns a 1 x TW strip of 8x8 complex output tiles; its accumulators (K: the RHS being
+//    assembled, W: the running product) stay in registers for the whole RHS evaluation.
+//  * the RK stage derivatives k1..k7, y and y_new are THREAD-PRIVATE streams in global memory,
+//    stored in accumulator-fragment order ([slot][thread] double2, fully coalesced, L2 resident):
+//    a thread only ever re-reads what it wrote, so the stage combinations need no barrier.
+//
+// RHS (rho Hermitian):  A = -i G rho,  G = H(t) - (i/2) sum_l r_l L_l^dag L_l
+//                       rho' = A + A^dag + sum_l r_l L_l rho L_l^dag
+// = (1 + 2 n_l) complex NP^3 products, each 4 real DMMA chains.
 #pragma once
 #include "common.cuh"
+
 namespace seq {
-static inline bool dmma_supported(int N, int max_smem) { (void)N; (void)max_smem; return false; }
-static inline size_t dmma_ws_elems(int N) { (void)N; return 0; }
-static inline int launch_dmma(const SolveParams& p, int sms, int max_smem, cudaStream_t s) { (void)p; (void)sms; (void)max_smem; (void)s; return SEQ_ERR_UNSUPPORTED; }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+__device__ __forceinline__ double dneg(double x) {
+  return __longlong_as_double(__double_as_longlong(x) ^ 0x8000000000000000ull);  // LOP3, keeps the FP64 pipe free
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <int NT> struct DmmaCfg {
+  static constexpr int NP = 8 * NT;
+  static constexpr int LD = NP + 4;
+  static constexpr int TW = (NT % 3 == 0) ? 3 : ((NT % 2 == 0) ? 2 : (NT == 5 ? 5 : 1));
+  static constexpr int WPR = NT / TW;            // warps per tile row
+  static constexpr int NW = NT * WPR;            // warps per CTA
+  static constexpr int NTHREADS = NW * 32;
+  static constexpr int PLANE = NP * LD;          // doubles per plane
+  static constexpr int MAT = 2 * PLANE;          // doubles per planar matrix
+  static constexpr int SLOTS = TW * 2;           // double2 per thread per state vector
+  static constexpr size_t SMEM = (size_t)(4 * MAT + 34 + 64) * sizeof(double);
+};
+
+// ---- prep: pack interleaved complex [N,N] into planar padded [2][NP][LD] (zero padded)
+__global__ void dmma_pack_planar_kernel(const cplx* __restrict__ src, double* __restrict__ dst, int N, int NP, int LD) {
+  int m = blockIdx.y;
+  const cplx* s = src + (long long)m * N * N;
+  double* d = dst + (long long)m * 2 * NP * LD;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < NP * LD; idx += gridDim.x * blockDim.x) {
+    int i = idx / LD, j = idx - i * LD;
+    cplx v = cmake(0, 0);
+    if (i < N && j < N) v = s[i * N + j];
+    d[idx] = v.x;
+    d[NP * LD + idx] = v.y;
+  }
+}
+
+// ---- prep: E^T in accumulator-fragment order: Ef[e][slot][tid] = (E[c0][r], E[c0+1][r]) for the
+// element (r, c0..c0+1) that thread `tid` owns in slot (t, plane)
+template <int NT>
+__global__ void dmma_pack_efrag_kernel(const cplx* __restrict__ E, double2* __restrict__ Ef, int N) {
+  typedef DmmaCfg<NT> C;
+  int e = blockIdx.x;
+  int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+  int tr = w / C::WPR, tc0 = (w % C::WPR) * C::TW;
+  for (int t = 0; t < C::TW; t++) {
+    int r = 8 * tr + g, c0 = 8 * (tc0 + t) + 2 * tg;
+    cplx a = cmake(0, 0), b = cmake(0, 0);
+    if (r < N && c0 < N) a = E[(long long)e * N * N + c0 * N + r];
+    if (r < N && c0 + 1 < N) b = E[(long long)e * N * N + (c0 + 1) * N + r];
+    Ef[((long long)e * C::SLOTS + t * 2 + 0) * C::NTHREADS + tid] = make_double2(a.x, b.x);
+    Ef[((long long)e * C::SLOTS + t * 2 + 1) * C::NTHREADS + tid] = make_double2(a.y, b.y);
+  }
+}
+
+struct DmmaExtra {
+  const double* G0p;   // planar padded G0 (shared)
+  const double* Gkp;   // [n_g] planar padded
+  const double* Lp;    // [n_l] planar padded
+  const double2* Ef;   // fragment-ordered E^T
+};
+
+template <int NT>
+struct DmmaState {
+  typedef DmmaCfg<NT> C;
+  double* Y; double* T; double* X0; double* X1; double* red; double* cval;
+  int tid, w, lane, g, tg, tr, tc0;
+};
+
+// acc += A(rows of tile-row tr) * B(cols of this warp's strip), A and B planar in shared memory
+template <int NT, bool BCONJT>
+__device__ __forceinline__ void warp_gemm(double (&acc)[DmmaCfg<NT>::TW][2][2], const double* __restrict__ A,
+                                          const double* __restrict__ Bm, int tr, int tc0, int g, int tg) {
+  typedef DmmaCfg<NT> C;
+  const double* Are = A + (8 * tr + g) * C::LD + tg;
+  const double* Aim = Are + C::PLANE;
+#pragma unroll
+  for (int k0 = 0; k0 < C::NP; k0 += 4) {
+    double ar = Are[k0], ai = Aim[k0];
+    double nar = dneg(ar), nai = dneg(ai);
+#pragma unroll
+    for (int t = 0; t < C::TW; t++) {
+      int n0 = 8 * (tc0 + t);
+      if (!BCONJT) {
+        const double* bp = Bm + (k0 + tg) * C::LD + n0 + g;
+        double br = bp[0], bi = bp[C::PLANE];
+        dmma884(acc[t][0][0], acc[t][0][1], ar, br);
+        dmma884(acc[t][0][0], acc[t][0][1], nai, bi);
+        dmma884(acc[t][1][0], acc[t][1][1], ar, bi);
+        dmma884(acc[t][1][0], acc[t][1][1], ai, br);
+      } else {
+        // B(k,n) = conj(L[n][k])
+        const double* lp = Bm + (n0 + g) * C::LD + k0 + tg;
+        double lr = lp[0], li = lp[C::PLANE];
+        dmma884(acc[t][0][0], acc[t][0][1], ar, lr);
+        dmma884(acc[t][0][0], acc[t][0][1], ai, li);
+        dmma884(acc[t][1][0], acc[t][1][1], ai, lr);
+        dmma884(acc[t][1][0], acc[t][1][1], nar, li);
+      }
+    }
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ void prefetch_L(double* dst, const double* __restrict__ src, int tid) {
+  typedef DmmaCfg<NT> C;
+  // planar padded matrix is a flat copy: MAT doubles = MAT/2 16-byte chunks
+  for (int c = tid; c < C::MAT / 2; c += C::NTHREADS) cp_async16(dst + 2 * c, src + 2 * c);
+  cp_async_commit();
+}
+
+// K (registers) <- RHS(t, Y in smem).  On exit no thread is still reading Y/T/X buffers is NOT
+// guaranteed: callers must barrier before overwriting Y.
+template <int NT>
+__device__ __forceinline__ void dmma_rhs(const SolveParams& p, const DmmaExtra& x, DmmaState<NT>& s, double t,
+                                         const double2* __restrict__ tabc, const double2* __restrict__ tabr,
+                                         const double* __restrict__ cscale, double (&K)[DmmaCfg<NT>::TW][2][2]) {
+  typedef DmmaCfg<NT> C;
+  const int nL = p.n_c + p.n_ctd;
+  // stream the first collapse operator behind the G products
+  if (nL > 0) prefetch_L<NT>(s.X1, x.Lp, s.tid);
+  if (s.tid < p.n_g) {
+    int m = s.tid;
+    double v;
+    if (m < p.n_ch) {
+      v = spline_eval(tabc + (long long)m * p.n_t, p.n_t, p.t0, p.dt, t);
+      if (cscale) v *= cscale[m];
+    } else {
+      v = spline_eval(tabr + (long long)(m - p.n_ch) * p.n_t, p.n_t, p.t0, p.dt, t);
+    }
+    s.cval[m] = v;
+  }
+  __syncthreads();  // cval visible; also: every warp finished the previous RHS (X0/T free), Y written
+  // G(t) = G0 + sum_m c_m Gk[m]  -> X0 (flat elementwise over the padded planar image)
+  {
+    const double2* g0 = reinterpret_cast<const double2*>(x.G0p);
+    double2* dst = reinterpret_cast<double2*>(s.X0);
+    for (int c = s.tid; c < C::MAT / 2; c += C::NTHREADS) {
+      double2 v = g0[c];
+      for (int m = 0; m < p.n_g; m++) {
+        double2 a = reinterpret_cast<const double2*>(x.Gkp + (long long)m * C::MAT)[c];
+        double cv = s.cval[m];
+        v.x = fma(cv, a.x, v.x);
+        v.y = fma(cv, a.y, v.y);
+      }
+      dst[c] = v;
+    }
+  }
+  __syncthreads();
+  double W[C::TW][2][2];
+#pragma unroll
+  for (int t = 0; t < C::TW; t++) { W[t][0][0] = W[t][0][1] = W[t][1][0] = W[t][1][1] = 0.0; }
+  warp_gemm<NT, false>(W, s.X0, s.Y, s.tr, s.tc0, s.g, s.tg);
+  // A = -i W  -> T (planar): A_re = W_im, A_im = -W_re ; keep own A in K
+#pragma unroll
+  for (int t = 0; t < C::TW; t++) {
+    int r = 8 * s.tr + s.g, c0 = 8 * (s.tc0 + t) + 2 * s.tg;
+    double are0 = W[t][1][0], are1 = W[t][1][1], aim0 = -W[t][0][0], aim1 = -W[t][0][1];
+    *reinterpret_cast<double2*>(s.T + r * C::LD + c0) = make_double2(are0, are1);
+    *reinterpret_cast<double2*>(s.T + C::PLANE + r * C::LD + c0) = make_double2(aim0, aim1);
+    K[t][0][0] = are0; K[t][0][1] = are1; K[t][1][0] = aim0; K[t][1][1] = aim1;
+  }
+  __syncthreads();  // A complete; X0 (G) no longer needed
+  // K += A^dag : K_re(i,j) += A_re(j,i) ; K_im(i,j) -= A_im(j,i)
+#pragma unroll
+  for (int t = 0; t < C::TW; t++) {
+    int r = 8 * s.tr + s.g, c0 = 8 * (s.tc0 + t) + 2 * s.tg;
+    K[t][0][0] += s.T[(c0)*C::LD + r];
+    K[t][0][1] += s.T[(c0 + 1) * C::LD + r];
+    K[t][1][0] -= s.T[C::PLANE + (c0)*C::LD + r];
+    K[t][1][1] -= s.T[C::PLANE + (c0 + 1) * C::LD + r];
+  }
+  for (int l = 0; l < nL; l++) {
+    double* Lb = (l & 1) ? s.X0 : s.X1;
+    cp_async_wait<0>();
+    __syncthreads();  // L_l landed for everyone; all reads of T and of the other X buffer are finished
+    if (l + 1 < nL) prefetch_L<NT>((l & 1) ? s.X1 : s.X0, x.Lp + (long long)(l + 1) * C::MAT, s.tid);
+#pragma unroll
+    for (int t = 0; t < C::TW; t++) { W[t][0][0] = W[t][0][1] = W[t][1][0] = W[t][1][1] = 0.0; }
+    warp_gemm<NT, false>(W, Lb, s.Y, s.tr, s.tc0, s.g, s.tg);
+    const double r_l = (l < p.n_c) ? 1.0 : s.cval[p.n_ch + (l - p.n_c)];
+#pragma unroll
+    for (int t = 0; t < C::TW; t++) {
+      int r = 8 * s.tr + s.g, c0 = 8 * (s.tc0 + t) + 2 * s.tg;
+      *reinterpret_cast<double2*>(s.T + r * C::LD + c0) = make_double2(r_l * W[t][0][0], r_l * W[t][0][1]);
+      *reinterpret_cast<double2*>(s.T + C::PLANE + r * C::LD + c0) = make_double2(r_l * W[t][1][0], r_l * W[t][1][1]);
+    }
+    __syncthreads();  // T = r_l L_l Y complete
+    warp_gemm<NT, true>(K, s.T, Lb, s.tr, s.tc0, s.g, s.tg);
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(DmmaCfg<NT>::NTHREADS, 1)
+solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__ DmmaExtra x) {
+  typedef DmmaCfg<NT> C;
+  extern __shared__ __align__(16) double smem[];
+  DmmaState<NT> s;
+  s.Y = smem;
+  s.T = smem + C::MAT;
+  s.X0 = smem + 2 * C::MAT;
+  s.X1 = smem + 3 * C::MAT;
+  s.red = smem + 4 * C::MAT;
+  s.cval = s.red + 34;
+  s.tid = threadIdx.x; s.w = s.tid >> 5; s.lane = s.tid & 31; s.g = s.lane >> 2; s.tg = s.lane & 3;
+  s.tr = s.w / C::WPR; s.tc0 = (s.w % C::WPR) * C::TW;
+  const int b = blockIdx.x, N = p.N, tid = s.tid;
+  const double2* tabc = p.tab + (long long)b * p.tab_bstride_c;
+  const double2* tabr = p.tab_rate + (long long)b * p.tab_bstride_r;
+  const double* cscale = p.coeff_scale ? p.coeff_scale + (long long)b * p.n_ch : nullptr;
+
+  // thread-private streams: y, yn, k1..k7 ; each SLOTS double2 per thread
+  double2* ws = reinterpret_cast<double2*>(p.ws + (long long)b * p.ws_stride) + tid;
+  constexpr int STREAM = C::SLOTS * C::NTHREADS;
+  double2* sy = ws; double2* syn = ws + STREAM;
+  double2* k1 = ws + 2 * STREAM; double2* k2 = ws + 3 * STREAM; double2* k3 = ws + 4 * STREAM;
+  double2* k4 = ws + 5 * STREAM; double2* k5 = ws + 6 * STREAM; double2* k6 = ws + 7 * STREAM; double2* k7 = ws + 8 * STREAM;
+#define SLOT(ptr, t, pl) (ptr)[((t)*2 + (pl)) * C::NTHREADS]
+
+  // zero the Y buffer once (padding must stay zero), then load rho0 into registers/streams
+  for (int c = tid; c < C::MAT; c += C::NTHREADS) s.Y[c] = 0.0;
+  double yv[C::TW][2][2];
+  {
+    const cplx* y0 = p.state0 + (long long)b * N * N;
+#pragma unroll
+    for (int t = 0; t < C::TW; t++) {
+      int r = 8 * s.tr + s.g, c0 = 8 * (s.tc0 + t) + 2 * s.tg;
+      cplx a = cmake(0, 0), bb = cmake(0, 0);
+      if (r < N && c0 < N) a = y0[r * N + c0];
+      if (r < N && c0 + 1 < N) bb = y0[r * N + c0 + 1];
+      yv[t][0][0] = a.x; yv[t][0][1] = bb.x; yv[t][1][0] = a.y; yv[t][1][1] = bb.y;
+      SLOT(sy, t, 0) = make_double2(a.x, bb.x);
+      SLOT(sy, t, 1) = make_double2(a.y, bb.y);
+    }
+  }
+  __syncthreads();
+
+  // write a state held in registers into the smem stage buffer Y
+  auto put_Y = [&](const double (&v)[C::TW][2][2]) {
+#pragma unroll
+    for (int t = 0; t < C::TW; t++) {
+      int r = 8 * s.tr + s.g, c0 = 8 * (s.tc0 + t) + 2 * s.tg;
+      *reinterpret_cast<double2*>(s.Y + r * C::LD + c0) = make_double2(v[t][0][0], v[t][0][1]);
+      *reinterpret_cast<double2*>(s.Y + C::PLANE + r * C::LD + c0) = make_double2(v[t][1][0], v[t][1][1]);
+    }
+  };
+  auto store_stream = [&](double2* dst, const double (&v)[C::TW][2][2]) {
+#pragma unroll
+    for (int t = 0; t < C::TW; t++) {
+      SLOT(dst, t, 0) = make_double2(v[t][0][0], v[t][0][1]);
+      SLOT(dst, t, 1) = make_double2(v[t][1][0], v[t][1][1]);
+    }
+  };
+  // v = y + h * sum_j a_j k_j  (thread-private)
+  auto combine = [&](double (&v)[C::TW][2][2], double h, int n, const double* a, double2* const* ks) {
+#pragma unroll
+    for (int t = 0; t < C::TW; t++)
+#pragma unroll
+      for (int pl = 0; pl < 2; pl++) {
+        double2 acc = make_double2(0.0, 0.0);
+        for (int j = 0; j < n; j++) {
+          double2 kv = SLOT(ks[j], t, pl);
+          acc.x = fma(a[j], kv.x, acc.x);
+          acc.y = fma(a[j], kv.y, acc.y);
+        }
+        double2 y0 = SLOT(sy, t, pl);
+        v[t][pl][0] = fma(h, acc.x, y0.x);
+        v[t][pl][1] = fma(h, acc.y, y0.y);
+      }
+  };
+
+  int status = SEQ_STATUS_OK, nacc = 0, nrej = 0, nrhs = 0;
+  double t = p.t0 + p.dt * (double)p.out_idx[0];
+  double h = p.first_step > 0 ? p.first_step : p.dt;
+  if (p.max_step > 0 && h > p.max_step) h = p.max_step;
+  bool have_k1 = false, prev_rejected = false;
+  double K[C::TW][2][2];
+
+  for (int o = 0; o < p.n_out; o++) {
+    if (o > 0) {
+      const double t_target = p.t0 + p.dt * (double)p.out_idx[o];
+      int nst = 0;
+      while (true) {
+        double rem = t_target - t;
+        if (rem <= 1e-13 * fmax(1.0, fabs(t_target))) break;
+        double htry = h;
+        if (p.max_step > 0 && htry > p.max_step) htry = p.max_step;
+        double q = ceil(rem / htry - 1e-9);
+        if (q < 1.0) q = 1.0;
+        htry = rem / q;
+        const bool landing = (q == 1.0);
+        double v[C::TW][2][2];
+        if (!have_k1) {
+          combine(v, 0.0, 0, nullptr, nullptr);
+          __syncthreads();
+          put_Y(v);
+          dmma_rhs<NT>(p, x, s, t, tabc, tabr, cscale, K);
+          store_stream(k1, K);
+          nrhs++;
+          have_k1 = true;
+        }
+        {
+          const double a[1] = {DP_A21}; double2* ks[1] = {k1};
+          combine(v, htry, 1, a, ks);
+          __syncthreads(); put_Y(v);
+          dmma_rhs<NT>(p, x, s, t + DP_C2 * htry, tabc, tabr, cscale, K);
+          store_stream(k2, K);
+        }
+        {
+          const double a[2] = {DP_A31, DP_A32}; double2* ks[2] = {k1, k2};
+          combine(v, htry, 2, a, ks);
+          __syncthreads(); put_Y(v);
+          dmma_rhs<NT>(p, x, s, t + DP_C3 * htry, tabc, tabr, cscale, K);
+          store_stream(k3, K);
+        }
+        {
+          const double a[3] = {DP_A41, DP_A42, DP_A43}; double2* ks[3] = {k1, k2, k3};
+          combine(v, htry, 3, a, ks);
+          __syncthreads(); put_Y(v);
+          dmma_rhs<NT>(p, x, s, t + DP_C4 * htry, tabc, tabr, cscale, K);
+          store_stream(k4, K);
+        }
+        {
+          const double a[4] = {DP_A51, DP_A52, DP_A53, DP_A54}; double2* ks[4] = {k1, k2, k3, k4};
+          combine(v, htry, 4, a, ks);
+          __syncthreads(); put_Y(v);
+          dmma_rhs<NT>(p, x, s, t + DP_C5 * htry, tabc, tabr, cscale, K);
+          store_stream(k5, K);
+        }
+        {
+          const double a[5] = {DP_A61, DP_A62, DP_A63, DP_A64, DP_A65}; double2* ks[5] = {k1, k2, k3, k4, k5};
+          combine(v, htry, 5, a, ks);
+          __syncthreads(); put_Y(v);
+          dmma_rhs<NT>(p, x, s, t + htry, tabc, tabr, cscale, K);
+          store_stream(k6, K);
+        }
+        {
+          const double a[5] = {DP_B1, DP_B3, DP_B4, DP_B5, DP_B6}; double2* ks[5] = {k1, k3, k4, k5, k6};
+          combine(v, htry, 5, a, ks);   // v = y_new
+          __syncthreads(); put_Y(v);
+          store_stream(syn, v);
+          dmma_rhs<NT>(p, x, s, t + htry, tabc, tabr, cscale, K);   // K = k7
+          store_stream(k7, K);
+        }
+        nrhs += 6;
+        // error estimate (thread-private), RMS over the N*N physical elements
+        double es = 0.0;
+#pragma unroll
+        for (int tt = 0; tt < C::TW; tt++) {
+          double e[2][2];
+#pragma unroll
+          for (int pl = 0; pl < 2; pl++) {
+            double2 a1 = SLOT(k1, tt, pl), a3 = SLOT(k3, tt, pl), a4 = SLOT(k4, tt, pl), a5 = SLOT(k5, tt, pl), a6 = SLOT(k6, tt, pl);
+            e[pl][0] = htry * (DP_E1 * a1.x + DP_E3 * a3.x + DP_E4 * a4.x + DP_E5 * a5.x + DP_E6 * a6.x + DP_E7 * K[tt][pl][0]);
+            e[pl][1] = htry * (DP_E1 * a1.y + DP_E3 * a3.y + DP_E4 * a4.y + DP_E5 * a5.y + DP_E6 * a6.y + DP_E7 * K[tt][pl][1]);
+          }
+          double2 yr = SLOT(sy, tt, 0), yi = SLOT(sy, tt, 1);
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            double y2 = c ? (yr.y * yr.y + yi.y * yi.y) : (yr.x * yr.x + yi.x * yi.x);
+            double n2 = v[tt][0][c] * v[tt][0][c] + v[tt][1][c] * v[tt][1][c];
+            double sc = p.atol + p.rtol * sqrt(fmax(y2, n2));
+            es += (e[0][c] * e[0][c] + e[1][c] * e[1][c]) / (sc * sc);
+          }
+        }
+        es = block_sum(es, s.red);
+        double err = sqrt(es / (double)(N * N));
+        if (!(err == err) || isinf(err)) { status = SEQ_STATUS_NONFINITE; break; }
+        double factor;
+        if (err <= 1.0) {
+          factor = (err == 0.0) ? SEQ_MAX_FACTOR : fmin(SEQ_MAX_FACTOR, SEQ_SAFETY * pow(err, -0.2));
+          if (prev_rejected) factor = fmin(1.0, factor);
+          prev_rejected = false;
+          double2* tmp = sy; sy = syn; syn = tmp;
+          tmp = k1; k1 = k7; k7 = tmp;
+          t = landing ? t_target : t + htry;
+          nacc++;
+        } else {
+          factor = fmax(SEQ_MIN_FACTOR, SEQ_SAFETY * pow(err, -0.2));
+          prev_rejected = true;
+          nrej++;
+        }
+        h = htry * factor;
+        if (++nst > p.nsteps) { status = SEQ_STATUS_MAX_STEPS; break; }
+        if (h < 1e-14 * fmax(1.0, fabs(t))) { status = SEQ_STATUS_STEP_UNDERFLOW; break; }
+      }
+      if (status != SEQ_STATUS_OK) break;
+    }
+    // ---- outputs at sample o (thread-private reads of the y stream)
+#pragma unroll
+    for (int tt = 0; tt < C::TW; tt++) {
+      double2 a = SLOT(sy, tt, 0), bb = SLOT(sy, tt, 1);
+      yv[tt][0][0] = a.x; yv[tt][0][1] = a.y; yv[tt][1][0] = bb.x; yv[tt][1][1] = bb.y;
+    }
+    for (int e = 0; e < p.n_e; e++) {
+      // Tr(E rho) = sum_ij E_ji^T ... with Ef holding E[c][r] for the owned (r,c)
+      cplx acc = cmake(0, 0);
+#pragma unroll
+      for (int tt = 0; tt < C::TW; tt++) {
+        double2 er = x.Ef[((long long)e * C::SLOTS + tt * 2 + 0) * C::NTHREADS + tid];
+        double2 ei = x.Ef[((long long)e * C::SLOTS + tt * 2 + 1) * C::NTHREADS + tid];
+        // (er + i ei) * (yr + i yi)
+        acc.x += er.x * yv[tt][0][0] - ei.x * yv[tt][1][0] + er.y * yv[tt][0][1] - ei.y * yv[tt][1][1];
+        acc.y += er.x * yv[tt][1][0] + ei.x * yv[tt][0][0] + er.y * yv[tt][1][1] + ei.y * yv[tt][0][1];
+      }
+      acc = block_sum_c(acc, s.red);
+      if (tid == 0) {
+        long long off = ((long long)b * p.n_e + e) * p.n_out + o;
+        if (p.flags & SEQ_FLAG_EXPECT_COMPLEX) ((cplx*)p.expect)[off] = acc;
+        else ((double*)p.expect)[off] = acc.x;
+      }
+    }
+    if (p.flags & SEQ_FLAG_STORE_STATES) {
+      cplx* dst = p.states + ((long long)b * p.n_out + o) * N * N;
+#pragma unroll
+      for (int tt = 0; tt < C::TW; tt++) {
+        int r = 8 * s.tr + s.g, c0 = 8 * (s.tc0 + tt) + 2 * s.tg;
+        if (r < N && c0 < N) dst[r * N + c0] = cmake(yv[tt][0][0], yv[tt][1][0]);
+        if (r < N && c0 + 1 < N) dst[r * N + c0 + 1] = cmake(yv[tt][0][1], yv[tt][1][1]);
+      }
+    }
+  }
+  {
+    cplx* fin = p.final_state + (long long)b * N * N;
+#pragma unroll
+    for (int tt = 0; tt < C::TW; tt++) {
+      double2 a = SLOT(sy, tt, 0), bb = SLOT(sy, tt, 1);
+      int r = 8 * s.tr + s.g, c0 = 8 * (s.tc0 + tt) + 2 * s.tg;
+      if (r < N && c0 < N) fin[r * N + c0] = cmake(a.x, bb.x);
+      if (r < N && c0 + 1 < N) fin[r * N + c0 + 1] = cmake(a.y, bb.y);
+    }
+  }
+  if (tid == 0) {
+    p.status[b] = status;
+    p.stats[b * 4 + 0] = nacc;
+    p.stats[b * 4 + 1] = nrej;
+    p.stats[b * 4 + 2] = nrhs;
+    p.stats[b * 4 + 3] = 0;
+  }
+#undef SLOT
+}
+
+// ---- host side ---------------------------------------------------------------------------
+static inline int dmma_nt(int N) { return (N + 7) / 8; }
+static inline bool dmma_supported(int N, int max_smem) {
+  int nt = dmma_nt(N);
+  if (nt < 1 || nt > 6) return false;
+  return DmmaCfg<6>::SMEM <= (size_t)max_smem;
+}
+// complex elements of per-trajectory scratch: 9 streams of SLOTS*NTHREADS double2
+static inline size_t dmma_ws_elems(int N) {
+  switch (dmma_nt(N)) {
+    case 1: return 9 * (size_t)DmmaCfg<1>::SLOTS * DmmaCfg<1>::NTHREADS;
+    case 2: return 9 * (size_t)DmmaCfg<2>::SLOTS * DmmaCfg<2>::NTHREADS;
+    case 3: return 9 * (size_t)DmmaCfg<3>::SLOTS * DmmaCfg<3>::NTHREADS;
+    case 4: return 9 * (size_t)DmmaCfg<4>::SLOTS * DmmaCfg<4>::NTHREADS;
+    case 5: return 9 * (size_t)DmmaCfg<5>::SLOTS * DmmaCfg<5>::NTHREADS;
+    default: return 9 * (size_t)DmmaCfg<6>::SLOTS * DmmaCfg<6>::NTHREADS;
+  }
+}
+// doubles of packed-operator scratch the DMMA path needs
+static inline size_t dmma_pack_doubles(int N, int n_g, int n_l, int n_e) {
+  int nt = dmma_nt(N), NP = 8 * nt, LD = NP + 4;
+  size_t mat = 2 * (size_t)NP * LD;
+  size_t slots_threads = dmma_ws_elems(N) / 9;  // SLOTS*NTHREADS
+  return (1 + (size_t)n_g + n_l) * mat + (size_t)n_e * slots_threads * 2 + 64;
+}
+
+template <int NT>
+static int launch_dmma_nt(const SolveParams& p, const cplx* G0, const cplx* Gk, double* pack, cudaStream_t st, int* launches) {
+  typedef DmmaCfg<NT> C;
+  const int N = p.N, n_l = p.n_c + p.n_ctd;
+  DmmaExtra x;
+  double* G0p = pack;
+  double* Gkp = G0p + C::MAT;
+  double* Lp = Gkp + (size_t)p.n_g * C::MAT;
+  double2* Ef = reinterpret_cast<double2*>(Lp + (size_t)n_l * C::MAT);
+  dim3 blk(256);
+  int gx = (C::NP * C::LD + 255) / 256;
+  dmma_pack_planar_kernel<<<dim3(gx, 1), blk, 0, st>>>(G0, G0p, N, C::NP, C::LD);
+  (*launches)++;
+  if (p.n_g > 0) { dmma_pack_planar_kernel<<<dim3(gx, p.n_g), blk, 0, st>>>(Gk, Gkp, N, C::NP, C::LD); (*launches)++; }
+  if (n_l > 0) { dmma_pack_planar_kernel<<<dim3(gx, n_l), blk, 0, st>>>(p.L, Lp, N, C::NP, C::LD); (*launches)++; }
+  if (p.n_e > 0) { dmma_pack_efrag_kernel<NT><<<p.n_e, C::NTHREADS, 0, st>>>(p.E, Ef, N); (*launches)++; }
+  x.G0p = G0p; x.Gkp = Gkp; x.Lp = Lp; x.Ef = Ef;
+  cudaError_t rc = cudaFuncSetAttribute(solve_dmma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+  if (rc != cudaSuccess) return SEQ_ERR_CUDA;
+  solve_dmma_kernel<NT><<<p.B, C::NTHREADS, C::SMEM, st>>>(p, x);
+  (*launches)++;
+  return SEQ_OK;
+}
+
+static inline int launch_dmma(const SolveParams& p, const cplx* G0, const cplx* Gk, double* pack, cudaStream_t st, int* launches) {
+  switch (dmma_nt(p.N)) {
+    case 1: return launch_dmma_nt<1>(p, G0, Gk, pack, st, launches);
+    case 2: return launch_dmma_nt<2>(p, G0, Gk, pack, st, launches);
+    case 3: return launch_dmma_nt<3>(p, G0, Gk, pack, st, launches);
+    case 4: return launch_dmma_nt<4>(p, G0, Gk, pack, st, launches);
+    case 5: return launch_dmma_nt<5>(p, G0, Gk, pack, st, launches);
+    case 6: return launch_dmma_nt<6>(p, G0, Gk, pack, st, launches);
+    default: return SEQ_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace seq

@@ -31,7 +31,7 @@ struct seq_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
-  DevBuf ws, gbuf, tab, cprime, stage_in, stage_out;
+  DevBuf ws, gbuf, tab, cprime, pack, stage_in, stage_out;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   int launches = 0;
@@ -314,7 +314,7 @@ int seq_engine_destroy(seq_engine* e) {
   if (!e) return SEQ_OK;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  DevBuf* bufs[] = {&e->ws, &e->gbuf, &e->tab, &e->cprime, &e->stage_in, &e->stage_out};
+  DevBuf* bufs[] = {&e->ws, &e->gbuf, &e->tab, &e->cprime, &e->pack, &e->stage_in, &e->stage_out};
   for (DevBuf* b : bufs) if (b->ptr) cudaFree(b->ptr);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
@@ -408,6 +408,10 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   const long long series_r = (long long)(d->rate_batch_stride ? B : 1) * d->n_ctd;
   rc = reserve(e, e->tab, (size_t)(series_c + series_r) * d->n_t * sizeof(double2) + 256);
   if (rc) return rc;
+  if (method == SEQ_METHOD_DMMA) {
+    rc = reserve(e, e->pack, dmma_pack_doubles(N, n_g, d->n_c + d->n_ctd, d->n_e) * sizeof(double));
+    if (rc) return rc;
+  }
   if (d->coeff_batch_stride && d->coeff_batch_stride != (int64_t)d->n_ch * d->n_t)
     return fail(e, SEQ_ERR_UNSUPPORTED, "coeff_batch_stride must be 0 or n_ch*n_t");
   if (d->rate_batch_stride && d->rate_batch_stride != (int64_t)d->n_ctd * d->n_t)
@@ -480,9 +484,8 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
     else solve_generic_kernel<false><<<B, threads, smem, e->stream>>>(p);
     e->launches++;
   } else if (method == SEQ_METHOD_DMMA) {
-    rc = launch_dmma(p, e->sm_count, e->max_smem_optin, e->stream);
+    rc = launch_dmma(p, G0, Gk, (double*)e->pack.ptr, e->stream, &e->launches);
     if (rc) return fail(e, rc, "DMMA kernel launch configuration failed for N=%d", N);
-    e->launches++;
   } else {
     rc = launch_small(p, e->sm_count, e->stream);
     if (rc) return fail(e, rc, "small-N kernel launch configuration failed for N=%d", N);

@@ -285,11 +285,18 @@ class _Deferral:
         self.results.append(res)
         return res
 
-    def flush(self):
+    def groups(self):
         groups = {}
         for i, it in enumerate(self.items):
             groups.setdefault(it.signature(), []).append(i)
-        for idxs in groups.values():
+        return list(groups.values())
+
+    def batch_problems(self):
+        """The collected solves as engine-level ``BatchProblem``s (one per compatible group)."""
+        return [_to_batch([self.items[i] for i in idxs]) for idxs in self.groups()]
+
+    def flush(self):
+        for idxs in self.groups():
             items = [self.items[i] for i in idxs]
             out = Engine.get().solve(_to_batch(items))
             for b, i in enumerate(idxs):
@@ -301,17 +308,19 @@ _active: List[_Deferral] = []
 
 
 @contextlib.contextmanager
-def deferred_solves():
+def deferred_solves(execute=True):
     """Collect every ``mesolve``/``sesolve`` issued inside the block and run them as batched
     engine calls (grouped by shared operators / grid / options) when the block exits.  The
-    ``Result`` objects returned inside the block are filled in at that point."""
+    ``Result`` objects returned inside the block are filled in at that point.  With
+    ``execute=False`` nothing is run: ``d.batch_problems()`` gives the lowered batches."""
     d = _Deferral()
     _active.append(d)
     try:
         yield d
     finally:
         _active.remove(d)
-    d.flush()
+    if execute:
+        d.flush()
 
 
 def mesolve(H, rho0, tlist, c_ops=None, e_ops=None, args=None, options=None, progress_bar=None, _safe_mode=True):
