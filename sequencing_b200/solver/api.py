@@ -363,7 +363,10 @@ def propagator(H, t, c_op_list=None, args=None, options=None, unitary_mode="batc
     dims = first.dims
     opt = Options(**{k: getattr(options, k) for k in ("atol", "rtol", "nsteps", "first_step", "max_step", "min_step")})
     opt.store_states = True
-    opt.normalize_output = False
+    # QuTiP's unitary "batch" mode renormalises every column at every output (sesolve with
+    # oper_evo and Options.normalize_output), which is what makes propagator()[-1]*psi agree with
+    # run() to 5e-9 (test_sequencing.py:158); the superoperator path is never normalised.
+    opt.normalize_output = bool(options.normalize_output) and not c_ops
     opt.kernel_method = options.kernel_method
     if not c_ops:
         kets = [qt.Qobj(np.eye(N)[:, n], dims=[dims[0], [1] * len(dims[0])]) for n in range(N)]

@@ -1,0 +1,27 @@
+"""Condense an ncu report into the few metrics the roofline discussion needs.
+usage: python tools/ncu_summary.py gpurun_out/x.ncu-rep > profiles/x_summary.json"""
+import csv, io, json, subprocess, sys
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
+    "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "smsp__pipe_tensor_subpipe_dmma_cycles_active.avg",
+    "sm__pipe_fp64_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg", "sm__cycles_active.avg",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+    "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warp_latency_per_inst_issued.ratio",
+]
+raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units = rows[0], rows[1]
+out = []
+for vals in rows[2:]:
+    d = {"kernel": vals[hdr.index("Kernel Name")]}
+    for h, u, v in zip(hdr, units, vals):
+        if any(h.endswith(k) for k in KEYS):
+            d[h.split(".TriageCompute.")[-1] + (f" [{u}]" if u else "")] = v
+    out.append(d)
+print(json.dumps(out, indent=1))
