@@ -63,6 +63,18 @@ __device__ __forceinline__ double cabs2(cplx a) { return a.x * a.x + a.y * a.y; 
 #define DP_E6 (22.0 / 525.0)
 #define DP_E7 (-1.0 / 40.0)
 
+// stage s (0..6): input = y + h sum_{j<s} DP_TAB_A[s][j] k_{j+1},  k_{s+1} = f(t + DP_TAB_C[s] h, input);
+// row 6 is the 5th-order solution (FSAL: its input is y_new)
+__constant__ double DP_TAB_A[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {DP_A21, 0, 0, 0, 0, 0},
+    {DP_A31, DP_A32, 0, 0, 0, 0},
+    {DP_A41, DP_A42, DP_A43, 0, 0, 0},
+    {DP_A51, DP_A52, DP_A53, DP_A54, 0, 0},
+    {DP_A61, DP_A62, DP_A63, DP_A64, DP_A65, 0},
+    {DP_B1, 0, DP_B3, DP_B4, DP_B5, DP_B6}};
+__constant__ double DP_TAB_C[7] = {0.0, DP_C2, DP_C3, DP_C4, DP_C5, 1.0, 1.0};
+
 // step-size controller (same constants as scipy's RK45 / Hairer's DOPRI5)
 #define SEQ_SAFETY 0.9
 #define SEQ_MIN_FACTOR 0.2

@@ -243,8 +243,9 @@ solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
   double2* ws = reinterpret_cast<double2*>(p.ws + (long long)b * p.ws_stride) + tid;
   constexpr int STREAM = C::SLOTS * C::NTHREADS;
   double2* sy = ws; double2* syn = ws + STREAM;
-  double2* k1 = ws + 2 * STREAM; double2* k2 = ws + 3 * STREAM; double2* k3 = ws + 4 * STREAM;
-  double2* k4 = ws + 5 * STREAM; double2* k5 = ws + 6 * STREAM; double2* k6 = ws + 7 * STREAM; double2* k7 = ws + 8 * STREAM;
+  double2* kp[7];
+#pragma unroll
+  for (int j = 0; j < 7; j++) kp[j] = ws + (2 + j) * STREAM;
 #define SLOT(ptr, t, pl) (ptr)[((t)*2 + (pl)) * C::NTHREADS]
 
   // zero the Y buffer once (padding must stay zero), then load rho0 into registers/streams
@@ -282,7 +283,7 @@ solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
     }
   };
   // v = y + h * sum_j a_j k_j  (thread-private)
-  auto combine = [&](double (&v)[C::TW][2][2], double h, int n, const double* a, double2* const* ks) {
+  auto combine = [&](double (&v)[C::TW][2][2], double h, int n, const double* __restrict__ a, double2* const* ks) {
 #pragma unroll
     for (int t = 0; t < C::TW; t++)
 #pragma unroll
@@ -320,59 +321,16 @@ solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
         htry = rem / q;
         const bool landing = (q == 1.0);
         double v[C::TW][2][2];
-        if (!have_k1) {
-          combine(v, 0.0, 0, nullptr, nullptr);
-          __syncthreads();
+        for (int st = have_k1 ? 1 : 0; st < 7; st++) {
+          combine(v, htry, st, DP_TAB_A[st], kp);      // st == 6: v = y_new
+          __syncthreads();                             // every warp is out of the previous RHS
           put_Y(v);
-          dmma_rhs<NT>(p, x, s, t, tabc, tabr, cscale, K);
-          store_stream(k1, K);
+          if (st == 6) store_stream(syn, v);
+          dmma_rhs<NT>(p, x, s, t + DP_TAB_C[st] * htry, tabc, tabr, cscale, K);
+          store_stream(kp[st], K);
           nrhs++;
-          have_k1 = true;
         }
-        {
-          const double a[1] = {DP_A21}; double2* ks[1] = {k1};
-          combine(v, htry, 1, a, ks);
-          __syncthreads(); put_Y(v);
-          dmma_rhs<NT>(p, x, s, t + DP_C2 * htry, tabc, tabr, cscale, K);
-          store_stream(k2, K);
-        }
-        {
-          const double a[2] = {DP_A31, DP_A32}; double2* ks[2] = {k1, k2};
-          combine(v, htry, 2, a, ks);
-          __syncthreads(); put_Y(v);
-          dmma_rhs<NT>(p, x, s, t + DP_C3 * htry, tabc, tabr, cscale, K);
-          store_stream(k3, K);
-        }
-        {
-          const double a[3] = {DP_A41, DP_A42, DP_A43}; double2* ks[3] = {k1, k2, k3};
-          combine(v, htry, 3, a, ks);
-          __syncthreads(); put_Y(v);
-          dmma_rhs<NT>(p, x, s, t + DP_C4 * htry, tabc, tabr, cscale, K);
-          store_stream(k4, K);
-        }
-        {
-          const double a[4] = {DP_A51, DP_A52, DP_A53, DP_A54}; double2* ks[4] = {k1, k2, k3, k4};
-          combine(v, htry, 4, a, ks);
-          __syncthreads(); put_Y(v);
-          dmma_rhs<NT>(p, x, s, t + DP_C5 * htry, tabc, tabr, cscale, K);
-          store_stream(k5, K);
-        }
-        {
-          const double a[5] = {DP_A61, DP_A62, DP_A63, DP_A64, DP_A65}; double2* ks[5] = {k1, k2, k3, k4, k5};
-          combine(v, htry, 5, a, ks);
-          __syncthreads(); put_Y(v);
-          dmma_rhs<NT>(p, x, s, t + htry, tabc, tabr, cscale, K);
-          store_stream(k6, K);
-        }
-        {
-          const double a[5] = {DP_B1, DP_B3, DP_B4, DP_B5, DP_B6}; double2* ks[5] = {k1, k3, k4, k5, k6};
-          combine(v, htry, 5, a, ks);   // v = y_new
-          __syncthreads(); put_Y(v);
-          store_stream(syn, v);
-          dmma_rhs<NT>(p, x, s, t + htry, tabc, tabr, cscale, K);   // K = k7
-          store_stream(k7, K);
-        }
-        nrhs += 6;
+        have_k1 = true;
         // error estimate (thread-private), RMS over the N*N physical elements
         double es = 0.0;
 #pragma unroll
@@ -380,7 +338,7 @@ solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
           double e[2][2];
 #pragma unroll
           for (int pl = 0; pl < 2; pl++) {
-            double2 a1 = SLOT(k1, tt, pl), a3 = SLOT(k3, tt, pl), a4 = SLOT(k4, tt, pl), a5 = SLOT(k5, tt, pl), a6 = SLOT(k6, tt, pl);
+            double2 a1 = SLOT(kp[0], tt, pl), a3 = SLOT(kp[2], tt, pl), a4 = SLOT(kp[3], tt, pl), a5 = SLOT(kp[4], tt, pl), a6 = SLOT(kp[5], tt, pl);
             e[pl][0] = htry * (DP_E1 * a1.x + DP_E3 * a3.x + DP_E4 * a4.x + DP_E5 * a5.x + DP_E6 * a6.x + DP_E7 * K[tt][pl][0]);
             e[pl][1] = htry * (DP_E1 * a1.y + DP_E3 * a3.y + DP_E4 * a4.y + DP_E5 * a5.y + DP_E6 * a6.y + DP_E7 * K[tt][pl][1]);
           }
@@ -402,7 +360,7 @@ solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
           if (prev_rejected) factor = fmin(1.0, factor);
           prev_rejected = false;
           double2* tmp = sy; sy = syn; syn = tmp;
-          tmp = k1; k1 = k7; k7 = tmp;
+          tmp = kp[0]; kp[0] = kp[6]; kp[6] = tmp;
           t = landing ? t_target : t + htry;
           nacc++;
         } else {

@@ -1,0 +1,459 @@
+// SEQ_METHOD_DMMA_STREAM: FP64 tensor-core Lindblad integrator for 48 < N <= 96, where rho, G and
+// the collapse operators no longer fit in shared memory together.
+//
+// The padded matrix (NPF = 2*BS, BS = 8*BT <= 48) is cut into 2x2 blocks.  Every matrix lives in L2
+// as four "block images" (planar re/im, padded leading dimension BS+4 - the exact shared-memory
+// layout of kernel_dmma.cuh), so a block moves L2 -> shared memory as a flat cp.async stream.  An RHS
+// evaluation is a list of block products  C[I][J] += A[I][Kb] * B[Kb][J]  (8 for -iG rho, 16 per
+// collapse operator) executed through a two-stage cp.async pipeline: while the 12 warps run the
+// DMMA chains of task i out of stage i&1, the two operand blocks of task i+1 land in the other
+// stage.  One __syncthreads per task.  Accumulators of a quadrant stay in registers over its two
+// K-blocks; finished quadrants go to L2: T (scratch, block images) or the thread-private k-stream.
+//
+// One CTA still integrates one trajectory over the whole time span; step control, spline
+// evaluation, error norm, expectation values and state stores are fused exactly as in the
+// resident kernel.
+#pragma once
+#include "kernel_dmma.cuh"
+
+namespace seq {
+
+template <int BT> struct StreamCfg {
+  typedef DmmaCfg<BT> C;
+  static constexpr int BS = C::NP;                 // block size (rows/cols)
+  static constexpr int NPF = 2 * BS;               // padded full dimension
+  static constexpr int BLK = C::MAT;               // doubles per block image
+  static constexpr int FULL = 4 * BLK;             // doubles per full matrix
+  static constexpr int QSLOTS = 4 * C::SLOTS;      // double2 per thread per state vector
+  static constexpr int NTHREADS = C::NTHREADS;
+  static constexpr size_t SMEM = (size_t)(4 * BLK + 34 + 64) * sizeof(double);
+};
+
+// interleaved complex [N,N] -> four block images (zero padded)
+__global__ void stream_pack_blocks_kernel(const cplx* __restrict__ src, double* __restrict__ dst, int N, int BS, int LD) {
+  int m = blockIdx.y;
+  const cplx* s = src + (long long)m * N * N;
+  const int plane = BS * LD, blk = 2 * plane;
+  double* d = dst + (long long)m * 4 * blk;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 4 * plane; idx += gridDim.x * blockDim.x) {
+    int q = idx / plane, rem = idx - q * plane;
+    int i = rem / LD, j = rem - i * LD;
+    int gi = (q >> 1) * BS + i, gj = (q & 1) * BS + j;
+    cplx v = cmake(0, 0);
+    if (j < BS && gi < N && gj < N) v = s[gi * N + gj];
+    d[q * blk + rem] = v.x;
+    d[q * blk + plane + rem] = v.y;
+  }
+}
+
+template <int BT>
+__global__ void stream_pack_efrag_kernel(const cplx* __restrict__ E, double2* __restrict__ Ef, int N) {
+  typedef StreamCfg<BT> S; typedef DmmaCfg<BT> C;
+  int e = blockIdx.x;
+  int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+  int tr = w / C::WPR, tc0 = (w % C::WPR) * C::TW;
+  for (int q = 0; q < 4; q++)
+    for (int t = 0; t < C::TW; t++) {
+      int r = (q >> 1) * S::BS + 8 * tr + g, c0 = (q & 1) * S::BS + 8 * (tc0 + t) + 2 * tg;
+      cplx a = cmake(0, 0), b = cmake(0, 0);
+      if (r < N && c0 < N) a = E[(long long)e * N * N + c0 * N + r];
+      if (r < N && c0 + 1 < N) b = E[(long long)e * N * N + (c0 + 1) * N + r];
+      long long base = ((long long)e * S::QSLOTS + q * C::SLOTS + t * 2) * S::NTHREADS + tid;
+      Ef[base] = make_double2(a.x, b.x);
+      Ef[base + S::NTHREADS] = make_double2(a.y, b.y);
+    }
+}
+
+template <int BT>
+__device__ __forceinline__ void stream_issue(double* stage, const double* __restrict__ Ablk, const double* __restrict__ Bblk, int tid) {
+  typedef StreamCfg<BT> S;
+  for (int c = tid; c < S::BLK / 2; c += S::NTHREADS) {
+    cp_async16(stage + 2 * c, Ablk + 2 * c);
+    cp_async16(stage + S::BLK + 2 * c, Bblk + 2 * c);
+  }
+  cp_async_commit();
+}
+
+template <int BT>
+__global__ void __launch_bounds__(StreamCfg<BT>::NTHREADS, 1)
+solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_constant__ DmmaExtra x) {
+  typedef StreamCfg<BT> S; typedef DmmaCfg<BT> C;
+  extern __shared__ __align__(16) double smem[];
+  double* red = smem + 4 * S::BLK;
+  double* cval = red + 34;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+  const int tr = w / C::WPR, tc0 = (w % C::WPR) * C::TW;
+  const int b = blockIdx.x, N = p.N;
+  const int nL = p.n_c + p.n_ctd;
+  const double2* tabc = p.tab + (long long)b * p.tab_bstride_c;
+  const double2* tabr = p.tab_rate + (long long)b * p.tab_bstride_r;
+  const double* cscale = p.coeff_scale ? p.coeff_scale + (long long)b * p.n_ch : nullptr;
+
+  // per-trajectory scratch: three block-image matrices, then 9 thread-private streams
+  double* wsd = reinterpret_cast<double*>(p.ws + (long long)b * p.ws_stride);
+  double* Gb = wsd; double* Yb = wsd + S::FULL; double* Tb = wsd + 2 * S::FULL;
+  double2* st0 = reinterpret_cast<double2*>(wsd + 3 * S::FULL) + tid;
+  constexpr int STREAM = S::QSLOTS * S::NTHREADS;
+  double2* sy = st0; double2* syn = st0 + STREAM;
+  double2* kp[7];
+#pragma unroll
+  for (int j = 0; j < 7; j++) kp[j] = st0 + (2 + j) * STREAM;
+#define QSLOT(ptr, q, t, pl) (ptr)[((q)*C::SLOTS + (t)*2 + (pl)) * S::NTHREADS]
+  // position of the (r, c0) pair this thread owns in quadrant q, tile t, inside a block image
+  auto blk_off = [&](int t) { return (8 * tr + g) * C::LD + 8 * (tc0 + t) + 2 * tg; };
+
+  // zero Y/T images once so the padding stays zero, load rho0 into the y stream
+  for (int c = tid; c < S::FULL; c += S::NTHREADS) { Yb[c] = 0.0; Tb[c] = 0.0; }
+  {
+    const cplx* y0 = p.state0 + (long long)b * N * N;
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+      for (int t = 0; t < C::TW; t++) {
+        int r = (q >> 1) * S::BS + 8 * tr + g, c0 = (q & 1) * S::BS + 8 * (tc0 + t) + 2 * tg;
+        cplx a = cmake(0, 0), bb = cmake(0, 0);
+        if (r < N && c0 < N) a = y0[r * N + c0];
+        if (r < N && c0 + 1 < N) bb = y0[r * N + c0 + 1];
+        QSLOT(sy, q, t, 0) = make_double2(a.x, bb.x);
+        QSLOT(sy, q, t, 1) = make_double2(a.y, bb.y);
+      }
+  }
+  __syncthreads();
+
+  // Yb <- y + h sum_j a_j k_j (thread-private streams -> own positions of the block images);
+  // optionally also keep the result in the stream `keep` (y_new)
+  auto stage_state = [&](double h, int n, const double* a, double2* const* ks, double2* keep) {
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+      for (int t = 0; t < C::TW; t++) {
+        double2 v[2];
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+          double2 acc = make_double2(0.0, 0.0);
+          for (int j = 0; j < n; j++) {
+            double2 kv = QSLOT(ks[j], q, t, pl);
+            acc.x = fma(a[j], kv.x, acc.x);
+            acc.y = fma(a[j], kv.y, acc.y);
+          }
+          double2 y0 = QSLOT(sy, q, t, pl);
+          v[pl] = make_double2(fma(h, acc.x, y0.x), fma(h, acc.y, y0.y));
+          if (keep) QSLOT(keep, q, t, pl) = v[pl];
+        }
+        double* dst = Yb + q * S::BLK + blk_off(t);
+        *reinterpret_cast<double2*>(dst) = v[0];
+        *reinterpret_cast<double2*>(dst + C::PLANE) = v[1];
+      }
+  };
+
+  // kout (thread-private stream) <- RHS(t, Yb)
+  auto rhs = [&](double t, double2* kout) {
+    if (tid < p.n_g) {
+      int m = tid;
+      double v;
+      if (m < p.n_ch) {
+        v = spline_eval(tabc + (long long)m * p.n_t, p.n_t, p.t0, p.dt, t);
+        if (cscale) v *= cscale[m];
+      } else {
+        v = spline_eval(tabr + (long long)(m - p.n_ch) * p.n_t, p.n_t, p.t0, p.dt, t);
+      }
+      cval[m] = v;
+    }
+    __syncthreads();   // cval visible; Yb complete; every warp is out of the previous RHS
+    {
+      const double2* g0 = reinterpret_cast<const double2*>(x.G0p);
+      double2* dst = reinterpret_cast<double2*>(Gb);
+      for (int c = tid; c < S::FULL / 2; c += S::NTHREADS) {
+        double2 v = g0[c];
+        for (int m = 0; m < p.n_g; m++) {
+          double2 a = reinterpret_cast<const double2*>(x.Gkp + (long long)m * S::FULL)[c];
+          double cv = cval[m];
+          v.x = fma(cv, a.x, v.x);
+          v.y = fma(cv, a.y, v.y);
+        }
+        dst[c] = v;
+      }
+    }
+    __syncthreads();   // Gb complete
+    const int ntask = 8 + 16 * nL;
+    // task i -> operand block images, quadrant, K-block, kind (0: G*Y, 1: L*Y, 2: T*L^dag)
+    auto task = [&](int i, const double*& A, const double*& B, int& q, int& kb, int& kind, int& l) {
+      if (i < 8) {
+        q = i >> 1; kb = i & 1; kind = 0; l = -1;
+        A = Gb + ((q >> 1) * 2 + kb) * S::BLK;
+        B = Yb + (kb * 2 + (q & 1)) * S::BLK;
+      } else {
+        int j = i - 8;
+        l = j >> 4;
+        int r = j & 15;
+        const double* Ll = x.Lp + (long long)l * S::FULL;
+        if (r < 8) {
+          q = r >> 1; kb = r & 1; kind = 1;
+          A = Ll + ((q >> 1) * 2 + kb) * S::BLK;
+          B = Yb + (kb * 2 + (q & 1)) * S::BLK;
+        } else {
+          r -= 8;
+          q = r >> 1; kb = r & 1; kind = 2;
+          A = Tb + ((q >> 1) * 2 + kb) * S::BLK;
+          B = Ll + ((q & 1) * 2 + kb) * S::BLK;   // L[J][Kb], used as conj-transpose
+        }
+      }
+    };
+    const double* A; const double* B; int q, kb, kind, l;
+    task(0, A, B, q, kb, kind, l);
+    stream_issue<BT>(smem, A, B, tid);
+    double W[C::TW][2][2];
+    for (int i = 0; i < ntask; i++) {
+      cp_async_wait<0>();
+      __syncthreads();   // operands of task i landed; every warp finished task i-1 (its stage is free)
+      if (i == 8) {
+        // K += A1^dag, A1 = -iG rho sits complete in Tb:  K_re(r,c) += A_re(c,r), K_im(r,c) -= A_im(c,r)
+        for (int qq = 0; qq < 4; qq++)
+#pragma unroll
+          for (int t = 0; t < C::TW; t++) {
+            int rl = 8 * tr + g, cl = 8 * (tc0 + t) + 2 * tg;
+            const double* src = Tb + ((qq & 1) * 2 + (qq >> 1)) * S::BLK;   // block (J, I)
+            double2 kr = QSLOT(kout, qq, t, 0), ki = QSLOT(kout, qq, t, 1);
+            kr.x += src[cl * C::LD + rl];
+            kr.y += src[(cl + 1) * C::LD + rl];
+            ki.x -= src[C::PLANE + cl * C::LD + rl];
+            ki.y -= src[C::PLANE + (cl + 1) * C::LD + rl];
+            QSLOT(kout, qq, t, 0) = kr;
+            QSLOT(kout, qq, t, 1) = ki;
+          }
+        __syncthreads();   // all A^dag reads done before any epilogue overwrites Tb
+      }
+      const double* cur = smem + (i & 1) * 2 * S::BLK;
+      int cq = q, ckb = kb, ckind = kind, cl_ = l;
+      if (i + 1 < ntask) {
+        task(i + 1, A, B, q, kb, kind, l);
+        stream_issue<BT>(smem + ((i + 1) & 1) * 2 * S::BLK, A, B, tid);
+      }
+      if (ckb == 0) {
+#pragma unroll
+        for (int t = 0; t < C::TW; t++) { W[t][0][0] = W[t][0][1] = W[t][1][0] = W[t][1][1] = 0.0; }
+      }
+      if (ckind == 2) warp_gemm<BT, true>(W, cur, cur + S::BLK, tr, tc0, g, tg);
+      else warp_gemm<BT, false>(W, cur, cur + S::BLK, tr, tc0, g, tg);
+      if (ckb == 1) {
+        if (ckind == 0) {
+#pragma unroll
+          for (int t = 0; t < C::TW; t++) {
+            double2 are = make_double2(W[t][1][0], W[t][1][1]), aim = make_double2(-W[t][0][0], -W[t][0][1]);
+            double* dst = Tb + cq * S::BLK + blk_off(t);
+            *reinterpret_cast<double2*>(dst) = are;
+            *reinterpret_cast<double2*>(dst + C::PLANE) = aim;
+            QSLOT(kout, cq, t, 0) = are;
+            QSLOT(kout, cq, t, 1) = aim;
+          }
+        } else if (ckind == 1) {
+          const double r_l = (cl_ < p.n_c) ? 1.0 : cval[p.n_ch + (cl_ - p.n_c)];
+#pragma unroll
+          for (int t = 0; t < C::TW; t++) {
+            double* dst = Tb + cq * S::BLK + blk_off(t);
+            *reinterpret_cast<double2*>(dst) = make_double2(r_l * W[t][0][0], r_l * W[t][0][1]);
+            *reinterpret_cast<double2*>(dst + C::PLANE) = make_double2(r_l * W[t][1][0], r_l * W[t][1][1]);
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < C::TW; t++) {
+            double2 kr = QSLOT(kout, cq, t, 0), ki = QSLOT(kout, cq, t, 1);
+            kr.x += W[t][0][0]; kr.y += W[t][0][1]; ki.x += W[t][1][0]; ki.y += W[t][1][1];
+            QSLOT(kout, cq, t, 0) = kr;
+            QSLOT(kout, cq, t, 1) = ki;
+          }
+        }
+      }
+    }
+    if (nL == 0) {
+      __syncthreads();
+      for (int qq = 0; qq < 4; qq++)
+#pragma unroll
+        for (int t = 0; t < C::TW; t++) {
+          int rl = 8 * tr + g, cl = 8 * (tc0 + t) + 2 * tg;
+          const double* src = Tb + ((qq & 1) * 2 + (qq >> 1)) * S::BLK;
+          double2 kr = QSLOT(kout, qq, t, 0), ki = QSLOT(kout, qq, t, 1);
+          kr.x += src[cl * C::LD + rl];
+          kr.y += src[(cl + 1) * C::LD + rl];
+          ki.x -= src[C::PLANE + cl * C::LD + rl];
+          ki.y -= src[C::PLANE + (cl + 1) * C::LD + rl];
+          QSLOT(kout, qq, t, 0) = kr;
+          QSLOT(kout, qq, t, 1) = ki;
+        }
+    }
+  };
+
+  int status = SEQ_STATUS_OK, nacc = 0, nrej = 0, nrhs = 0;
+  double t = p.t0 + p.dt * (double)p.out_idx[0];
+  double h = p.first_step > 0 ? p.first_step : p.dt;
+  if (p.max_step > 0 && h > p.max_step) h = p.max_step;
+  bool have_k1 = false, prev_rejected = false;
+
+  for (int o = 0; o < p.n_out; o++) {
+    if (o > 0) {
+      const double t_target = p.t0 + p.dt * (double)p.out_idx[o];
+      int nst = 0;
+      while (true) {
+        double rem = t_target - t;
+        if (rem <= 1e-13 * fmax(1.0, fabs(t_target))) break;
+        double htry = h;
+        if (p.max_step > 0 && htry > p.max_step) htry = p.max_step;
+        double qn = ceil(rem / htry - 1e-9);
+        if (qn < 1.0) qn = 1.0;
+        htry = rem / qn;
+        const bool landing = (qn == 1.0);
+        for (int st = have_k1 ? 1 : 0; st < 7; st++) {
+          __syncthreads();
+          stage_state(htry, st, DP_TAB_A[st], kp, st == 6 ? syn : nullptr);
+          rhs(t + DP_TAB_C[st] * htry, kp[st]);
+          nrhs++;
+        }
+        have_k1 = true;
+        double es = 0.0;
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+          for (int tt = 0; tt < C::TW; tt++) {
+            double2 e[2];
+#pragma unroll
+            for (int pl = 0; pl < 2; pl++) {
+              double2 a1 = QSLOT(kp[0], q, tt, pl), a3 = QSLOT(kp[2], q, tt, pl), a4 = QSLOT(kp[3], q, tt, pl),
+                      a5 = QSLOT(kp[4], q, tt, pl), a6 = QSLOT(kp[5], q, tt, pl), a7 = QSLOT(kp[6], q, tt, pl);
+              e[pl].x = htry * (DP_E1 * a1.x + DP_E3 * a3.x + DP_E4 * a4.x + DP_E5 * a5.x + DP_E6 * a6.x + DP_E7 * a7.x);
+              e[pl].y = htry * (DP_E1 * a1.y + DP_E3 * a3.y + DP_E4 * a4.y + DP_E5 * a5.y + DP_E6 * a6.y + DP_E7 * a7.y);
+            }
+            double2 yr = QSLOT(sy, q, tt, 0), yi = QSLOT(sy, q, tt, 1), nr = QSLOT(syn, q, tt, 0), ni = QSLOT(syn, q, tt, 1);
+            double sc0 = p.atol + p.rtol * sqrt(fmax(yr.x * yr.x + yi.x * yi.x, nr.x * nr.x + ni.x * ni.x));
+            double sc1 = p.atol + p.rtol * sqrt(fmax(yr.y * yr.y + yi.y * yi.y, nr.y * nr.y + ni.y * ni.y));
+            es += (e[0].x * e[0].x + e[1].x * e[1].x) / (sc0 * sc0) + (e[0].y * e[0].y + e[1].y * e[1].y) / (sc1 * sc1);
+          }
+        es = block_sum(es, red);
+        double err = sqrt(es / (double)(N * N));
+        if (!(err == err) || isinf(err)) { status = SEQ_STATUS_NONFINITE; break; }
+        double factor;
+        if (err <= 1.0) {
+          factor = (err == 0.0) ? SEQ_MAX_FACTOR : fmin(SEQ_MAX_FACTOR, SEQ_SAFETY * pow(err, -0.2));
+          if (prev_rejected) factor = fmin(1.0, factor);
+          prev_rejected = false;
+          double2* tmp = sy; sy = syn; syn = tmp;
+          tmp = kp[0]; kp[0] = kp[6]; kp[6] = tmp;
+          t = landing ? t_target : t + htry;
+          nacc++;
+        } else {
+          factor = fmax(SEQ_MIN_FACTOR, SEQ_SAFETY * pow(err, -0.2));
+          prev_rejected = true;
+          nrej++;
+        }
+        h = htry * factor;
+        if (++nst > p.nsteps) { status = SEQ_STATUS_MAX_STEPS; break; }
+        if (h < 1e-14 * fmax(1.0, fabs(t))) { status = SEQ_STATUS_STEP_UNDERFLOW; break; }
+      }
+      if (status != SEQ_STATUS_OK) break;
+    }
+    for (int e = 0; e < p.n_e; e++) {
+      cplx acc = cmake(0, 0);
+      for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int tt = 0; tt < C::TW; tt++) {
+          long long base = ((long long)e * S::QSLOTS + q * C::SLOTS + tt * 2) * S::NTHREADS + tid;
+          double2 er = x.Ef[base], ei = x.Ef[base + S::NTHREADS];
+          double2 yr = QSLOT(sy, q, tt, 0), yi = QSLOT(sy, q, tt, 1);
+          acc.x += er.x * yr.x - ei.x * yi.x + er.y * yr.y - ei.y * yi.y;
+          acc.y += er.x * yi.x + ei.x * yr.x + er.y * yi.y + ei.y * yr.y;
+        }
+      acc = block_sum_c(acc, red);
+      if (tid == 0) {
+        long long off = ((long long)b * p.n_e + e) * p.n_out + o;
+        if (p.flags & SEQ_FLAG_EXPECT_COMPLEX) ((cplx*)p.expect)[off] = acc;
+        else ((double*)p.expect)[off] = acc.x;
+      }
+    }
+    if (p.flags & SEQ_FLAG_STORE_STATES) {
+      cplx* dst = p.states + ((long long)b * p.n_out + o) * N * N;
+      for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int tt = 0; tt < C::TW; tt++) {
+          int r = (q >> 1) * S::BS + 8 * tr + g, c0 = (q & 1) * S::BS + 8 * (tc0 + tt) + 2 * tg;
+          double2 yr = QSLOT(sy, q, tt, 0), yi = QSLOT(sy, q, tt, 1);
+          if (r < N && c0 < N) dst[r * N + c0] = cmake(yr.x, yi.x);
+          if (r < N && c0 + 1 < N) dst[r * N + c0 + 1] = cmake(yr.y, yi.y);
+        }
+    }
+  }
+  {
+    cplx* fin = p.final_state + (long long)b * N * N;
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+      for (int tt = 0; tt < C::TW; tt++) {
+        int r = (q >> 1) * S::BS + 8 * tr + g, c0 = (q & 1) * S::BS + 8 * (tc0 + tt) + 2 * tg;
+        double2 yr = QSLOT(sy, q, tt, 0), yi = QSLOT(sy, q, tt, 1);
+        if (r < N && c0 < N) fin[r * N + c0] = cmake(yr.x, yi.x);
+        if (r < N && c0 + 1 < N) fin[r * N + c0 + 1] = cmake(yr.y, yi.y);
+      }
+  }
+  if (tid == 0) {
+    p.status[b] = status;
+    p.stats[b * 4 + 0] = nacc;
+    p.stats[b * 4 + 1] = nrej;
+    p.stats[b * 4 + 2] = nrhs;
+    p.stats[b * 4 + 3] = 0;
+  }
+#undef QSLOT
+}
+
+// ---- host side ---------------------------------------------------------------------------
+static inline int stream_bt(int N) { int nt = (N + 7) / 8; return (nt + 1) / 2; }   // tiles per block
+static inline bool stream_supported(int N, int max_smem) {
+  int bt = stream_bt(N);
+  return N > 48 && bt >= 4 && bt <= 6 && StreamCfg<6>::SMEM <= (size_t)max_smem;
+}
+template <int BT> static size_t stream_ws_elems_bt() {
+  typedef StreamCfg<BT> S;
+  // 3 block-image matrices (doubles) + 9 streams of QSLOTS*NTHREADS double2, in complex (16 B) units
+  return (3 * (size_t)S::FULL + 1) / 2 + 9 * (size_t)S::QSLOTS * S::NTHREADS + 8;
+}
+static inline size_t stream_ws_elems(int N) {
+  switch (stream_bt(N)) {
+    case 4: return stream_ws_elems_bt<4>();
+    case 5: return stream_ws_elems_bt<5>();
+    default: return stream_ws_elems_bt<6>();
+  }
+}
+static inline size_t stream_pack_doubles(int N, int n_g, int n_l, int n_e) {
+  int bt = stream_bt(N), BS = 8 * bt, LD = BS + 4;
+  size_t full = 4 * 2 * (size_t)BS * LD;
+  size_t qslots_threads = (stream_ws_elems(N) - (3 * full + 1) / 2 - 8) / 9;
+  return (1 + (size_t)n_g + n_l) * full + (size_t)n_e * qslots_threads * 2 + 64;
+}
+
+template <int BT>
+static int launch_stream_bt(const SolveParams& p, const cplx* G0, const cplx* Gk, double* pack, cudaStream_t st, int* launches) {
+  typedef StreamCfg<BT> S; typedef DmmaCfg<BT> C;
+  const int N = p.N, n_l = p.n_c + p.n_ctd;
+  double* G0p = pack;
+  double* Gkp = G0p + S::FULL;
+  double* Lp = Gkp + (size_t)p.n_g * S::FULL;
+  double2* Ef = reinterpret_cast<double2*>(Lp + (size_t)n_l * S::FULL);
+  dim3 blk(256);
+  int gx = (4 * C::PLANE + 255) / 256;
+  stream_pack_blocks_kernel<<<dim3(gx, 1), blk, 0, st>>>(G0, G0p, N, S::BS, C::LD);
+  (*launches)++;
+  if (p.n_g > 0) { stream_pack_blocks_kernel<<<dim3(gx, p.n_g), blk, 0, st>>>(Gk, Gkp, N, S::BS, C::LD); (*launches)++; }
+  if (n_l > 0) { stream_pack_blocks_kernel<<<dim3(gx, n_l), blk, 0, st>>>(p.L, Lp, N, S::BS, C::LD); (*launches)++; }
+  if (p.n_e > 0) { stream_pack_efrag_kernel<BT><<<p.n_e, S::NTHREADS, 0, st>>>(p.E, Ef, N); (*launches)++; }
+  DmmaExtra x;
+  x.G0p = G0p; x.Gkp = Gkp; x.Lp = Lp; x.Ef = Ef;
+  cudaError_t rc = cudaFuncSetAttribute(solve_dmma_stream_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM);
+  if (rc != cudaSuccess) return SEQ_ERR_CUDA;
+  solve_dmma_stream_kernel<BT><<<p.B, S::NTHREADS, S::SMEM, st>>>(p, x);
+  (*launches)++;
+  return SEQ_OK;
+}
+
+static inline int launch_stream(const SolveParams& p, const cplx* G0, const cplx* Gk, double* pack, cudaStream_t st, int* launches) {
+  switch (stream_bt(p.N)) {
+    case 4: return launch_stream_bt<4>(p, G0, Gk, pack, st, launches);
+    case 5: return launch_stream_bt<5>(p, G0, Gk, pack, st, launches);
+    case 6: return launch_stream_bt<6>(p, G0, Gk, pack, st, launches);
+    default: return SEQ_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace seq

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "kernel_generic.cuh"
 #include "kernel_dmma.cuh"
+#include "kernel_dmma_stream.cuh"
 #include "kernel_small.cuh"
 
 using namespace seq;
@@ -268,6 +269,7 @@ static int pick_method(const seq_engine* e, const seq_solve_desc* d) {
   const bool ket = d->flags & SEQ_FLAG_KET;
   if (!ket && small_supported(d->N, d->n_ch + d->n_ctd, d->n_c + d->n_ctd)) return SEQ_METHOD_SMALL;
   if (!ket && d->H0_batch_stride == 0 && dmma_supported(d->N, e ? e->max_smem_optin : 232448)) return SEQ_METHOD_DMMA;
+  if (!ket && d->H0_batch_stride == 0 && stream_supported(d->N, e ? e->max_smem_optin : 232448)) return SEQ_METHOD_DMMA_STREAM;
   return SEQ_METHOD_GENERIC;
 }
 
@@ -279,6 +281,7 @@ static size_t ws_elems_per_traj(const seq_solve_desc* d, int method) {
   size_t N2 = (size_t)d->N * d->N, NN = state_elems(d);
   if (method == SEQ_METHOD_GENERIC) return 2 * N2 + 9 * NN;
   if (method == SEQ_METHOD_DMMA) return dmma_ws_elems(d->N);
+  if (method == SEQ_METHOD_DMMA_STREAM) return stream_ws_elems(d->N);
   return 0;
 }
 
@@ -290,7 +293,7 @@ extern "C" {
 int seq_engine_abi_version(void) { return SEQ_ENGINE_ABI_VERSION; }
 
 const char* seq_engine_build_info(void) {
-  return "seq_engine abi=1 arch=sm_100a kernels=generic(fma),dmma(8x8x4 resident),small(registers) built " __DATE__;
+  return "seq_engine abi=1 arch=sm_100a kernels=generic(fma),dmma(8x8x4 resident),dmma_stream(8x8x4 blocked),small(registers) built " __DATE__;
 }
 
 int seq_engine_create(int device, void* stream, seq_engine** out) {
@@ -394,7 +397,9 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
     return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_DMMA does not cover N=%d ket=%d h0_stride=%lld", N, (int)ket, (long long)d->H0_batch_stride);
   if (method == SEQ_METHOD_SMALL && (ket || !small_supported(N, n_g, d->n_c + d->n_ctd)))
     return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_SMALL does not cover N=%d ket=%d", N, (int)ket);
-  if (method != SEQ_METHOD_GENERIC && method != SEQ_METHOD_DMMA && method != SEQ_METHOD_SMALL)
+  if (method == SEQ_METHOD_DMMA_STREAM && (ket || !stream_supported(N, e->max_smem_optin) || d->H0_batch_stride))
+    return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_DMMA_STREAM does not cover N=%d ket=%d h0_stride=%lld", N, (int)ket, (long long)d->H0_batch_stride);
+  if (method < SEQ_METHOD_GENERIC || method > SEQ_METHOD_DMMA_STREAM)
     return fail(e, SEQ_ERR_UNSUPPORTED, "method %d is not implemented", method);
 
   // ---- scratch
@@ -410,6 +415,10 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   if (rc) return rc;
   if (method == SEQ_METHOD_DMMA) {
     rc = reserve(e, e->pack, dmma_pack_doubles(N, n_g, d->n_c + d->n_ctd, d->n_e) * sizeof(double));
+    if (rc) return rc;
+  }
+  if (method == SEQ_METHOD_DMMA_STREAM) {
+    rc = reserve(e, e->pack, stream_pack_doubles(N, n_g, d->n_c + d->n_ctd, d->n_e) * sizeof(double));
     if (rc) return rc;
   }
   if (d->coeff_batch_stride && d->coeff_batch_stride != (int64_t)d->n_ch * d->n_t)
@@ -486,6 +495,9 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   } else if (method == SEQ_METHOD_DMMA) {
     rc = launch_dmma(p, G0, Gk, (double*)e->pack.ptr, e->stream, &e->launches);
     if (rc) return fail(e, rc, "DMMA kernel launch configuration failed for N=%d", N);
+  } else if (method == SEQ_METHOD_DMMA_STREAM) {
+    rc = launch_stream(p, G0, Gk, (double*)e->pack.ptr, e->stream, &e->launches);
+    if (rc) return fail(e, rc, "streaming DMMA kernel launch configuration failed for N=%d", N);
   } else {
     rc = launch_small(p, e->sm_count, e->stream);
     if (rc) return fail(e, rc, "small-N kernel launch configuration failed for N=%d", N);

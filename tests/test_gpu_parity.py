@@ -224,6 +224,21 @@ def test_workload_c4_two_transmons_bus(gpu_engine):
     _check_problem(gpu_engine, lambda: workloads.c4_two_transmons_bus(2), [_lib.METHOD_AUTO], n_check=1, tol_truth=5e-6, truth=False)
 
 
+def test_dmma_stream_block_sizes_match_generic(gpu_engine):
+    """The blocked/streamed tensor-core kernel (48 < N <= 96) against the FP64-FMA kernel, incl. no collapse ops."""
+    for N, n_c, n_ctd in ((49, 2, 1), (64, 2, 0), (65, 0, 0), (72, 1, 1), (80, 2, 0), (81, 0, 2), (90, 3, 0), (96, 1, 0)):
+        mk = lambda: random_problem(N=N, B=2, n_t=5, n_ch=2, n_c=n_c, n_ctd=n_ctd, n_e=2, seed=N, hscale=0.3, store_states=True)
+        a, g = mk(), mk()
+        a.method, g.method = _lib.METHOD_DMMA_STREAM, _lib.METHOD_GENERIC
+        oa, og = gpu_engine.solve(a), gpu_engine.solve(g)
+        assert oa.method == "dmma_stream"
+        assert np.max(np.abs(oa.states - og.states)) < 1e-13, N
+        assert np.max(np.abs(oa.expect - og.expect)) < 1e-13, N
+        np.testing.assert_array_equal(oa.stats[:, :2], og.stats[:, :2])
+    auto = random_problem(N=90, B=1, n_t=3, n_ch=1, n_c=1, n_e=1, seed=1)
+    assert gpu_engine.solve(auto).method == "dmma_stream"
+
+
 def test_dmma_all_tile_counts_match_generic(gpu_engine):
     """Every padded size NP = 8..48 of the tensor-core kernel against the FP64-FMA kernel."""
     for N in (5, 8, 9, 16, 17, 24, 29, 32, 37, 40, 41, 48):

@@ -40,8 +40,14 @@ if "c3" in which:
     cmp("c3", w.c3_drag(16), [G, D])
 if "c2" in which:
     cmp("c2", w.c2_selective(4, 4), [G, D])
+S = _lib.METHOD_DMMA_STREAM
+if "stream" in which:
+    for N in (49, 57, 64, 65, 72, 80, 81, 90, 96):
+        cmp(f"rand{N}", random_problem(N=N, B=2, n_t=6, n_ch=2, n_c=2, n_ctd=1, n_e=2, seed=N, hscale=0.3), [G, S], oracle=False)
 if "c4" in which:
-    cmp("c4", w.c4_two_transmons_bus(4), [G], n_check=1)
+    cmp("c4", w.c4_two_transmons_bus(4), [G, S], n_check=1)
+if "c4big" in which:
+    cmp("c4big", w.c4_two_transmons_bus(148), [S], oracle=False)
 if "c2big" in which:
     bp = w.c2_selective(16, 16)
     cmp("c2big", bp, [D], oracle=False)
