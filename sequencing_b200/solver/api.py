@@ -298,10 +298,26 @@ class _Deferral:
     def flush(self):
         for idxs in self.groups():
             items = [self.items[i] for i in idxs]
-            out = Engine.get().solve(_to_batch(items))
+            out = _solve_maybe_sharded(_to_batch(items))
             for b, i in enumerate(idxs):
                 _fill(self.results[i], self.items[i], out, b)
         self.items, self.results = [], []
+
+
+def _solve_maybe_sharded(bp: BatchProblem) -> BatchOutput:
+    """Under ``torch.distributed`` (one process per GPU) a deferred sweep is sharded across the
+    ranks and gathered, so the same sweep script scales by launching it with torchrun."""
+    try:
+        import torch.distributed as dist
+
+        active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    except Exception:
+        active = False
+    if active and bp.B > 1:
+        from ..distributed import solve_sharded
+
+        return solve_sharded(bp, engine=Engine.get())
+    return Engine.get().solve(bp)
 
 
 _active: List[_Deferral] = []
