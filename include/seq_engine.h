@@ -57,6 +57,9 @@ extern "C" {
 #define SEQ_FLAG_STORE_STATES 0x4u    /* write every output state to `states` (Options.store_states) */
 #define SEQ_FLAG_EXPECT_COMPLEX 0x8u  /* `expect` is complex128 (non-Hermitian e_ops)               */
 #define SEQ_FLAG_HOST_POINTERS 0x10u  /* all data pointers are host pointers (end-to-end call)      */
+#define SEQ_FLAG_NO_ORDER_SWITCH 0x20u /* always step with the Dormand-Prince 5(4) pair (default: the
+                                          controller may drop to a 4-stage RK4(3) pair while steps
+                                          are capped by max_step and the error estimate is tiny)   */
 
 /* kernel selection (0 = let the engine choose by N) */
 #define SEQ_METHOD_AUTO 0

@@ -63,22 +63,41 @@ __device__ __forceinline__ double cabs2(cplx a) { return a.x * a.x + a.y * a.y; 
 #define DP_E6 (22.0 / 525.0)
 #define DP_E7 (-1.0 / 40.0)
 
-// stage s (0..6): input = y + h sum_{j<s} DP_TAB_A[s][j] k_{j+1},  k_{s+1} = f(t + DP_TAB_C[s] h, input);
-// row 6 is the 5th-order solution (FSAL: its input is y_new)
-__constant__ double DP_TAB_A[7][6] = {
-    {0, 0, 0, 0, 0, 0},
-    {DP_A21, 0, 0, 0, 0, 0},
-    {DP_A31, DP_A32, 0, 0, 0, 0},
-    {DP_A41, DP_A42, DP_A43, 0, 0, 0},
-    {DP_A51, DP_A52, DP_A53, DP_A54, 0, 0},
-    {DP_A61, DP_A62, DP_A63, DP_A64, DP_A65, 0},
-    {DP_B1, 0, DP_B3, DP_B4, DP_B5, DP_B6}};
-__constant__ double DP_TAB_C[7] = {0.0, DP_C2, DP_C3, DP_C4, DP_C5, 1.0, 1.0};
+// ---- embedded pairs.  pair 0: Dormand-Prince 5(4), 7 stages (6 RHS/step with FSAL);
+// pair 1: the 3/8-rule RK4 with a 3rd-order FSAL error estimator (Hairer/Norsett/Wanner II.4),
+// 5 stages (4 RHS/step with FSAL).  Stage s: input = y + h sum_{j<s} RK_A[pair][s][j] k_{j+1},
+// k_{s+1} = f(t + RK_C[pair][s] h, input); the last row is the propagated solution (its input is
+// y_new, so its derivative is k1 of the next step for either pair); error = h sum_j RK_E[pair][j] k_{j+1}.
+__constant__ double RK_A[2][7][6] = {
+    {{0, 0, 0, 0, 0, 0},
+     {DP_A21, 0, 0, 0, 0, 0},
+     {DP_A31, DP_A32, 0, 0, 0, 0},
+     {DP_A41, DP_A42, DP_A43, 0, 0, 0},
+     {DP_A51, DP_A52, DP_A53, DP_A54, 0, 0},
+     {DP_A61, DP_A62, DP_A63, DP_A64, DP_A65, 0},
+     {DP_B1, 0, DP_B3, DP_B4, DP_B5, DP_B6}},
+    {{0, 0, 0, 0, 0, 0},
+     {1.0 / 3.0, 0, 0, 0, 0, 0},
+     {-1.0 / 3.0, 1.0, 0, 0, 0, 0},
+     {1.0, -1.0, 1.0, 0, 0, 0},
+     {1.0 / 8.0, 3.0 / 8.0, 3.0 / 8.0, 1.0 / 8.0, 0, 0},
+     {0, 0, 0, 0, 0, 0},
+     {0, 0, 0, 0, 0, 0}}};
+__constant__ double RK_C[2][7] = {{0.0, DP_C2, DP_C3, DP_C4, DP_C5, 1.0, 1.0}, {0.0, 1.0 / 3.0, 2.0 / 3.0, 1.0, 1.0, 0, 0}};
+__constant__ double RK_E[2][7] = {{DP_E1, 0.0, DP_E3, DP_E4, DP_E5, DP_E6, DP_E7},
+                                  {1.0 / 24.0, -1.0 / 8.0, 1.0 / 8.0, 1.0 / 8.0, -1.0 / 6.0, 0, 0}};
+__constant__ int RK_STAGES[2] = {7, 5};
+__constant__ double RK_EXPO[2] = {-0.2, -0.25};
 
 // step-size controller (same constants as scipy's RK45 / Hairer's DOPRI5)
 #define SEQ_SAFETY 0.9
 #define SEQ_MIN_FACTOR 0.2
 #define SEQ_MAX_FACTOR 10.0
+// order switching: probe the 4(3) pair when a 5(4) step was accepted at a capped step size with an
+// error estimate below SEQ_PROBE_ERR; keep it only while it holds the capped step with its own
+// error estimate below SEQ_STAY_ERR (otherwise 6 RHS at the capped step beat 4 RHS at a shorter one).
+#define SEQ_PROBE_ERR 0.02
+#define SEQ_STAY_ERR 0.25
 
 // ---- kernel parameter block (device pointers into caller buffers + engine scratch)
 struct SolveParams {
@@ -145,6 +164,90 @@ __device__ __forceinline__ cplx block_sum_c(cplx v, double* scratch) {
   double r = block_sum(v.x, scratch);
   double i = block_sum(v.y, scratch);
   return cmake(r, i);
+}
+
+// ---- per-trajectory step controller, shared by every integration kernel so that they take
+// identical decisions.  All members are CTA-uniform.
+struct StepCtl {
+  double t, h;
+  int pair;            // 0: DP5(4), 1: RK4(3)
+  int status, nacc, nrej, nrhs;
+  int probe_wait, probe_backoff;
+  bool have_k1, prev_rejected;
+};
+
+__device__ __forceinline__ void ctl_init(StepCtl& c, const SolveParams& p) {
+  c.t = p.t0 + p.dt * (double)p.out_idx[0];
+  c.h = p.first_step > 0 ? p.first_step : p.dt;
+  if (p.max_step > 0 && c.h > p.max_step) c.h = p.max_step;
+  c.pair = 0;
+  c.status = SEQ_STATUS_OK;
+  c.nacc = c.nrej = c.nrhs = 0;
+  c.probe_wait = 0;
+  c.probe_backoff = 1;
+  c.have_k1 = false;
+  c.prev_rejected = false;
+}
+
+// Next trial step towards t_target.  Returns false when the target is reached.
+// `capped`: the step is limited by max_step / the output grid, not by the error controller.
+__device__ __forceinline__ bool ctl_next(const StepCtl& c, const SolveParams& p, double t_target, double& htry,
+                                         bool& landing, bool& capped) {
+  double rem = t_target - c.t;
+  if (rem <= 1e-13 * fmax(1.0, fabs(t_target))) return false;
+  htry = c.h;
+  if (p.max_step > 0 && htry > p.max_step) htry = p.max_step;
+  double q = ceil(rem / htry - 1e-9);
+  if (q < 1.0) q = 1.0;
+  htry = rem / q;
+  landing = (q == 1.0);
+  capped = c.h > htry * (1.0 + 1e-9) || (p.max_step > 0 && c.h >= p.max_step);
+  return true;
+}
+
+// Accept/reject and choose the next step size and pair.  Returns true if the step was accepted.
+__device__ __forceinline__ bool ctl_update(StepCtl& c, const SolveParams& p, double err, double htry, bool landing,
+                                           bool capped, double t_target, int& nst) {
+  if (!(err == err) || isinf(err)) { c.status = SEQ_STATUS_NONFINITE; return false; }
+  const bool switching = !(p.flags & SEQ_FLAG_NO_ORDER_SWITCH);
+  bool accepted;
+  if (err <= 1.0) {
+    double factor = (err == 0.0) ? SEQ_MAX_FACTOR : fmin(SEQ_MAX_FACTOR, SEQ_SAFETY * pow(err, RK_EXPO[c.pair]));
+    if (c.prev_rejected) factor = fmin(1.0, factor);
+    c.prev_rejected = false;
+    c.t = landing ? t_target : c.t + htry;
+    c.nacc++;
+    c.h = htry * factor;
+    if (switching) {
+      if (c.pair == 0) {
+        if (c.probe_wait > 0) c.probe_wait--;
+        if (capped && err <= SEQ_PROBE_ERR && c.probe_wait == 0) c.pair = 1;
+      } else if (capped && err <= SEQ_STAY_ERR) {
+        c.probe_backoff = 1;
+      } else {
+        c.pair = 0;
+        c.probe_backoff = min(2 * c.probe_backoff, 64);
+        c.probe_wait = c.probe_backoff;
+      }
+    }
+    accepted = true;
+  } else {
+    c.nrej++;
+    if (c.pair == 1) {
+      // the low-order probe failed: redo the same step with the 5(4) pair, back off the next probe
+      c.pair = 0;
+      c.probe_backoff = min(2 * c.probe_backoff, 64);
+      c.probe_wait = c.probe_backoff;
+      c.h = htry;
+    } else {
+      c.h = htry * fmax(SEQ_MIN_FACTOR, SEQ_SAFETY * pow(err, RK_EXPO[0]));
+      c.prev_rejected = true;
+    }
+    accepted = false;
+  }
+  if (++nst > p.nsteps) c.status = SEQ_STATUS_MAX_STEPS;
+  else if (c.h < 1e-14 * fmax(1.0, fabs(c.t))) c.status = SEQ_STATUS_STEP_UNDERFLOW;
+  return accepted;
 }
 
 }  // namespace seq

@@ -161,19 +161,39 @@ __device__ __forceinline__ void dmma_rhs(const SolveParams& p, const DmmaExtra& 
     s.cval[m] = v;
   }
   __syncthreads();  // cval visible; also: every warp finished the previous RHS (X0/T free), Y written
-  // G(t) = G0 + sum_m c_m Gk[m]  -> X0 (flat elementwise over the padded planar image)
+  // G(t) = G0 + sum_m c_m Gk[m]  -> X0 (flat elementwise over the padded planar image).
+  // Operator-outer / chunk-inner with the chunk loop unrolled: CH independent 16-byte L2 loads
+  // are in flight per operator instead of one dependent load per element.
   {
+    constexpr int NCHUNK = C::MAT / 2;                                   // double2 chunks
+    constexpr int CH = (NCHUNK + C::NTHREADS - 1) / C::NTHREADS;           // chunks per thread
+    double2 acc[CH];
     const double2* g0 = reinterpret_cast<const double2*>(x.G0p);
-    double2* dst = reinterpret_cast<double2*>(s.X0);
-    for (int c = s.tid; c < C::MAT / 2; c += C::NTHREADS) {
-      double2 v = g0[c];
-      for (int m = 0; m < p.n_g; m++) {
-        double2 a = reinterpret_cast<const double2*>(x.Gkp + (long long)m * C::MAT)[c];
-        double cv = s.cval[m];
-        v.x = fma(cv, a.x, v.x);
-        v.y = fma(cv, a.y, v.y);
+#pragma unroll
+    for (int i = 0; i < CH; i++) {
+      int c = s.tid + i * C::NTHREADS;
+      acc[i] = (c < NCHUNK) ? g0[c] : make_double2(0.0, 0.0);
+    }
+    for (int m = 0; m < p.n_g; m++) {
+      const double2* gm = reinterpret_cast<const double2*>(x.Gkp + (long long)m * C::MAT);
+      const double cv = s.cval[m];
+      double2 a[CH];
+#pragma unroll
+      for (int i = 0; i < CH; i++) {
+        int c = s.tid + i * C::NTHREADS;
+        a[i] = (c < NCHUNK) ? gm[c] : make_double2(0.0, 0.0);
       }
-      dst[c] = v;
+#pragma unroll
+      for (int i = 0; i < CH; i++) {
+        acc[i].x = fma(cv, a[i].x, acc[i].x);
+        acc[i].y = fma(cv, a[i].y, acc[i].y);
+      }
+    }
+    double2* dst = reinterpret_cast<double2*>(s.X0);
+#pragma unroll
+    for (int i = 0; i < CH; i++) {
+      int c = s.tid + i * C::NTHREADS;
+      if (c < NCHUNK) dst[c] = acc[i];
     }
   }
   __syncthreads();
@@ -282,97 +302,97 @@ solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       SLOT(dst, t, 1) = make_double2(v[t][1][0], v[t][1][1]);
     }
   };
-  // v = y + h * sum_j a_j k_j  (thread-private)
+  // v = y + h * sum_j a_j k_j  (thread-private).  Stream-outer / slot-inner: the 2*TW loads of one
+  // stream are independent and issued together.
   auto combine = [&](double (&v)[C::TW][2][2], double h, int n, const double* __restrict__ a, double2* const* ks) {
+    double2 acc[C::TW][2];
+#pragma unroll
+    for (int t = 0; t < C::TW; t++) { acc[t][0] = make_double2(0.0, 0.0); acc[t][1] = make_double2(0.0, 0.0); }
+    for (int j = 0; j < n; j++) {
+      const double aj = a[j];
+      const double2* kj = ks[j];
+      double2 kv[C::TW][2];
+#pragma unroll
+      for (int t = 0; t < C::TW; t++) { kv[t][0] = SLOT(kj, t, 0); kv[t][1] = SLOT(kj, t, 1); }
+#pragma unroll
+      for (int t = 0; t < C::TW; t++)
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+          acc[t][pl].x = fma(aj, kv[t][pl].x, acc[t][pl].x);
+          acc[t][pl].y = fma(aj, kv[t][pl].y, acc[t][pl].y);
+        }
+    }
 #pragma unroll
     for (int t = 0; t < C::TW; t++)
 #pragma unroll
       for (int pl = 0; pl < 2; pl++) {
-        double2 acc = make_double2(0.0, 0.0);
-        for (int j = 0; j < n; j++) {
-          double2 kv = SLOT(ks[j], t, pl);
-          acc.x = fma(a[j], kv.x, acc.x);
-          acc.y = fma(a[j], kv.y, acc.y);
-        }
         double2 y0 = SLOT(sy, t, pl);
-        v[t][pl][0] = fma(h, acc.x, y0.x);
-        v[t][pl][1] = fma(h, acc.y, y0.y);
+        v[t][pl][0] = fma(h, acc[t][pl].x, y0.x);
+        v[t][pl][1] = fma(h, acc[t][pl].y, y0.y);
       }
   };
 
-  int status = SEQ_STATUS_OK, nacc = 0, nrej = 0, nrhs = 0;
-  double t = p.t0 + p.dt * (double)p.out_idx[0];
-  double h = p.first_step > 0 ? p.first_step : p.dt;
-  if (p.max_step > 0 && h > p.max_step) h = p.max_step;
-  bool have_k1 = false, prev_rejected = false;
+  StepCtl ctl;
+  ctl_init(ctl, p);
   double K[C::TW][2][2];
 
   for (int o = 0; o < p.n_out; o++) {
     if (o > 0) {
       const double t_target = p.t0 + p.dt * (double)p.out_idx[o];
       int nst = 0;
-      while (true) {
-        double rem = t_target - t;
-        if (rem <= 1e-13 * fmax(1.0, fabs(t_target))) break;
-        double htry = h;
-        if (p.max_step > 0 && htry > p.max_step) htry = p.max_step;
-        double q = ceil(rem / htry - 1e-9);
-        if (q < 1.0) q = 1.0;
-        htry = rem / q;
-        const bool landing = (q == 1.0);
-        double v[C::TW][2][2];
-        for (int st = have_k1 ? 1 : 0; st < 7; st++) {
-          combine(v, htry, st, DP_TAB_A[st], kp);      // st == 6: v = y_new
+      double htry;
+      bool landing, capped;
+      while (ctl.status == SEQ_STATUS_OK && ctl_next(ctl, p, t_target, htry, landing, capped)) {
+        const int pair = ctl.pair, S = RK_STAGES[pair];
+        for (int st = ctl.have_k1 ? 1 : 0; st < S; st++) {
+          double v[C::TW][2][2];
+          combine(v, htry, st, RK_A[pair][st], kp);    // st == S-1: v = y_new
           __syncthreads();                             // every warp is out of the previous RHS
           put_Y(v);
-          if (st == 6) store_stream(syn, v);
-          dmma_rhs<NT>(p, x, s, t + DP_TAB_C[st] * htry, tabc, tabr, cscale, K);
+          if (st == S - 1) store_stream(syn, v);
+          dmma_rhs<NT>(p, x, s, ctl.t + RK_C[pair][st] * htry, tabc, tabr, cscale, K);
           store_stream(kp[st], K);
-          nrhs++;
+          ctl.nrhs++;
         }
-        have_k1 = true;
-        // error estimate (thread-private), RMS over the N*N physical elements
+        ctl.have_k1 = true;
+        // error estimate (thread-private streams), RMS over the N*N physical elements
         double es = 0.0;
+        {
+          double2 e[C::TW][2];
 #pragma unroll
-        for (int tt = 0; tt < C::TW; tt++) {
-          double e[2][2];
+          for (int tt = 0; tt < C::TW; tt++) { e[tt][0] = make_double2(0.0, 0.0); e[tt][1] = make_double2(0.0, 0.0); }
+          for (int j = 0; j < S; j++) {
+            const double ej = RK_E[pair][j];
+            const double2* kj = kp[j];
+            double2 kv[C::TW][2];
 #pragma unroll
-          for (int pl = 0; pl < 2; pl++) {
-            double2 a1 = SLOT(kp[0], tt, pl), a3 = SLOT(kp[2], tt, pl), a4 = SLOT(kp[3], tt, pl), a5 = SLOT(kp[4], tt, pl), a6 = SLOT(kp[5], tt, pl);
-            e[pl][0] = htry * (DP_E1 * a1.x + DP_E3 * a3.x + DP_E4 * a4.x + DP_E5 * a5.x + DP_E6 * a6.x + DP_E7 * K[tt][pl][0]);
-            e[pl][1] = htry * (DP_E1 * a1.y + DP_E3 * a3.y + DP_E4 * a4.y + DP_E5 * a5.y + DP_E6 * a6.y + DP_E7 * K[tt][pl][1]);
+            for (int tt = 0; tt < C::TW; tt++) { kv[tt][0] = SLOT(kj, tt, 0); kv[tt][1] = SLOT(kj, tt, 1); }
+#pragma unroll
+            for (int tt = 0; tt < C::TW; tt++)
+#pragma unroll
+              for (int pl = 0; pl < 2; pl++) {
+                e[tt][pl].x = fma(ej, kv[tt][pl].x, e[tt][pl].x);
+                e[tt][pl].y = fma(ej, kv[tt][pl].y, e[tt][pl].y);
+              }
           }
-          double2 yr = SLOT(sy, tt, 0), yi = SLOT(sy, tt, 1);
 #pragma unroll
-          for (int c = 0; c < 2; c++) {
-            double y2 = c ? (yr.y * yr.y + yi.y * yi.y) : (yr.x * yr.x + yi.x * yi.x);
-            double n2 = v[tt][0][c] * v[tt][0][c] + v[tt][1][c] * v[tt][1][c];
-            double sc = p.atol + p.rtol * sqrt(fmax(y2, n2));
-            es += (e[0][c] * e[0][c] + e[1][c] * e[1][c]) / (sc * sc);
+          for (int tt = 0; tt < C::TW; tt++) {
+            double2 yr = SLOT(sy, tt, 0), yi = SLOT(sy, tt, 1), nr = SLOT(syn, tt, 0), ni = SLOT(syn, tt, 1);
+            double sc0 = p.atol + p.rtol * sqrt(fmax(yr.x * yr.x + yi.x * yi.x, nr.x * nr.x + ni.x * ni.x));
+            double sc1 = p.atol + p.rtol * sqrt(fmax(yr.y * yr.y + yi.y * yi.y, nr.y * nr.y + ni.y * ni.y));
+            double e0 = htry * htry * (e[tt][0].x * e[tt][0].x + e[tt][1].x * e[tt][1].x);
+            double e1 = htry * htry * (e[tt][0].y * e[tt][0].y + e[tt][1].y * e[tt][1].y);
+            es += e0 / (sc0 * sc0) + e1 / (sc1 * sc1);
           }
         }
         es = block_sum(es, s.red);
         double err = sqrt(es / (double)(N * N));
-        if (!(err == err) || isinf(err)) { status = SEQ_STATUS_NONFINITE; break; }
-        double factor;
-        if (err <= 1.0) {
-          factor = (err == 0.0) ? SEQ_MAX_FACTOR : fmin(SEQ_MAX_FACTOR, SEQ_SAFETY * pow(err, -0.2));
-          if (prev_rejected) factor = fmin(1.0, factor);
-          prev_rejected = false;
+        if (ctl_update(ctl, p, err, htry, landing, capped, t_target, nst)) {
           double2* tmp = sy; sy = syn; syn = tmp;
-          tmp = kp[0]; kp[0] = kp[6]; kp[6] = tmp;
-          t = landing ? t_target : t + htry;
-          nacc++;
-        } else {
-          factor = fmax(SEQ_MIN_FACTOR, SEQ_SAFETY * pow(err, -0.2));
-          prev_rejected = true;
-          nrej++;
+          tmp = kp[0]; kp[0] = kp[S - 1]; kp[S - 1] = tmp;
         }
-        h = htry * factor;
-        if (++nst > p.nsteps) { status = SEQ_STATUS_MAX_STEPS; break; }
-        if (h < 1e-14 * fmax(1.0, fabs(t))) { status = SEQ_STATUS_STEP_UNDERFLOW; break; }
       }
-      if (status != SEQ_STATUS_OK) break;
+      if (ctl.status != SEQ_STATUS_OK) break;
     }
     // ---- outputs at sample o (thread-private reads of the y stream)
 #pragma unroll
@@ -419,10 +439,10 @@ solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
     }
   }
   if (tid == 0) {
-    p.status[b] = status;
-    p.stats[b * 4 + 0] = nacc;
-    p.stats[b * 4 + 1] = nrej;
-    p.stats[b * 4 + 2] = nrhs;
+    p.status[b] = ctl.status;
+    p.stats[b * 4 + 0] = ctl.nacc;
+    p.stats[b * 4 + 1] = ctl.nrej;
+    p.stats[b * 4 + 2] = ctl.nrhs;
     p.stats[b * 4 + 3] = 0;
   }
 #undef SLOT

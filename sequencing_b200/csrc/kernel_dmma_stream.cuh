@@ -121,27 +121,39 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
 
   // Yb <- y + h sum_j a_j k_j (thread-private streams -> own positions of the block images);
   // optionally also keep the result in the stream `keep` (y_new)
-  auto stage_state = [&](double h, int n, const double* a, double2* const* ks, double2* keep) {
-    for (int q = 0; q < 4; q++)
+  auto stage_state = [&](double h, int n, const double* __restrict__ a, double2* const* ks, double2* keep) {
+    for (int q = 0; q < 4; q++) {
+      double2 acc[C::TW][2];
+#pragma unroll
+      for (int t = 0; t < C::TW; t++) { acc[t][0] = make_double2(0.0, 0.0); acc[t][1] = make_double2(0.0, 0.0); }
+      for (int j = 0; j < n; j++) {
+        const double aj = a[j];
+        const double2* kj = ks[j];
+        double2 kv[C::TW][2];
+#pragma unroll
+        for (int t = 0; t < C::TW; t++) { kv[t][0] = QSLOT(kj, q, t, 0); kv[t][1] = QSLOT(kj, q, t, 1); }
+#pragma unroll
+        for (int t = 0; t < C::TW; t++)
+#pragma unroll
+          for (int pl = 0; pl < 2; pl++) {
+            acc[t][pl].x = fma(aj, kv[t][pl].x, acc[t][pl].x);
+            acc[t][pl].y = fma(aj, kv[t][pl].y, acc[t][pl].y);
+          }
+      }
 #pragma unroll
       for (int t = 0; t < C::TW; t++) {
         double2 v[2];
 #pragma unroll
         for (int pl = 0; pl < 2; pl++) {
-          double2 acc = make_double2(0.0, 0.0);
-          for (int j = 0; j < n; j++) {
-            double2 kv = QSLOT(ks[j], q, t, pl);
-            acc.x = fma(a[j], kv.x, acc.x);
-            acc.y = fma(a[j], kv.y, acc.y);
-          }
           double2 y0 = QSLOT(sy, q, t, pl);
-          v[pl] = make_double2(fma(h, acc.x, y0.x), fma(h, acc.y, y0.y));
+          v[pl] = make_double2(fma(h, acc[t][pl].x, y0.x), fma(h, acc[t][pl].y, y0.y));
           if (keep) QSLOT(keep, q, t, pl) = v[pl];
         }
         double* dst = Yb + q * S::BLK + blk_off(t);
         *reinterpret_cast<double2*>(dst) = v[0];
         *reinterpret_cast<double2*>(dst + C::PLANE) = v[1];
       }
+    }
   };
 
   // kout (thread-private stream) <- RHS(t, Yb)
@@ -159,17 +171,34 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
     }
     __syncthreads();   // cval visible; Yb complete; every warp is out of the previous RHS
     {
+      // G(t) = G0 + sum_m c_m Gk[m] over the block images, 8 independent 16-byte loads in flight
       const double2* g0 = reinterpret_cast<const double2*>(x.G0p);
       double2* dst = reinterpret_cast<double2*>(Gb);
-      for (int c = tid; c < S::FULL / 2; c += S::NTHREADS) {
-        double2 v = g0[c];
-        for (int m = 0; m < p.n_g; m++) {
-          double2 a = reinterpret_cast<const double2*>(x.Gkp + (long long)m * S::FULL)[c];
-          double cv = cval[m];
-          v.x = fma(cv, a.x, v.x);
-          v.y = fma(cv, a.y, v.y);
+      constexpr int NCHUNK = S::FULL / 2, UN = 8;
+      for (int base = tid; base < NCHUNK; base += UN * S::NTHREADS) {
+        double2 acc[UN];
+#pragma unroll
+        for (int i = 0; i < UN; i++) {
+          int c = base + i * S::NTHREADS;
+          acc[i] = (c < NCHUNK) ? g0[c] : make_double2(0.0, 0.0);
         }
-        dst[c] = v;
+        for (int m = 0; m < p.n_g; m++) {
+          const double2* gm = reinterpret_cast<const double2*>(x.Gkp + (long long)m * S::FULL);
+          const double cv = cval[m];
+          double2 a[UN];
+#pragma unroll
+          for (int i = 0; i < UN; i++) {
+            int c = base + i * S::NTHREADS;
+            a[i] = (c < NCHUNK) ? gm[c] : make_double2(0.0, 0.0);
+          }
+#pragma unroll
+          for (int i = 0; i < UN; i++) { acc[i].x = fma(cv, a[i].x, acc[i].x); acc[i].y = fma(cv, a[i].y, acc[i].y); }
+        }
+#pragma unroll
+        for (int i = 0; i < UN; i++) {
+          int c = base + i * S::NTHREADS;
+          if (c < NCHUNK) dst[c] = acc[i];
+        }
       }
     }
     __syncthreads();   // Gb complete
@@ -281,71 +310,61 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
     }
   };
 
-  int status = SEQ_STATUS_OK, nacc = 0, nrej = 0, nrhs = 0;
-  double t = p.t0 + p.dt * (double)p.out_idx[0];
-  double h = p.first_step > 0 ? p.first_step : p.dt;
-  if (p.max_step > 0 && h > p.max_step) h = p.max_step;
-  bool have_k1 = false, prev_rejected = false;
+  StepCtl ctl;
+  ctl_init(ctl, p);
 
   for (int o = 0; o < p.n_out; o++) {
     if (o > 0) {
       const double t_target = p.t0 + p.dt * (double)p.out_idx[o];
       int nst = 0;
-      while (true) {
-        double rem = t_target - t;
-        if (rem <= 1e-13 * fmax(1.0, fabs(t_target))) break;
-        double htry = h;
-        if (p.max_step > 0 && htry > p.max_step) htry = p.max_step;
-        double qn = ceil(rem / htry - 1e-9);
-        if (qn < 1.0) qn = 1.0;
-        htry = rem / qn;
-        const bool landing = (qn == 1.0);
-        for (int st = have_k1 ? 1 : 0; st < 7; st++) {
+      double htry;
+      bool landing, capped;
+      while (ctl.status == SEQ_STATUS_OK && ctl_next(ctl, p, t_target, htry, landing, capped)) {
+        const int pair = ctl.pair, S_ = RK_STAGES[pair];
+        for (int st = ctl.have_k1 ? 1 : 0; st < S_; st++) {
           __syncthreads();
-          stage_state(htry, st, DP_TAB_A[st], kp, st == 6 ? syn : nullptr);
-          rhs(t + DP_TAB_C[st] * htry, kp[st]);
-          nrhs++;
+          stage_state(htry, st, RK_A[pair][st], kp, st == S_ - 1 ? syn : nullptr);
+          rhs(ctl.t + RK_C[pair][st] * htry, kp[st]);
+          ctl.nrhs++;
         }
-        have_k1 = true;
+        ctl.have_k1 = true;
         double es = 0.0;
-        for (int q = 0; q < 4; q++)
+        for (int q = 0; q < 4; q++) {
+          double2 e[C::TW][2];
+#pragma unroll
+          for (int tt = 0; tt < C::TW; tt++) { e[tt][0] = make_double2(0.0, 0.0); e[tt][1] = make_double2(0.0, 0.0); }
+          for (int j = 0; j < S_; j++) {
+            const double ej = RK_E[pair][j];
+            const double2* kj = kp[j];
+            double2 kv[C::TW][2];
+#pragma unroll
+            for (int tt = 0; tt < C::TW; tt++) { kv[tt][0] = QSLOT(kj, q, tt, 0); kv[tt][1] = QSLOT(kj, q, tt, 1); }
+#pragma unroll
+            for (int tt = 0; tt < C::TW; tt++)
+#pragma unroll
+              for (int pl = 0; pl < 2; pl++) {
+                e[tt][pl].x = fma(ej, kv[tt][pl].x, e[tt][pl].x);
+                e[tt][pl].y = fma(ej, kv[tt][pl].y, e[tt][pl].y);
+              }
+          }
 #pragma unroll
           for (int tt = 0; tt < C::TW; tt++) {
-            double2 e[2];
-#pragma unroll
-            for (int pl = 0; pl < 2; pl++) {
-              double2 a1 = QSLOT(kp[0], q, tt, pl), a3 = QSLOT(kp[2], q, tt, pl), a4 = QSLOT(kp[3], q, tt, pl),
-                      a5 = QSLOT(kp[4], q, tt, pl), a6 = QSLOT(kp[5], q, tt, pl), a7 = QSLOT(kp[6], q, tt, pl);
-              e[pl].x = htry * (DP_E1 * a1.x + DP_E3 * a3.x + DP_E4 * a4.x + DP_E5 * a5.x + DP_E6 * a6.x + DP_E7 * a7.x);
-              e[pl].y = htry * (DP_E1 * a1.y + DP_E3 * a3.y + DP_E4 * a4.y + DP_E5 * a5.y + DP_E6 * a6.y + DP_E7 * a7.y);
-            }
             double2 yr = QSLOT(sy, q, tt, 0), yi = QSLOT(sy, q, tt, 1), nr = QSLOT(syn, q, tt, 0), ni = QSLOT(syn, q, tt, 1);
             double sc0 = p.atol + p.rtol * sqrt(fmax(yr.x * yr.x + yi.x * yi.x, nr.x * nr.x + ni.x * ni.x));
             double sc1 = p.atol + p.rtol * sqrt(fmax(yr.y * yr.y + yi.y * yi.y, nr.y * nr.y + ni.y * ni.y));
-            es += (e[0].x * e[0].x + e[1].x * e[1].x) / (sc0 * sc0) + (e[0].y * e[0].y + e[1].y * e[1].y) / (sc1 * sc1);
+            double e0 = htry * htry * (e[tt][0].x * e[tt][0].x + e[tt][1].x * e[tt][1].x);
+            double e1 = htry * htry * (e[tt][0].y * e[tt][0].y + e[tt][1].y * e[tt][1].y);
+            es += e0 / (sc0 * sc0) + e1 / (sc1 * sc1);
           }
+        }
         es = block_sum(es, red);
         double err = sqrt(es / (double)(N * N));
-        if (!(err == err) || isinf(err)) { status = SEQ_STATUS_NONFINITE; break; }
-        double factor;
-        if (err <= 1.0) {
-          factor = (err == 0.0) ? SEQ_MAX_FACTOR : fmin(SEQ_MAX_FACTOR, SEQ_SAFETY * pow(err, -0.2));
-          if (prev_rejected) factor = fmin(1.0, factor);
-          prev_rejected = false;
+        if (ctl_update(ctl, p, err, htry, landing, capped, t_target, nst)) {
           double2* tmp = sy; sy = syn; syn = tmp;
-          tmp = kp[0]; kp[0] = kp[6]; kp[6] = tmp;
-          t = landing ? t_target : t + htry;
-          nacc++;
-        } else {
-          factor = fmax(SEQ_MIN_FACTOR, SEQ_SAFETY * pow(err, -0.2));
-          prev_rejected = true;
-          nrej++;
+          tmp = kp[0]; kp[0] = kp[S_ - 1]; kp[S_ - 1] = tmp;
         }
-        h = htry * factor;
-        if (++nst > p.nsteps) { status = SEQ_STATUS_MAX_STEPS; break; }
-        if (h < 1e-14 * fmax(1.0, fabs(t))) { status = SEQ_STATUS_STEP_UNDERFLOW; break; }
       }
-      if (status != SEQ_STATUS_OK) break;
+      if (ctl.status != SEQ_STATUS_OK) break;
     }
     for (int e = 0; e < p.n_e; e++) {
       cplx acc = cmake(0, 0);
@@ -389,10 +408,10 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
       }
   }
   if (tid == 0) {
-    p.status[b] = status;
-    p.stats[b * 4 + 0] = nacc;
-    p.stats[b * 4 + 1] = nrej;
-    p.stats[b * 4 + 2] = nrhs;
+    p.status[b] = ctl.status;
+    p.stats[b * 4 + 0] = ctl.nacc;
+    p.stats[b * 4 + 1] = ctl.nrej;
+    p.stats[b * 4 + 2] = ctl.nrhs;
     p.stats[b * 4 + 3] = 0;
   }
 #undef QSLOT

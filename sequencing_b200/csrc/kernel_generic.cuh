@@ -177,13 +177,9 @@ __global__ void solve_generic_kernel(const __grid_constant__ SolveParams p) {
   c.T = ws; ws += N2;
   cplx* y = ws; ws += c.NN;
   cplx* ys = ws; ws += c.NN;
-  cplx* k1 = ws; ws += c.NN;
-  cplx* k2 = ws; ws += c.NN;
-  cplx* k3 = ws; ws += c.NN;
-  cplx* k4 = ws; ws += c.NN;
-  cplx* k5 = ws; ws += c.NN;
-  cplx* k6 = ws; ws += c.NN;
-  cplx* k7 = ws; ws += c.NN;
+  cplx* kk[7];
+#pragma unroll
+  for (int j = 0; j < 7; j++) { kk[j] = ws; ws += c.NN; }
   const int NN = c.NN;
   const int tid = threadIdx.x, nth = blockDim.x;
 
@@ -191,110 +187,68 @@ __global__ void solve_generic_kernel(const __grid_constant__ SolveParams p) {
   for (int i = tid; i < NN; i += nth) y[i] = y0[i];
   __syncthreads();
 
-  int status = SEQ_STATUS_OK, nacc = 0, nrej = 0, nrhs = 0;
-  double t = p.t0 + p.dt * (double)p.out_idx[0];
-  double h = p.first_step > 0 ? p.first_step : p.dt;
-  if (p.max_step > 0 && h > p.max_step) h = p.max_step;
-  bool have_k1 = false, prev_rejected = false;
-
-  for (int o = 0; o < p.n_out && status == SEQ_STATUS_OK; o++) {
+  StepCtl ctl;
+  ctl_init(ctl, p);
+  for (int o = 0; o < p.n_out && ctl.status == SEQ_STATUS_OK; o++) {
     if (o > 0) {
       const double t_target = p.t0 + p.dt * (double)p.out_idx[o];
       int nst = 0;
-      while (true) {
-        double rem = t_target - t;
-        if (rem <= 1e-13 * fmax(1.0, fabs(t_target))) break;
-        double htry = h;
-        if (p.max_step > 0 && htry > p.max_step) htry = p.max_step;
-        double q = ceil(rem / htry - 1e-9);
-        if (q < 1.0) q = 1.0;
-        htry = rem / q;
-        const bool landing = (q == 1.0);
-        if (!have_k1) { rhs<KET>(c, t, y, k1); nrhs++; have_k1 = true; }
-        for (int i = tid; i < NN; i += nth) {
-          cplx v = y[i], a = k1[i];
-          ys[i] = cmake(fma(htry * DP_A21, a.x, v.x), fma(htry * DP_A21, a.y, v.y));
+      double htry;
+      bool landing, capped;
+      while (ctl.status == SEQ_STATUS_OK && ctl_next(ctl, p, t_target, htry, landing, capped)) {
+        const int pair = ctl.pair, S = RK_STAGES[pair];
+        for (int st = ctl.have_k1 ? 1 : 0; st < S; st++) {
+          // stage input ys = y + h sum_j a_j k_j   (st == S-1: ys = y_new)
+          for (int i = tid; i < NN; i += nth) {
+            double ax = 0.0, ay = 0.0;
+            for (int j = 0; j < st; j++) {
+              double aj = RK_A[pair][st][j];
+              cplx kv = kk[j][i];
+              ax = fma(aj, kv.x, ax);
+              ay = fma(aj, kv.y, ay);
+            }
+            cplx v = y[i];
+            ys[i] = cmake(fma(htry, ax, v.x), fma(htry, ay, v.y));
+          }
+          __syncthreads();
+          rhs<KET>(c, ctl.t + RK_C[pair][st] * htry, ys, kk[st]);
+          ctl.nrhs++;
         }
-        __syncthreads();
-        rhs<KET>(c, t + DP_C2 * htry, ys, k2);
-        for (int i = tid; i < NN; i += nth) {
-          cplx v = y[i], a = k1[i], b2 = k2[i];
-          ys[i] = cmake(v.x + htry * (DP_A31 * a.x + DP_A32 * b2.x), v.y + htry * (DP_A31 * a.y + DP_A32 * b2.y));
-        }
-        __syncthreads();
-        rhs<KET>(c, t + DP_C3 * htry, ys, k3);
-        for (int i = tid; i < NN; i += nth) {
-          cplx v = y[i], a = k1[i], b2 = k2[i], b3 = k3[i];
-          ys[i] = cmake(v.x + htry * (DP_A41 * a.x + DP_A42 * b2.x + DP_A43 * b3.x),
-                        v.y + htry * (DP_A41 * a.y + DP_A42 * b2.y + DP_A43 * b3.y));
-        }
-        __syncthreads();
-        rhs<KET>(c, t + DP_C4 * htry, ys, k4);
-        for (int i = tid; i < NN; i += nth) {
-          cplx v = y[i], a = k1[i], b2 = k2[i], b3 = k3[i], b4 = k4[i];
-          ys[i] = cmake(v.x + htry * (DP_A51 * a.x + DP_A52 * b2.x + DP_A53 * b3.x + DP_A54 * b4.x),
-                        v.y + htry * (DP_A51 * a.y + DP_A52 * b2.y + DP_A53 * b3.y + DP_A54 * b4.y));
-        }
-        __syncthreads();
-        rhs<KET>(c, t + DP_C5 * htry, ys, k5);
-        for (int i = tid; i < NN; i += nth) {
-          cplx v = y[i], a = k1[i], b2 = k2[i], b3 = k3[i], b4 = k4[i], b5 = k5[i];
-          ys[i] = cmake(v.x + htry * (DP_A61 * a.x + DP_A62 * b2.x + DP_A63 * b3.x + DP_A64 * b4.x + DP_A65 * b5.x),
-                        v.y + htry * (DP_A61 * a.y + DP_A62 * b2.y + DP_A63 * b3.y + DP_A64 * b4.y + DP_A65 * b5.y));
-        }
-        __syncthreads();
-        rhs<KET>(c, t + htry, ys, k6);
-        for (int i = tid; i < NN; i += nth) {
-          cplx v = y[i], a = k1[i], b3 = k3[i], b4 = k4[i], b5 = k5[i], b6 = k6[i];
-          ys[i] = cmake(v.x + htry * (DP_B1 * a.x + DP_B3 * b3.x + DP_B4 * b4.x + DP_B5 * b5.x + DP_B6 * b6.x),
-                        v.y + htry * (DP_B1 * a.y + DP_B3 * b3.y + DP_B4 * b4.y + DP_B5 * b5.y + DP_B6 * b6.y));
-        }
-        __syncthreads();
-        rhs<KET>(c, t + htry, ys, k7);
-        nrhs += 6;
+        ctl.have_k1 = true;
         // error estimate, RMS norm scaled by atol + rtol*max(|y|,|y_new|)  (ZVODE's weighted RMS norm)
         double es = 0.0;
         for (int i = tid; i < NN; i += nth) {
-          cplx a = k1[i], b3 = k3[i], b4 = k4[i], b5 = k5[i], b6 = k6[i], b7 = k7[i];
-          double ex = htry * (DP_E1 * a.x + DP_E3 * b3.x + DP_E4 * b4.x + DP_E5 * b5.x + DP_E6 * b6.x + DP_E7 * b7.x);
-          double ey = htry * (DP_E1 * a.y + DP_E3 * b3.y + DP_E4 * b4.y + DP_E5 * b5.y + DP_E6 * b6.y + DP_E7 * b7.y);
+          double ex = 0.0, ey = 0.0;
+          for (int j = 0; j < S; j++) {
+            double ej = RK_E[pair][j];
+            cplx kv = kk[j][i];
+            ex = fma(ej, kv.x, ex);
+            ey = fma(ej, kv.y, ey);
+          }
+          ex *= htry; ey *= htry;
           double sc = p.atol + p.rtol * sqrt(fmax(cabs2(y[i]), cabs2(ys[i])));
           es += (ex * ex + ey * ey) / (sc * sc);
         }
         es = block_sum(es, c.red);
         double err = sqrt(es / (double)NN);
-        if (!(err == err) || isinf(err)) { status = SEQ_STATUS_NONFINITE; break; }
-        double factor;
-        if (err <= 1.0) {
-          factor = (err == 0.0) ? SEQ_MAX_FACTOR : fmin(SEQ_MAX_FACTOR, SEQ_SAFETY * pow(err, -0.2));
-          if (prev_rejected) factor = fmin(1.0, factor);
-          prev_rejected = false;
+        if (ctl_update(ctl, p, err, htry, landing, capped, t_target, nst)) {
           cplx* tmp = y; y = ys; ys = tmp;
-          tmp = k1; k1 = k7; k7 = tmp;
-          t = landing ? t_target : t + htry;
-          nacc++;
-        } else {
-          factor = fmax(SEQ_MIN_FACTOR, SEQ_SAFETY * pow(err, -0.2));
-          prev_rejected = true;
-          nrej++;
+          tmp = kk[0]; kk[0] = kk[S - 1]; kk[S - 1] = tmp;
         }
-        h = htry * factor;
-        if (++nst > p.nsteps) { status = SEQ_STATUS_MAX_STEPS; break; }
-        if (h < 1e-14 * fmax(1.0, fabs(t))) { status = SEQ_STATUS_STEP_UNDERFLOW; break; }
       }
-      if (status != SEQ_STATUS_OK) break;
+      if (ctl.status != SEQ_STATUS_OK) break;
     }
-    if (KET && (p.flags & SEQ_FLAG_NORMALIZE)) have_k1 = false;  // state is rescaled below
+    if (KET && (p.flags & SEQ_FLAG_NORMALIZE)) ctl.have_k1 = false;  // state is rescaled below
     emit_output<KET>(c, o, y);
     __syncthreads();
   }
   cplx* fin = p.final_state + (long long)c.b * NN;
   for (int i = tid; i < NN; i += nth) fin[i] = y[i];
   if (tid == 0) {
-    p.status[c.b] = status;
-    p.stats[c.b * 4 + 0] = nacc;
-    p.stats[c.b * 4 + 1] = nrej;
-    p.stats[c.b * 4 + 2] = nrhs;
+    p.status[c.b] = ctl.status;
+    p.stats[c.b * 4 + 0] = ctl.nacc;
+    p.stats[c.b * 4 + 1] = ctl.nrej;
+    p.stats[c.b * 4 + 2] = ctl.nrhs;
     p.stats[c.b * 4 + 3] = 0;
   }
 }

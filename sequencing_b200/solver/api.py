@@ -53,12 +53,13 @@ class Options:
         self.normalize_output = normalize_output
         self.rhs_reuse = rhs_reuse
         self.kernel_method = _lib.METHOD_AUTO  # engine-specific: force a kernel (tests)
+        self.order_switch = True               # engine-specific: allow the RK4(3) pair on capped steps
         for key, val in ignored.items():
             setattr(self, key, val)
 
     def _key(self):
         return (self.atol, self.rtol, self.nsteps, self.first_step, self.max_step, self.min_step,
-                bool(self.normalize_output), int(self.kernel_method))
+                bool(self.normalize_output), int(self.kernel_method), bool(getattr(self, 'order_switch', True)))
 
 
 def rhs_clear():
@@ -245,6 +246,7 @@ def _to_batch(items: Sequence[_Lowered]) -> BatchProblem:
         store_states=first.store_states, expect_complex=not all(first.e_real),
         atol=opt.atol, rtol=opt.rtol, max_step=opt.max_step or 0.0, first_step=opt.first_step or 0.0,
         min_step=opt.min_step or 0.0, nsteps=int(opt.nsteps), method=int(opt.kernel_method),
+        order_switch=bool(getattr(opt, 'order_switch', True)),
     )
 
 

@@ -40,6 +40,7 @@ class BatchProblem:
     min_step: float = 0.0
     nsteps: int = 1000
     method: int = _lib.METHOD_AUTO
+    order_switch: bool = True           # let the controller drop to the 4-stage RK4(3) pair on capped steps
 
     @property
     def N(self):
@@ -122,6 +123,8 @@ class Engine:
             flags |= _lib.FLAG_STORE_STATES
         if bp.expect_complex:
             flags |= _lib.FLAG_EXPECT_COMPLEX
+        if not bp.order_switch:
+            flags |= _lib.FLAG_NO_ORDER_SWITCH
         if host:
             flags |= _lib.FLAG_HOST_POINTERS
         d.flags = flags

@@ -12,7 +12,7 @@ def run(name, bp, nb=2):
     for tag, (a, r) in {"def": (1e-8, 1e-6), "tight": (1e-10, 1e-8), "vtight": (1e-12, 1e-10)}.items():
         q = copy.copy(bp); q.atol, q.rtol = a, r
         outs[tag] = eng.solve(q)
-        print(name, tag, "gpu steps", outs[tag].stats[:nb, :2].tolist(), "ms", outs[tag].kernel_ms)
+        print(name, tag, "gpu steps/rhs", outs[tag].stats[:nb, :3].tolist(), "ms", outs[tag].kernel_ms)
     for b in range(nb):
         refs = {}
         for tag, (a, r) in {"def": (1e-8, 1e-6), "tight": (1e-10, 1e-8), "vtight": (1e-13, 1e-11)}.items():
