@@ -18,7 +18,7 @@
 //
 // RHS (rho Hermitian):  A = -i G rho,  G = H(t) - (i/2) sum_l r_l L_l^dag L_l
 //                       rho' = A + A^dag + sum_l r_l L_l rho L_l^dag
-// = (1 + 2 n_l) complex NP^3 products, each 4 real DMMA chains.
+// = (1 + 2 n_l) complex NP^3 products, each 3 real DMMA chains (Karatsuba form, see warp_gemm).
 #pragma once
 #include "common.cuh"
 
@@ -97,38 +97,56 @@ struct DmmaState {
   int tid, w, lane, g, tg, tr, tc0;
 };
 
-// acc += A(rows of tile-row tr) * B(cols of this warp's strip), A and B planar in shared memory
+// acc += A(rows of tile-row tr) * B(cols of this warp's strip), A and B planar in shared memory.
+// Complex product with THREE real DMMA chains per tile-step (Gauss/Karatsuba) instead of four:
+//   P1 = Ar Br, P2 = Ai Bi, P3 = (Ar+Ai)(Br+Bi)      ->  Cr = P1 - P2,  Ci = P3 - P1 - P2
+//   B = conj(L)^T:            P3 = (Ar+Ai)(Lr-Li)      ->  Cr = P1 + P2,  Ci = P3 - P1 + P2
+// The operand sums run on the FP64 FMA pipe, which is otherwise idle while the tensor pipe is busy.
 template <int NT, bool BCONJT>
 __device__ __forceinline__ void warp_gemm(double (&acc)[DmmaCfg<NT>::TW][2][2], const double* __restrict__ A,
                                           const double* __restrict__ Bm, int tr, int tc0, int g, int tg) {
   typedef DmmaCfg<NT> C;
   const double* Are = A + (8 * tr + g) * C::LD + tg;
   const double* Aim = Are + C::PLANE;
+  double P[C::TW][3][2];
+#pragma unroll
+  for (int t = 0; t < C::TW; t++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) { P[t][i][0] = 0.0; P[t][i][1] = 0.0; }
 #pragma unroll
   for (int k0 = 0; k0 < C::NP; k0 += 4) {
-    double ar = Are[k0], ai = Aim[k0];
-    double nar = dneg(ar), nai = dneg(ai);
+    const double ar = Are[k0], ai = Aim[k0];
+    const double as = ar + ai;
 #pragma unroll
     for (int t = 0; t < C::TW; t++) {
-      int n0 = 8 * (tc0 + t);
+      const int n0 = 8 * (tc0 + t);
+      double br, bi, bs;
       if (!BCONJT) {
         const double* bp = Bm + (k0 + tg) * C::LD + n0 + g;
-        double br = bp[0], bi = bp[C::PLANE];
-        dmma884(acc[t][0][0], acc[t][0][1], ar, br);
-        dmma884(acc[t][0][0], acc[t][0][1], nai, bi);
-        dmma884(acc[t][1][0], acc[t][1][1], ar, bi);
-        dmma884(acc[t][1][0], acc[t][1][1], ai, br);
+        br = bp[0]; bi = bp[C::PLANE];
+        bs = br + bi;
       } else {
-        // B(k,n) = conj(L[n][k])
-        const double* lp = Bm + (n0 + g) * C::LD + k0 + tg;
-        double lr = lp[0], li = lp[C::PLANE];
-        dmma884(acc[t][0][0], acc[t][0][1], ar, lr);
-        dmma884(acc[t][0][0], acc[t][0][1], ai, li);
-        dmma884(acc[t][1][0], acc[t][1][1], ai, lr);
-        dmma884(acc[t][1][0], acc[t][1][1], nar, li);
+        const double* lp = Bm + (n0 + g) * C::LD + k0 + tg;   // B(k,n) = conj(L[n][k])
+        br = lp[0]; bi = lp[C::PLANE];
+        bs = br - bi;
       }
+      dmma884(P[t][0][0], P[t][0][1], ar, br);
+      dmma884(P[t][1][0], P[t][1][1], ai, bi);
+      dmma884(P[t][2][0], P[t][2][1], as, bs);
     }
   }
+#pragma unroll
+  for (int t = 0; t < C::TW; t++)
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      if (!BCONJT) {
+        acc[t][0][c] += P[t][0][c] - P[t][1][c];
+        acc[t][1][c] += P[t][2][c] - P[t][0][c] - P[t][1][c];
+      } else {
+        acc[t][0][c] += P[t][0][c] + P[t][1][c];
+        acc[t][1][c] += P[t][2][c] - P[t][0][c] + P[t][1][c];
+      }
+    }
 }
 
 template <int NT>
