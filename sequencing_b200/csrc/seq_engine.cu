@@ -267,7 +267,7 @@ static int validate(seq_engine* e, const seq_solve_desc* d) {
 static int pick_method(const seq_engine* e, const seq_solve_desc* d) {
   if (d->method != SEQ_METHOD_AUTO) return d->method;
   const bool ket = d->flags & SEQ_FLAG_KET;
-  if (!ket && small_supported(d->N, d->n_ch + d->n_ctd, d->n_c + d->n_ctd)) return SEQ_METHOD_SMALL;
+  if (!ket && d->H0_batch_stride == 0 && small_supported(d->N, d->n_ch + d->n_ctd, d->n_e)) return SEQ_METHOD_SMALL;
   if (!ket && d->H0_batch_stride == 0 && dmma_supported(d->N, e ? e->max_smem_optin : 232448)) return SEQ_METHOD_DMMA;
   if (!ket && d->H0_batch_stride == 0 && stream_supported(d->N, e ? e->max_smem_optin : 232448)) return SEQ_METHOD_DMMA_STREAM;
   return SEQ_METHOD_GENERIC;
@@ -293,7 +293,7 @@ extern "C" {
 int seq_engine_abi_version(void) { return SEQ_ENGINE_ABI_VERSION; }
 
 const char* seq_engine_build_info(void) {
-  return "seq_engine abi=1 arch=sm_100a kernels=generic(fma),dmma(8x8x4 resident),dmma_stream(8x8x4 blocked),small(registers) built " __DATE__;
+  return "seq_engine abi=1 arch=sm_100a kernels=generic(fma),dmma(8x8x4 resident),dmma_stream(8x8x4 blocked),small(thread-per-trajectory real superoperator) built " __DATE__;
 }
 
 int seq_engine_create(int device, void* stream, seq_engine** out) {
@@ -395,8 +395,8 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   const int method = pick_method(e, d);
   if (method == SEQ_METHOD_DMMA && (ket || !dmma_supported(N, e->max_smem_optin) || d->H0_batch_stride))
     return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_DMMA does not cover N=%d ket=%d h0_stride=%lld", N, (int)ket, (long long)d->H0_batch_stride);
-  if (method == SEQ_METHOD_SMALL && (ket || !small_supported(N, n_g, d->n_c + d->n_ctd)))
-    return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_SMALL does not cover N=%d ket=%d", N, (int)ket);
+  if (method == SEQ_METHOD_SMALL && (ket || d->H0_batch_stride || !small_supported(N, n_g, d->n_e)))
+    return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_SMALL does not cover N=%d ket=%d h0_stride=%lld (density matrices, N <= 6, shared H0)", N, (int)ket, (long long)d->H0_batch_stride);
   if (method == SEQ_METHOD_DMMA_STREAM && (ket || !stream_supported(N, e->max_smem_optin) || d->H0_batch_stride))
     return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_DMMA_STREAM does not cover N=%d ket=%d h0_stride=%lld", N, (int)ket, (long long)d->H0_batch_stride);
   if (method < SEQ_METHOD_GENERIC || method > SEQ_METHOD_DMMA_STREAM)
@@ -419,6 +419,10 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   }
   if (method == SEQ_METHOD_DMMA_STREAM) {
     rc = reserve(e, e->pack, stream_pack_doubles(N, n_g, d->n_c + d->n_ctd, d->n_e) * sizeof(double));
+    if (rc) return rc;
+  }
+  if (method == SEQ_METHOD_SMALL) {
+    rc = reserve(e, e->pack, small_pack_doubles(N, n_g, d->n_e) * sizeof(double));
     if (rc) return rc;
   }
   if (d->coeff_batch_stride && d->coeff_batch_stride != (int64_t)d->n_ch * d->n_t)
@@ -499,9 +503,8 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
     rc = launch_stream(p, G0, Gk, (double*)e->pack.ptr, e->stream, &e->launches);
     if (rc) return fail(e, rc, "streaming DMMA kernel launch configuration failed for N=%d", N);
   } else {
-    rc = launch_small(p, e->sm_count, e->stream);
+    rc = launch_small(p, G0, Gk, (double*)e->pack.ptr, e->sm_count, e->stream, &e->launches);
     if (rc) return fail(e, rc, "small-N kernel launch configuration failed for N=%d", N);
-    e->launches++;
   }
   CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
   e->timed = true;

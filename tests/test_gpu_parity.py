@@ -250,3 +250,58 @@ def test_dmma_all_tile_counts_match_generic(gpu_engine):
         assert np.max(np.abs(oa.states - og.states)) < 1e-13, N
         assert np.max(np.abs(oa.expect - og.expect)) < 1e-13, N
         np.testing.assert_array_equal(oa.stats[:, :2], og.stats[:, :2])
+
+
+def test_small_kernel_all_sizes_match_generic(gpu_engine):
+    """The thread-per-trajectory kernel (N <= 6, real superoperator form) against the FP64-FMA kernel:
+    every N, with/without constant and time-dependent collapse operators, ragged last warp."""
+    for N in (1, 2, 3, 4, 5, 6):
+        for n_c, n_ctd, n_ch in ((2, 0, 2), (0, 0, 1), (1, 2, 2), (0, 1, 0)):
+            mk = lambda: random_problem(N=N, B=70, n_t=12, n_ch=n_ch, n_c=n_c, n_ctd=n_ctd, n_e=2, seed=N, hscale=0.3, store_states=True)
+            a, g = mk(), mk()
+            a.method, g.method = _lib.METHOD_SMALL, _lib.METHOD_GENERIC
+            oa, og = gpu_engine.solve(a), gpu_engine.solve(g)
+            assert oa.method == "small" and og.method == "generic"
+            assert np.all(oa.status == 0)
+            assert np.max(np.abs(oa.states - og.states)) < 1e-13, (N, n_c, n_ctd)
+            assert np.max(np.abs(oa.expect - og.expect)) < 1e-13, (N, n_c, n_ctd)
+            np.testing.assert_array_equal(oa.stats[:, :2], og.stats[:, :2])
+    auto = random_problem(N=4, B=3, n_t=5, n_ch=1, n_c=1, n_e=1, seed=1)
+    assert gpu_engine.solve(auto).method == "small"
+
+
+def test_small_kernel_complex_expect_scale_and_rejections(gpu_engine):
+    """Non-Hermitian e_ops (complex expectation), per-trajectory coeff_scale on a shared table, and an
+    uncapped run whose lanes reject steps at different times (per-lane step control inside a warp)."""
+    rng = np.random.default_rng(3)
+    bp = random_problem(N=3, B=40, n_t=30, n_ch=2, n_c=2, n_e=2, seed=21, hscale=0.6, store_states=True)
+    bp.E = bp.E + 0.3 * (rng.normal(size=bp.E.shape) + 1j * rng.normal(size=bp.E.shape))
+    bp.expect_complex = True
+    bp.coeff = bp.coeff[:1]
+    bp.coeff_scale = rng.uniform(0.2, 3.0, size=(40, 2))
+    bp.max_step = 0.0
+    outs = {}
+    for m in (_lib.METHOD_SMALL, _lib.METHOD_GENERIC):
+        bp.method = m
+        outs[m] = gpu_engine.solve(bp)
+    a, g = outs[_lib.METHOD_SMALL], outs[_lib.METHOD_GENERIC]
+    assert a.method == "small" and np.all(a.status == 0)
+    assert len(set(a.stats[:, 0].tolist())) > 1          # lanes really take different numbers of steps
+    assert np.max(np.abs(a.states - g.states)) < 1e-12
+    assert np.max(np.abs(a.expect - g.expect)) < 1e-12
+    ex = np.einsum("eij,btji->bet", bp.E, a.states)
+    np.testing.assert_allclose(a.expect, ex, atol=1e-13)
+
+
+def test_small_kernel_large_batch_properties(gpu_engine):
+    """C1 at bench size (65536 trajectories): size-independent properties - unit trace, populations in
+    [0, 1], and the sweep is symmetric in the sign of the drive amplitude."""
+    from sequencing_b200 import workloads
+    bp = workloads.c1_rabi(4096)
+    out = gpu_engine.solve(bp)
+    assert out.method == "small" and np.all(out.status == 0)
+    tr = np.einsum("bii->b", out.final_state).real
+    assert np.max(np.abs(tr - 1)) < 1e-9
+    pop = out.expect[:, 0, -1]
+    assert pop.min() > -1e-9 and pop.max() < 1 + 1e-9
+    np.testing.assert_allclose(pop, pop[::-1], atol=1e-9)
