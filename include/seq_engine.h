@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SEQ_ENGINE_ABI_VERSION 1
+#define SEQ_ENGINE_ABI_VERSION 2
 
 /* return codes */
 #define SEQ_OK 0
@@ -67,6 +67,8 @@ extern "C" {
 #define SEQ_METHOD_DMMA 2      /* FP64 tensor-core (DMMA.8x8x4) tiles, rho resident in smem  */
 #define SEQ_METHOD_SMALL 3     /* N <= 8: several trajectories per CTA, state in registers   */
 #define SEQ_METHOD_DMMA_STREAM 4 /* DMMA with operands streamed through smem (N too big to stay resident) */
+#define SEQ_METHOD_LARGE 5     /* one big system (N > 96): every SM works on ONE right-hand side through a
+                                  stream-K DMMA ZGEMM; optionally rho row-sharded over the GPUs of the box */
 
 typedef struct seq_engine seq_engine;
 
@@ -138,6 +140,27 @@ int64_t seq_engine_workspace_bytes(const seq_engine* eng, const seq_solve_desc* 
 
 /* The hot path.  Replaces qutip.mesolve / qutip.sesolve at basic.py:504-512. */
 int seq_engine_solve(seq_engine* eng, const seq_solve_desc* desc);
+
+/*
+ * Row-sharded solve of ONE large system across `world` processes (one per GPU), config C5 of
+ * BASELINE.json (transmon + two cavities, N = 1875).  Every rank passes the SAME descriptor (full
+ * operators, full initial state, full-size output buffers) and gets the full result back; rank r
+ * evaluates rows [r*m, (r+1)*m) of every right-hand side, m = 16*ceil(ceil(N/world)/16).  The stage
+ * state is exchanged once per RHS evaluation through `all_gather`, the error norm once per step
+ * through `all_reduce_sum`; both hooks are called with DEVICE pointers and must enqueue the
+ * collective on the engine's stream (ncclAllGather / ncclAllReduce on that stream, or
+ * torch.distributed on the stream the engine was created with).  `comm == NULL` or world == 1: one GPU.
+ * Replaces: the single qutip.mesolve call of basic.py:504-512 for a system too large for one SM.
+ */
+typedef struct seq_comm {
+  int32_t rank, world;
+  void* ctx;
+  /* recv[r*count .. (r+1)*count) <- rank r's send[0..count)   (doubles) */
+  int (*all_gather)(void* ctx, const double* send, double* recv, int64_t count);
+  /* buf[0..count) <- sum over ranks, in place (doubles) */
+  int (*all_reduce_sum)(void* ctx, double* buf, int64_t count);
+} seq_comm;
+int seq_engine_solve_sharded(seq_engine* eng, const seq_solve_desc* desc, const seq_comm* comm);
 
 /* Method the engine would pick for this descriptor (SEQ_METHOD_*), without running it. */
 int seq_engine_select_method(const seq_engine* eng, const seq_solve_desc* desc);

@@ -176,8 +176,29 @@ struct StepCtl {
   bool have_k1, prev_rejected;
 };
 
-__device__ __forceinline__ void ctl_init(StepCtl& c, const SolveParams& p) {
-  c.t = p.t0 + p.dt * (double)p.out_idx[0];
+// host copies of the tableau for the host-driven large-N stepper (same numbers as RK_A/RK_C/RK_E)
+static const double H_RK_A[2][7][6] = {
+    {{0, 0, 0, 0, 0, 0},
+     {DP_A21, 0, 0, 0, 0, 0},
+     {DP_A31, DP_A32, 0, 0, 0, 0},
+     {DP_A41, DP_A42, DP_A43, 0, 0, 0},
+     {DP_A51, DP_A52, DP_A53, DP_A54, 0, 0},
+     {DP_A61, DP_A62, DP_A63, DP_A64, DP_A65, 0},
+     {DP_B1, 0, DP_B3, DP_B4, DP_B5, DP_B6}},
+    {{0, 0, 0, 0, 0, 0},
+     {1.0 / 3.0, 0, 0, 0, 0, 0},
+     {-1.0 / 3.0, 1.0, 0, 0, 0, 0},
+     {1.0, -1.0, 1.0, 0, 0, 0},
+     {1.0 / 8.0, 3.0 / 8.0, 3.0 / 8.0, 1.0 / 8.0, 0, 0},
+     {0, 0, 0, 0, 0, 0},
+     {0, 0, 0, 0, 0, 0}}};
+static const double H_RK_C[2][7] = {{0.0, DP_C2, DP_C3, DP_C4, DP_C5, 1.0, 1.0}, {0.0, 1.0 / 3.0, 2.0 / 3.0, 1.0, 1.0, 0, 0}};
+static const double H_RK_E[2][7] = {{DP_E1, 0.0, DP_E3, DP_E4, DP_E5, DP_E6, DP_E7},
+                                    {1.0 / 24.0, -1.0 / 8.0, 1.0 / 8.0, 1.0 / 8.0, -1.0 / 6.0, 0, 0}};
+static const int H_RK_STAGES[2] = {7, 5};
+
+__host__ __device__ __forceinline__ void ctl_init_at(StepCtl& c, const SolveParams& p, double t_start) {
+  c.t = t_start;
   c.h = p.first_step > 0 ? p.first_step : p.dt;
   if (p.max_step > 0 && c.h > p.max_step) c.h = p.max_step;
   c.pair = 0;
@@ -188,10 +209,13 @@ __device__ __forceinline__ void ctl_init(StepCtl& c, const SolveParams& p) {
   c.have_k1 = false;
   c.prev_rejected = false;
 }
+__device__ __forceinline__ void ctl_init(StepCtl& c, const SolveParams& p) {
+  ctl_init_at(c, p, p.t0 + p.dt * (double)p.out_idx[0]);
+}
 
 // Next trial step towards t_target.  Returns false when the target is reached.
 // `capped`: the step is limited by max_step / the output grid, not by the error controller.
-__device__ __forceinline__ bool ctl_next(const StepCtl& c, const SolveParams& p, double t_target, double& htry,
+__host__ __device__ __forceinline__ bool ctl_next(const StepCtl& c, const SolveParams& p, double t_target, double& htry,
                                          bool& landing, bool& capped) {
   double rem = t_target - c.t;
   if (rem <= 1e-13 * fmax(1.0, fabs(t_target))) return false;
@@ -206,13 +230,13 @@ __device__ __forceinline__ bool ctl_next(const StepCtl& c, const SolveParams& p,
 }
 
 // Accept/reject and choose the next step size and pair.  Returns true if the step was accepted.
-__device__ __forceinline__ bool ctl_update(StepCtl& c, const SolveParams& p, double err, double htry, bool landing,
+__host__ __device__ __forceinline__ bool ctl_update(StepCtl& c, const SolveParams& p, double err, double htry, bool landing,
                                            bool capped, double t_target, int& nst) {
   if (!(err == err) || isinf(err)) { c.status = SEQ_STATUS_NONFINITE; return false; }
   const bool switching = !(p.flags & SEQ_FLAG_NO_ORDER_SWITCH);
   bool accepted;
   if (err <= 1.0) {
-    double factor = (err == 0.0) ? SEQ_MAX_FACTOR : fmin(SEQ_MAX_FACTOR, SEQ_SAFETY * pow(err, RK_EXPO[c.pair]));
+    double factor = (err == 0.0) ? SEQ_MAX_FACTOR : fmin(SEQ_MAX_FACTOR, SEQ_SAFETY * pow(err, c.pair ? -0.25 : -0.2));
     if (c.prev_rejected) factor = fmin(1.0, factor);
     c.prev_rejected = false;
     c.t = landing ? t_target : c.t + htry;
@@ -226,7 +250,7 @@ __device__ __forceinline__ bool ctl_update(StepCtl& c, const SolveParams& p, dou
         c.probe_backoff = 1;
       } else {
         c.pair = 0;
-        c.probe_backoff = min(2 * c.probe_backoff, 64);
+        c.probe_backoff = (2 * c.probe_backoff < 64) ? 2 * c.probe_backoff : 64;
         c.probe_wait = c.probe_backoff;
       }
     }
@@ -236,11 +260,11 @@ __device__ __forceinline__ bool ctl_update(StepCtl& c, const SolveParams& p, dou
     if (c.pair == 1) {
       // the low-order probe failed: redo the same step with the 5(4) pair, back off the next probe
       c.pair = 0;
-      c.probe_backoff = min(2 * c.probe_backoff, 64);
+      c.probe_backoff = (2 * c.probe_backoff < 64) ? 2 * c.probe_backoff : 64;
       c.probe_wait = c.probe_backoff;
       c.h = htry;
     } else {
-      c.h = htry * fmax(SEQ_MIN_FACTOR, SEQ_SAFETY * pow(err, RK_EXPO[0]));
+      c.h = htry * fmax(SEQ_MIN_FACTOR, SEQ_SAFETY * pow(err, -0.2));
       c.prev_rejected = true;
     }
     accepted = false;

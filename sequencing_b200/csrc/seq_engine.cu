@@ -17,6 +17,7 @@
 #include "kernel_dmma.cuh"
 #include "kernel_dmma_stream.cuh"
 #include "kernel_small.cuh"
+#include "kernel_large.cuh"
 
 using namespace seq;
 
@@ -32,7 +33,9 @@ struct seq_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
-  DevBuf ws, gbuf, tab, cprime, pack, stage_in, stage_out;
+  DevBuf ws, gbuf, tab, cprime, pack, stage_in, stage_out, large;
+  const seq_comm* comm = nullptr;   // set for the duration of seq_engine_solve_sharded
+  double* host_err = nullptr;       // pinned: error norm read back once per step by the large-N stepper
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   int launches = 0;
@@ -270,6 +273,7 @@ static int pick_method(const seq_engine* e, const seq_solve_desc* d) {
   if (!ket && d->H0_batch_stride == 0 && small_supported(d->N, d->n_ch + d->n_ctd, d->n_e)) return SEQ_METHOD_SMALL;
   if (!ket && d->H0_batch_stride == 0 && dmma_supported(d->N, e ? e->max_smem_optin : 232448)) return SEQ_METHOD_DMMA;
   if (!ket && d->H0_batch_stride == 0 && stream_supported(d->N, e ? e->max_smem_optin : 232448)) return SEQ_METHOD_DMMA_STREAM;
+  if (!ket && d->H0_batch_stride == 0 && d->N > 96) return SEQ_METHOD_LARGE;
   return SEQ_METHOD_GENERIC;
 }
 
@@ -293,7 +297,7 @@ extern "C" {
 int seq_engine_abi_version(void) { return SEQ_ENGINE_ABI_VERSION; }
 
 const char* seq_engine_build_info(void) {
-  return "seq_engine abi=1 arch=sm_100a kernels=generic(fma),dmma(8x8x4 resident),dmma_stream(8x8x4 blocked),small(thread-per-trajectory real superoperator) built " __DATE__;
+  return "seq_engine abi=2 arch=sm_100a kernels=generic(fma),dmma(8x8x4 resident),dmma_stream(8x8x4 blocked),small(thread-per-trajectory real superoperator),large(stream-K DMMA ZGEMM, row-sharded) built " __DATE__;
 }
 
 int seq_engine_create(int device, void* stream, seq_engine** out) {
@@ -317,8 +321,9 @@ int seq_engine_destroy(seq_engine* e) {
   if (!e) return SEQ_OK;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  DevBuf* bufs[] = {&e->ws, &e->gbuf, &e->tab, &e->cprime, &e->pack, &e->stage_in, &e->stage_out};
+  DevBuf* bufs[] = {&e->ws, &e->gbuf, &e->tab, &e->cprime, &e->pack, &e->stage_in, &e->stage_out, &e->large};
   for (DevBuf* b : bufs) if (b->ptr) cudaFree(b->ptr);
+  if (e->host_err) cudaFreeHost(e->host_err);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   delete e;
@@ -387,6 +392,190 @@ int seq_engine_spline_prep(seq_engine* e, const double* y, double* M, int64_t n_
   return SEQ_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// SEQ_METHOD_LARGE: host-driven embedded-RK stepper over grid-wide kernels (kernel_large.cuh).
+// One trajectory at a time; with a communicator, rho's rows are sharded over the ranks and the
+// stage state is all-gathered once per RHS evaluation.
+// ------------------------------------------------------------------------------------------
+static int grid_for(long long n, int sms) {
+  long long g = (n + 255) / 256;
+  long long cap = (long long)sms * 8;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+__global__ void large_store_expect_kernel(const cplx* __restrict__ acc, void* __restrict__ expect, long long base, long long stride,
+                                          int n_e, int complex_out) {
+  int e = threadIdx.x;
+  if (e >= n_e) return;
+  if (complex_out) ((cplx*)expect)[base + e * stride] = acc[e];
+  else ((double*)expect)[base + e * stride] = acc[e].x;
+}
+
+static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams& p, const cplx* G0, const cplx* Gk) {
+  const seq_comm* comm = e->comm;
+  const int world = (comm && comm->world > 1) ? comm->world : 1;
+  const int rank = world > 1 ? comm->rank : 0;
+  const int N = d->N, NP = large_np(N), B = d->B;
+  const int n_g = p.n_g, n_l = p.n_c + p.n_ctd, n_e = p.n_e;
+  const int m = ((N + world - 1) / world + 15) / 16 * 16;   // rows per rank
+  const long long rows_full = (long long)world * m;          // >= NP
+  const long long row0 = (long long)rank * m;
+  const int Mrows = (int)((N - row0) < 0 ? 0 : ((N - row0) > m ? m : (N - row0)));
+  const long long opsz = 2LL * NP * NP, ysz = 2LL * rows_full * NP, lsz = 2LL * m * NP;
+  const long long mplane = (long long)m * NP, yplane = rows_full * NP, oplane = (long long)NP * NP;
+  cudaStream_t st = e->stream;
+  const int sms = e->sm_count;
+
+  size_t total = (size_t)(1 + n_g + n_l + 1) * opsz + ysz + (world > 1 ? lsz : 0) + (size_t)(2 + 7 + 1) * lsz + 64 + 2 + 2 * (size_t)(n_e + 1);
+  int rc = reserve(e, e->large, total * sizeof(double) + 256);
+  if (rc) return rc;
+  if (!e->host_err) CUDA_TRY(e, cudaMallocHost((void**)&e->host_err, 2 * sizeof(double)));
+  double* base = (double*)e->large.ptr;
+  double* G0p = base; base += opsz;
+  double* Gkp = base; base += (size_t)n_g * opsz;
+  double* Lp = base; base += (size_t)n_l * opsz;
+  double* Gt = base; base += opsz;
+  double* Yfull = base; base += ysz;
+  double* Ysend = nullptr;
+  if (world > 1) { Ysend = base; base += lsz; }
+  double* ycur = base; base += lsz;
+  double* ynew = base; base += lsz;
+  double* kbuf[7];
+  for (int j = 0; j < 7; j++) { kbuf[j] = base; base += lsz; }
+  double* T = base; base += lsz;
+  double* cval = base; base += 64;
+  double* derr = base; base += 2;
+  cplx* eacc = (cplx*)base;
+
+  // operators -> planar padded
+  large_pack_kernel<<<grid_for(oplane, sms), 256, 0, st>>>(G0, G0p, N, NP, NP);
+  e->launches++;
+  for (int g = 0; g < n_g; g++) { large_pack_kernel<<<grid_for(oplane, sms), 256, 0, st>>>(Gk + (size_t)g * N * N, Gkp + (size_t)g * opsz, N, NP, NP); e->launches++; }
+  for (int l = 0; l < n_l; l++) { large_pack_kernel<<<grid_for(oplane, sms), 256, 0, st>>>(p.L + (size_t)l * N * N, Lp + (size_t)l * opsz, N, NP, NP); e->launches++; }
+
+  std::vector<int> out_idx(d->n_out);
+  CUDA_TRY(e, cudaMemcpyAsync(out_idx.data(), d->out_idx, sizeof(int) * d->n_out, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(e, cudaStreamSynchronize(st));
+
+  for (int b = 0; b < B; b++) {
+    // rho0 -> full stage buffer and this rank's rows
+    large_pack_kernel<<<grid_for(yplane, sms), 256, 0, st>>>(p.state0 + (size_t)b * N * N, Yfull, N, NP, rows_full);
+    e->launches++;
+    CUDA_TRY(e, cudaMemcpyAsync(ycur, Yfull + row0 * NP, mplane * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(e, cudaMemcpyAsync(ycur + mplane, Yfull + yplane + row0 * NP, mplane * sizeof(double), cudaMemcpyDeviceToDevice, st));
+
+    auto rhs = [&](double t, double* kout) -> int {
+      if (n_g > 0) { large_coeff_kernel<<<1, 64, 0, st>>>(p, b, t, cval); e->launches++; }
+      large_build_G_kernel<<<grid_for(opsz, sms), 256, 0, st>>>(G0p, Gkp, cval, n_g, opsz, Gt);
+      e->launches++;
+      CUDA_TRY(e, cudaMemsetAsync(kout, 0, lsz * sizeof(double), st));
+      if (Mrows <= 0) return SEQ_OK;
+      ZgemmArgs a;
+      // K = -i G[R,:] Y
+      a.Ar = Gt + row0 * NP; a.Ai = Gt + oplane + row0 * NP; a.lda = NP;
+      a.Br = Yfull; a.Bi = Yfull + yplane; a.ldb = NP;
+      a.Cr = kout; a.Ci = kout + mplane; a.ldc = NP;
+      a.M = Mrows; a.Ncols = NP; a.K = NP; a.alpha_r = 0.0; a.alpha_i = -1.0; a.scale = nullptr;
+      int r2 = launch_zgemm<false>(a, sms, st); if (r2) return r2; e->launches++;
+      // K += i Y[R,:] G^dag
+      a.Ar = Yfull + row0 * NP; a.Ai = Yfull + yplane + row0 * NP;
+      a.Br = Gt; a.Bi = Gt + oplane;
+      a.alpha_i = 1.0;
+      r2 = launch_zgemm<true>(a, sms, st); if (r2) return r2; e->launches++;
+      for (int l = 0; l < n_l; l++) {
+        const double* Ll = Lp + (size_t)l * opsz;
+        CUDA_TRY(e, cudaMemsetAsync(T, 0, lsz * sizeof(double), st));
+        a.Ar = Ll + row0 * NP; a.Ai = Ll + oplane + row0 * NP;
+        a.Br = Yfull; a.Bi = Yfull + yplane;
+        a.Cr = T; a.Ci = T + mplane; a.alpha_r = 1.0; a.alpha_i = 0.0; a.scale = nullptr;
+        r2 = launch_zgemm<false>(a, sms, st); if (r2) return r2; e->launches++;
+        a.Ar = T; a.Ai = T + mplane;
+        a.Br = Ll; a.Bi = Ll + oplane;
+        a.Cr = kout; a.Ci = kout + mplane;
+        a.scale = (l < p.n_c) ? nullptr : cval + p.n_ch + (l - p.n_c);
+        r2 = launch_zgemm<true>(a, sms, st); if (r2) return r2; e->launches++;
+      }
+      return SEQ_OK;
+    };
+
+    StepCtl ctl;
+    ctl_init_at(ctl, p, p.t0 + p.dt * (double)out_idx[0]);
+    for (int o = 0; o < d->n_out; o++) {
+      if (o > 0) {
+        const double t_target = p.t0 + p.dt * (double)out_idx[o];
+        int nst = 0;
+        double htry;
+        bool landing, capped;
+        while (ctl.status == SEQ_STATUS_OK && ctl_next(ctl, p, t_target, htry, landing, capped)) {
+          const int pair = ctl.pair, S = H_RK_STAGES[pair];
+          for (int s_ = ctl.have_k1 ? 1 : 0; s_ < S; s_++) {
+            if (s_ > 0) {
+              LargeCombine c;
+              c.y = ycur; c.nk = s_; c.h = htry; c.n_plane = mplane;
+              for (int j = 0; j < s_; j++) { c.k[j] = kbuf[j]; c.a[j] = H_RK_A[pair][s_][j]; }
+              if (world > 1) { c.dst = Ysend; c.dst_plane = mplane; }
+              else { c.dst = Yfull; c.dst_plane = yplane; }
+              c.keep = (s_ == S - 1) ? ynew : nullptr;
+              large_combine_kernel<<<grid_for(lsz, sms), 256, 0, st>>>(c);
+              e->launches++;
+              if (world > 1) {
+                if (comm->all_gather(comm->ctx, Ysend, Yfull, mplane) || comm->all_gather(comm->ctx, Ysend + mplane, Yfull + yplane, mplane))
+                  return fail(e, SEQ_ERR_CUDA, "all_gather hook failed");
+              }
+            }
+            int r2 = rhs(ctl.t + H_RK_C[pair][s_] * htry, kbuf[s_]);
+            if (r2) return r2;
+            ctl.nrhs++;
+          }
+          ctl.have_k1 = true;
+          LargeErr er;
+          er.y = ycur; er.yn = ynew; er.nk = S; er.h = htry; er.atol = p.atol; er.rtol = p.rtol;
+          for (int j = 0; j < S; j++) { er.k[j] = kbuf[j]; er.e[j] = H_RK_E[pair][j]; }
+          er.m = m; er.NP = NP; er.N = N; er.row0 = row0; er.out = derr;
+          CUDA_TRY(e, cudaMemsetAsync(derr, 0, sizeof(double), st));
+          large_err_kernel<<<grid_for(mplane, sms), 256, 0, st>>>(er);
+          e->launches++;
+          if (world > 1 && comm->all_reduce_sum(comm->ctx, derr, 1)) return fail(e, SEQ_ERR_CUDA, "all_reduce_sum hook failed");
+          CUDA_TRY(e, cudaMemcpyAsync(e->host_err, derr, sizeof(double), cudaMemcpyDeviceToHost, st));
+          CUDA_TRY(e, cudaStreamSynchronize(st));
+          const double err = sqrt(e->host_err[0] / ((double)N * N));
+          if (ctl_update(ctl, p, err, htry, landing, capped, t_target, nst)) {
+            std::swap(ycur, ynew);
+            std::swap(kbuf[0], kbuf[S - 1]);
+          }
+        }
+        if (ctl.status != SEQ_STATUS_OK) break;
+      }
+      // outputs: after an accepted step the full stage buffer holds y (the FSAL stage input)
+      if (n_e > 0) {
+        CUDA_TRY(e, cudaMemsetAsync(eacc, 0, sizeof(cplx) * n_e, st));
+        dim3 ge(grid_for((long long)N * N, sms), n_e);
+        large_expect_kernel<<<ge, 256, 0, st>>>(p.E, Yfull, yplane, N, NP, eacc);
+        large_store_expect_kernel<<<1, 64, 0, st>>>(eacc, p.expect, (long long)b * n_e * d->n_out + o, d->n_out, n_e,
+                                                    (p.flags & SEQ_FLAG_EXPECT_COMPLEX) ? 1 : 0);
+        e->launches += 2;
+      }
+      if (p.flags & SEQ_FLAG_STORE_STATES) {
+        large_unpack_kernel<<<grid_for((long long)N * N, sms), 256, 0, st>>>(Yfull, p.states + ((size_t)b * d->n_out + o) * N * N, N, NP, rows_full);
+        e->launches++;
+      }
+    }
+    if (ctl.status == SEQ_STATUS_OK) {
+      large_unpack_kernel<<<grid_for((long long)N * N, sms), 256, 0, st>>>(Yfull, p.final_state + (size_t)b * N * N, N, NP, rows_full);
+      e->launches++;
+    } else {
+      CUDA_TRY(e, cudaMemsetAsync(p.final_state + (size_t)b * N * N, 0, sizeof(cplx) * N * N, st));
+    }
+    int h_stats[4] = {ctl.nacc, ctl.nrej, ctl.nrhs, 0};
+    int h_status = ctl.status;
+    CUDA_TRY(e, cudaMemcpyAsync(p.status + b, &h_status, sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(e, cudaMemcpyAsync(p.stats + 4 * b, h_stats, sizeof(h_stats), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(e, cudaStreamSynchronize(st));   // h_status / h_stats live on this stack frame
+  }
+  CUDA_TRY(e, cudaGetLastError());
+  return SEQ_OK;
+}
+
 static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   const int N = d->N, B = d->B;
   const size_t N2 = (size_t)N * N;
@@ -399,8 +588,12 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
     return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_SMALL does not cover N=%d ket=%d h0_stride=%lld (density matrices, N <= 6, shared H0)", N, (int)ket, (long long)d->H0_batch_stride);
   if (method == SEQ_METHOD_DMMA_STREAM && (ket || !stream_supported(N, e->max_smem_optin) || d->H0_batch_stride))
     return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_DMMA_STREAM does not cover N=%d ket=%d h0_stride=%lld", N, (int)ket, (long long)d->H0_batch_stride);
-  if (method < SEQ_METHOD_GENERIC || method > SEQ_METHOD_DMMA_STREAM)
+  if (method == SEQ_METHOD_LARGE && (ket || d->H0_batch_stride))
+    return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_LARGE covers density matrices with a shared H0 only (N=%d ket=%d)", N, (int)ket);
+  if (method < SEQ_METHOD_GENERIC || method > SEQ_METHOD_LARGE)
     return fail(e, SEQ_ERR_UNSUPPORTED, "method %d is not implemented", method);
+  if (e->comm && e->comm->world > 1 && method != SEQ_METHOD_LARGE)
+    return fail(e, SEQ_ERR_UNSUPPORTED, "row-sharded solves run SEQ_METHOD_LARGE only (got method %d for N=%d)", method, N);
 
   // ---- scratch
   const size_t nG0 = d->H0_batch_stride ? (size_t)B : 1;
@@ -502,6 +695,9 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   } else if (method == SEQ_METHOD_DMMA_STREAM) {
     rc = launch_stream(p, G0, Gk, (double*)e->pack.ptr, e->stream, &e->launches);
     if (rc) return fail(e, rc, "streaming DMMA kernel launch configuration failed for N=%d", N);
+  } else if (method == SEQ_METHOD_LARGE) {
+    rc = solve_large(e, d, p, G0, Gk);
+    if (rc) return rc;
   } else {
     rc = launch_small(p, G0, Gk, (double*)e->pack.ptr, e->sm_count, e->stream, &e->launches);
     if (rc) return fail(e, rc, "small-N kernel launch configuration failed for N=%d", N);
@@ -595,6 +791,24 @@ int seq_engine_solve(seq_engine* e, const seq_solve_desc* d) {
   }
   if (d->flags & SEQ_FLAG_HOST_POINTERS) return solve_host(e, d);
   return solve_device(e, d);
+}
+
+int seq_engine_solve_sharded(seq_engine* e, const seq_solve_desc* d, const seq_comm* comm) {
+  if (!e) return SEQ_ERR_INVALID;
+  if (comm && comm->world > 1) {
+    if (comm->rank < 0 || comm->rank >= comm->world || !comm->all_gather || !comm->all_reduce_sum)
+      return fail(e, SEQ_ERR_INVALID, "bad communicator (rank %d of %d, hooks %p %p)", comm->rank, comm->world,
+                  (void*)comm->all_gather, (void*)comm->all_reduce_sum);
+    if (d && d->method != SEQ_METHOD_AUTO && d->method != SEQ_METHOD_LARGE)
+      return fail(e, SEQ_ERR_UNSUPPORTED, "row-sharded solves run SEQ_METHOD_LARGE only");
+  }
+  e->comm = comm;
+  seq_solve_desc dd;
+  const seq_solve_desc* use = d;
+  if (d && d->size == sizeof(seq_solve_desc) && comm && comm->world > 1) { dd = *d; dd.method = SEQ_METHOD_LARGE; use = &dd; }
+  int rc = seq_engine_solve(e, use);
+  e->comm = nullptr;
+  return rc;
 }
 
 int seq_engine_apply_unitary(seq_engine* e, const void* U, void* states, int32_t N, int32_t B, int is_ket) {

@@ -1,4 +1,5 @@
-"""Multi-GPU batch sharding: one process per GPU, independent trajectories, no data-path collective.
+"""Multi-GPU: batch sharding of sweeps (independent trajectories, no data-path collective) and the
+row-sharded solve of ONE large system (an all-gather of the stage state per RHS evaluation).
 
 Sweeps and initial-state batches are independent units: every rank integrates a
 contiguous ``B/G`` slice of the batch on its own GPU with the shared operators replicated, and the
@@ -107,3 +108,78 @@ def solve_sharded(bp: BatchProblem, engine=None, group=None, gather: bool = True
         states=g(out.states) if out.states is not None else None,
         status=g(out.status), stats=g(out.stats), kernel_ms=out.kernel_ms, launches=out.launches, method=out.method,
     )
+
+
+# ---------------------------------------------------------------------------------------------
+# Row-sharded solve of one large system (C5): rho split into row blocks, one all-gather per RHS
+# ---------------------------------------------------------------------------------------------
+def row_block(N: int, rank: int, world: int):
+    """Rows ``[lo, hi)`` of rho that rank ``rank`` evaluates: blocks of m = 16*ceil(ceil(N/world)/16)
+    rows (the engine's tile granularity), the tail ranks may be short or empty."""
+    m = ((N + world - 1) // world + 15) // 16 * 16
+    lo = min(N, rank * m)
+    return lo, min(N, lo + m)
+
+
+class _DevArray:
+    """A device pointer as an object torch can wrap without copying (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def make_comm(group=None):
+    """``seq_comm`` hooks backed by torch.distributed (NCCL): the engine calls them with device
+    pointers while it enqueues the stepper on torch's current stream, so the collectives are ordered
+    with the kernels.  Returns (comm, keepalive) - keep ``keepalive`` referenced during the solve."""
+    import torch
+    import torch.distributed as dist
+
+    from .solver import _lib
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    stats = {"all_gather": 0, "all_reduce": 0, "bytes_gathered": 0}
+
+    def _wrap(ptr, n):
+        return torch.as_tensor(_DevArray(ptr, n), device=torch.device("cuda", torch.cuda.current_device()))
+
+    def all_gather(ctx, send, recv, count):
+        try:
+            dist.all_gather_into_tensor(_wrap(recv, count * world), _wrap(send, count), group=group)
+            stats["all_gather"] += 1
+            stats["bytes_gathered"] += 8 * count * world
+            return 0
+        except Exception as exc:  # the C side turns a non-zero return into an error message
+            print(f"[seq_comm] all_gather failed: {exc}", flush=True)
+            return 1
+
+    def all_reduce(ctx, buf, count):
+        try:
+            dist.all_reduce(_wrap(buf, count), group=group)
+            stats["all_reduce"] += 1
+            return 0
+        except Exception as exc:
+            print(f"[seq_comm] all_reduce failed: {exc}", flush=True)
+            return 1
+
+    ag, ar = _lib.ALL_GATHER_FN(all_gather), _lib.ALL_REDUCE_FN(all_reduce)
+    comm = _lib.Comm(rank=rank, world=world, ctx=None, all_gather=ag, all_reduce_sum=ar)
+    return comm, (ag, ar, stats)
+
+
+def solve_rows_sharded(bp: BatchProblem, engine=None, group=None) -> BatchOutput:
+    """Integrate ONE large Lindblad system with rho row-sharded over every rank of the process group
+    (config C5: transmon + two cavities, N = 1875, 8 x B200).  Every rank passes the same problem and
+    receives the full result.  Without an initialised process group this is a single-GPU solve."""
+    import torch
+    import torch.distributed as dist
+
+    from .solver import Engine
+
+    engine = engine or Engine.get(torch.cuda.current_device())
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return engine.solve_rows_sharded(bp, None)
+    comm, keep = make_comm(group)
+    out = engine.solve_rows_sharded(bp, comm)
+    out.comm_stats = keep[2]
+    return out

@@ -10,19 +10,19 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "_seq_engine.so")
 
 # mirrors of the #defines in include/seq_engine.h
-ABI_VERSION = 1
+ABI_VERSION = 2
 SEQ_OK = 0
 STATUS_OK, STATUS_MAX_STEPS, STATUS_NONFINITE, STATUS_STEP_UNDERFLOW = 0, 1, 2, 3
 FLAG_KET, FLAG_NORMALIZE, FLAG_STORE_STATES, FLAG_EXPECT_COMPLEX, FLAG_HOST_POINTERS = 0x1, 0x2, 0x4, 0x8, 0x10
 FLAG_NO_ORDER_SWITCH = 0x20
-METHOD_AUTO, METHOD_GENERIC, METHOD_DMMA, METHOD_SMALL, METHOD_DMMA_STREAM = 0, 1, 2, 3, 4
-METHOD_NAMES = {0: "auto", 1: "generic", 2: "dmma", 3: "small", 4: "dmma_stream"}
+METHOD_AUTO, METHOD_GENERIC, METHOD_DMMA, METHOD_SMALL, METHOD_DMMA_STREAM, METHOD_LARGE = 0, 1, 2, 3, 4, 5
+METHOD_NAMES = {0: "auto", 1: "generic", 2: "dmma", 3: "small", 4: "dmma_stream", 5: "large"}
 
 EXPORTS = (
     "seq_engine_abi_version", "seq_engine_build_info", "seq_engine_create", "seq_engine_destroy",
     "seq_engine_last_error", "seq_engine_workspace_bytes", "seq_engine_solve",
     "seq_engine_select_method", "seq_engine_last_launch_count", "seq_engine_last_kernel_ms",
-    "seq_engine_spline_prep", "seq_engine_apply_unitary", "seq_engine_expect",
+    "seq_engine_spline_prep", "seq_engine_apply_unitary", "seq_engine_expect", "seq_engine_solve_sharded",
 )
 
 
@@ -49,6 +49,17 @@ class SolveDesc(C.Structure):
         ("expect", C.c_void_p), ("final_state", C.c_void_p), ("states", C.c_void_p),
         ("status", C.c_void_p), ("stats", C.c_void_p),
     ]
+
+
+ALL_GATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
+ALL_REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
+
+
+class Comm(C.Structure):
+    """``struct seq_comm`` - collective hooks of the row-sharded large-system solve."""
+
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("ctx", C.c_void_p),
+                ("all_gather", ALL_GATHER_FN), ("all_reduce_sum", ALL_REDUCE_FN)]
 
 
 _lib = None
@@ -79,6 +90,7 @@ def load():
     lib.seq_engine_workspace_bytes.restype = i64
     lib.seq_engine_solve.argtypes = [vp, C.POINTER(SolveDesc)]
     lib.seq_engine_select_method.argtypes = [vp, C.POINTER(SolveDesc)]
+    lib.seq_engine_solve_sharded.argtypes = [vp, C.POINTER(SolveDesc), C.POINTER(Comm)]
     lib.seq_engine_last_launch_count.argtypes = [vp]
     lib.seq_engine_last_kernel_ms.argtypes = [vp]
     lib.seq_engine_last_kernel_ms.restype = C.c_float

@@ -246,6 +246,27 @@ class Engine:
         self._last_method = self.lib.seq_engine_select_method(self.handle, C.byref(desc))
         return self._finish(bp, outs)
 
+    def solve_rows_sharded(self, bp: BatchProblem, comm: "_lib.Comm") -> BatchOutput:
+        """ONE large system with rho row-sharded across the ranks of ``comm`` (C5): every rank calls
+        this with the same ``bp`` and gets the full result.  ``comm`` carries the all-gather /
+        all-reduce hooks (``sequencing_b200.distributed.make_comm``); device-resident operands."""
+        tens = self.to_device(bp)
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            outs = {}
+            for name, (shape, dt) in self._out_shapes(bp).items():
+                tdt = {np.float64: torch.float64, np.complex128: torch.complex128, np.int32: torch.int32}[dt]
+                outs[name] = torch.zeros(shape, dtype=tdt, device=self.device)
+            ptr = {k: (v.data_ptr() if v.numel() else None) for k, v in tens.items()}
+            ptr.update({k: (v.data_ptr() if v.numel() else None) for k, v in outs.items()})
+            desc = self._desc(bp, ptr, host=False)
+            self._check(self.lib.seq_engine_solve_sharded(self.handle, C.byref(desc), C.byref(comm) if comm is not None else None))
+            self.last_launches = self.lib.seq_engine_last_launch_count(self.handle)
+            self.total_launches += self.last_launches
+            self._last_method = _lib.METHOD_LARGE if (comm is not None and comm.world > 1) else self.lib.seq_engine_select_method(self.handle, C.byref(desc))
+            torch.cuda.synchronize(self.device)
+        return self._finish(bp, {k: v.cpu().numpy() for k, v in outs.items()})
+
     def _finish(self, bp, out) -> BatchOutput:
         self.last_kernel_ms = float(self.lib.seq_engine_last_kernel_ms(self.handle))
         return BatchOutput(

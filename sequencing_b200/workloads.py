@@ -122,3 +122,35 @@ def c4_two_transmons_bus(B=512, cavity_levels=10, store_states=False):
                 cav.displace(0.5)
             seq.run(init, e_ops=e_ops, options=_options(system.dt, store_states))
     return _single(d.batch_problems())
+
+
+def c5_transmon_two_cavities(cavity_levels=25, n_ops=100, sigma=10, store_states=False):
+    """C5: transmon(3) (x) cavity(L) (x) cavity(L) (N = 3 L^2 = 1875 at L=25), one long sequence of
+    ``n_ops`` alternating cavity displacements and qubit rotations (n_t = 4*sigma*n_ops), decay on all
+    three modes + transmon dephasing (n_c = 6: decay and dephasing on every mode).  B = 1: the single
+    large system whose rho is row-sharded across the GPUs of the box."""
+    qubit = Transmon("qubit", levels=3, kerr=-0.2, t1=20e3, t2=15e3)
+    cav_a = Cavity("cavity_a", levels=cavity_levels, kerr=-1e-5, t1=100e3, t2=80e3)
+    cav_b = Cavity("cavity_b", levels=cavity_levels, kerr=-1e-5, t1=120e3, t2=90e3)
+    system = System("system", modes=[qubit, cav_a, cav_b])
+    system.set_cross_kerr(cav_a, qubit, chi=-2e-3)
+    system.set_cross_kerr(cav_b, qubit, chi=-1.5e-3)
+    system.set_cross_kerr(cav_a, cav_b, chi=-1e-5)
+    for mode in (qubit, cav_a, cav_b):
+        mode.gaussian_pulse.sigma = sigma
+    rng = np.random.default_rng(0)
+    init = system.fock_dm()
+    e_ops = [qubit.fock_dm(1), cav_a.n, cav_b.n]
+    with deferred_solves(execute=False) as d:
+        seq = get_sequence(system)
+        for i in range(n_ops):
+            which = i % 3
+            if which == 0:
+                cav_a.displace(0.3 * np.exp(1j * rng.uniform(0, 2 * np.pi)))
+            elif which == 1:
+                qubit.rotate(rng.uniform(0.2, 1.0) * np.pi, rng.uniform(0, 2 * np.pi))
+            else:
+                cav_b.displace(0.3 * np.exp(1j * rng.uniform(0, 2 * np.pi)))
+            sync()
+        seq.run(init, e_ops=e_ops, options=_options(system.dt, store_states))
+    return _single(d.batch_problems())

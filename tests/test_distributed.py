@@ -84,3 +84,27 @@ def test_two_rank_sharded_solve_and_gather_gloo():
         p.join(timeout=60)
     assert all(ok for _, ok, _ in got), got
     assert got[0][2] == got[1][2]     # every rank ends with the full sweep
+
+
+def test_row_blocks_cover_rho_and_match_the_engine_granularity():
+    """Row-sharded large-system mode (C5): blocks of m = 16*ceil(ceil(N/world)/16) rows, covering [0, N)."""
+    from sequencing_b200.distributed import row_block
+    for N in (97, 150, 243, 1875):
+        for world in (1, 2, 4, 8):
+            spans = [row_block(N, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == N
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            m = max(hi - lo for lo, hi in spans)
+            assert m % 16 == 0 or world == 1 or m == spans[0][1] - spans[0][0]
+            assert all((hi - lo) in (m,) or hi == N for lo, hi in spans)
+    assert [row_block(1875, r, 8) for r in (0, 7)] == [(0, 240), (1680, 1875)]
+
+
+def test_comm_struct_matches_header():
+    """``struct seq_comm`` of include/seq_engine.h: two int32, a pointer, two function pointers."""
+    import ctypes as C
+    from sequencing_b200.solver import _lib
+    assert [f[0] for f in _lib.Comm._fields_] == ["rank", "world", "ctx", "all_gather", "all_reduce_sum"]
+    assert C.sizeof(_lib.Comm) == 32
+    hdr = open(os.path.join(ROOT, "include", "seq_engine.h")).read()
+    assert "typedef struct seq_comm" in hdr and "seq_engine_solve_sharded" in hdr

@@ -305,3 +305,50 @@ def test_small_kernel_large_batch_properties(gpu_engine):
     pop = out.expect[:, 0, -1]
     assert pop.min() > -1e-9 and pop.max() < 1 + 1e-9
     np.testing.assert_allclose(pop, pop[::-1], atol=1e-9)
+
+
+def test_large_path_matches_generic(gpu_engine):
+    """SEQ_METHOD_LARGE (grid-wide stream-K DMMA ZGEMMs, host-driven stepper) against the FP64-FMA kernel:
+    sizes around the tile edges (48-row / 96-column tiles, K chunks of 16), with and without collapse terms."""
+    for N, n_c, n_ctd, n_ch in ((97, 2, 0, 2), (112, 0, 0, 1), (130, 1, 1, 2), (200, 1, 0, 2)):
+        mk = lambda: random_problem(N=N, B=2, n_t=4, n_ch=n_ch, n_c=n_c, n_ctd=n_ctd, n_e=2, seed=N, hscale=0.3, store_states=True)
+        a, g = mk(), mk()
+        a.method, g.method = _lib.METHOD_LARGE, _lib.METHOD_GENERIC
+        oa, og = gpu_engine.solve(a), gpu_engine.solve(g)
+        assert oa.method == "large" and og.method == "generic"
+        assert np.all(oa.status == 0)
+        assert np.max(np.abs(oa.states - og.states)) < 1e-12, N
+        assert np.max(np.abs(oa.expect - og.expect)) < 1e-12, N
+        np.testing.assert_array_equal(oa.stats[:, :2], og.stats[:, :2])
+    auto = random_problem(N=100, B=1, n_t=3, n_ch=1, n_c=1, n_e=1, seed=1)
+    assert gpu_engine.solve(auto).method == "large"
+
+
+def test_large_path_rejections_and_complex_expect(gpu_engine):
+    """Uncapped steps (the controller rejects some) and non-Hermitian e_ops through the large path."""
+    rng = np.random.default_rng(4)
+    mk = lambda: random_problem(N=104, B=1, n_t=6, n_ch=2, n_c=1, n_e=2, seed=31, hscale=4.0, store_states=True)
+    a, g = mk(), mk()
+    for bp in (a, g):
+        bp.E = bp.E + 0.3 * (rng.normal(size=bp.E.shape) + 1j * rng.normal(size=bp.E.shape)) if bp is a else a.E
+        bp.expect_complex = True
+        bp.max_step = 0.0
+    a.method, g.method = _lib.METHOD_LARGE, _lib.METHOD_GENERIC
+    oa, og = gpu_engine.solve(a), gpu_engine.solve(g)
+    assert np.all(oa.status == 0) and oa.stats[0, 1] > 0          # at least one rejected step
+    np.testing.assert_array_equal(oa.stats[:, :2], og.stats[:, :2])
+    assert np.max(np.abs(oa.states - og.states)) < 1e-11
+    assert np.max(np.abs(oa.expect - og.expect)) < 1e-11
+
+
+def test_rows_sharded_two_gpus():
+    """rho row-sharded over 2 GPUs (NCCL all-gather per RHS) against the single-GPU large path."""
+    import os, subprocess, sys
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(root, "tools", "mgpu_rows_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ROWS_SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

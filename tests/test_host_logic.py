@@ -239,7 +239,7 @@ def test_abi_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.seq_engine_abi_version() == 1
+    assert lib.seq_engine_abi_version() == _lib.ABI_VERSION == 2
     assert b"sm_100a" in lib.seq_engine_build_info()
 
 
@@ -266,6 +266,11 @@ def test_abi_validation_without_gpu():
     d.flags = _lib.FLAG_KET
     assert lib.seq_engine_select_method(None, ctypes.byref(d)) == _lib.METHOD_GENERIC
     d.flags = 0
+    for N, want in ((3, _lib.METHOD_SMALL), (6, _lib.METHOD_SMALL), (7, _lib.METHOD_DMMA), (48, _lib.METHOD_DMMA),
+                    (49, _lib.METHOD_DMMA_STREAM), (96, _lib.METHOD_DMMA_STREAM), (97, _lib.METHOD_LARGE), (1875, _lib.METHOD_LARGE)):
+        d.N = N
+        assert lib.seq_engine_select_method(None, ctypes.byref(d)) == want, N
+    d.N = 45
     assert lib.seq_engine_workspace_bytes(None, ctypes.byref(d)) > 0
     d.size = 7
     assert lib.seq_engine_workspace_bytes(None, ctypes.byref(d)) == -1
