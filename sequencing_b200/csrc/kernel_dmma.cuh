@@ -16,6 +16,12 @@
 //    stored in accumulator-fragment order ([slot][thread] double2, fully coalesced, L2 resident):
 //    a thread only ever re-reads what it wrote, so the stage combinations need no barrier.
 //
+//  * operator TILE SPARSITY: the reference's operators are Kronecker-embedded ladder / number
+//    operators, so most 8x4 fragments of G and of every L_l are exactly zero.  dmma_masks_kernel
+//    records, per operator and 8-row tile, which of the NP/4 k-steps hold a non-zero fragment; the
+//    product loops skip the others (warp-uniform branches, exact: only 0*x terms are dropped).
+//    Dense operators have all bits set and run the full loops.
+//
 // RHS (rho Hermitian):  A = -i G rho,  G = H(t) - (i/2) sum_l r_l L_l^dag L_l
 //                       rho' = A + A^dag + sum_l r_l L_l rho L_l^dag
 // = (1 + 2 n_l) complex NP^3 products, each 3 real DMMA chains (Karatsuba form, see warp_gemm).
@@ -48,7 +54,8 @@ template <int NT> struct DmmaCfg {
   static constexpr int PLANE = NP * LD;          // doubles per plane
   static constexpr int MAT = 2 * PLANE;          // doubles per planar matrix
   static constexpr int SLOTS = TW * 2;           // double2 per thread per state vector
-  static constexpr size_t SMEM = (size_t)(4 * MAT + 34 + 64) * sizeof(double);
+  static constexpr int MAXL = 64;                // collapse operators whose masks fit the smem table
+  static constexpr size_t SMEM = (size_t)(4 * MAT + 34 + 64) * sizeof(double) + (size_t)(1 + MAXL) * 8 * sizeof(unsigned);
 };
 
 // ---- prep: pack interleaved complex [N,N] into planar padded [2][NP][LD] (zero padded)
@@ -83,17 +90,49 @@ __global__ void dmma_pack_efrag_kernel(const cplx* __restrict__ E, double2* __re
   }
 }
 
+// ---- prep: tile-sparsity masks.  masks[(op * 8) + tr] bit ks = 1 iff rows 8tr..8tr+7, columns
+// 4ks..4ks+3 of packed operator `op` hold a non-zero (either plane).  Operator 0 is the union
+// pattern of G0 and every Gk (the pattern of G(t) at any t), operators 1.. are the L_l.
+// `blk`/`LD`/`PLANE` describe one planar image; `nimg` images per operator (1: resident layout,
+// 4: the 2x2 block images of the streaming kernel, masks then indexed [op][img][tr]).
+__global__ void dmma_masks_kernel(const double* __restrict__ G0p, const double* __restrict__ Gkp, int n_g,
+                                  const double* __restrict__ Lp, int n_l, int NT, int LD, int nimg, unsigned* __restrict__ masks) {
+  const int op = blockIdx.x;                 // 0: G union, 1..n_l: L
+  const int PLANE = 8 * NT * LD, IMG = 2 * PLANE, nks = 2 * NT;
+  for (int w = threadIdx.x; w < nimg * NT; w += blockDim.x) {
+    const int img = w / NT, tr = w - img * NT;
+    unsigned m = 0;
+    const int nsrc = (op == 0) ? 1 + n_g : 1;
+    for (int sidx = 0; sidx < nsrc; sidx++) {
+      const double* base = (op == 0) ? (sidx == 0 ? G0p : Gkp + (long long)(sidx - 1) * nimg * IMG) : Lp + (long long)(op - 1) * nimg * IMG;
+      base += (long long)img * IMG;
+      for (int ks = 0; ks < nks; ks++) {
+        bool nz = false;
+        for (int r = 0; r < 8; r++)
+          for (int c = 0; c < 4; c++) {
+            const int off = (8 * tr + r) * LD + 4 * ks + c;
+            nz = nz || base[off] != 0.0 || base[PLANE + off] != 0.0;
+          }
+        if (nz) m |= 1u << ks;
+      }
+    }
+    masks[(op * nimg + img) * 8 + tr] = m;
+  }
+}
+
 struct DmmaExtra {
   const double* G0p;   // planar padded G0 (shared)
   const double* Gkp;   // [n_g] planar padded
   const double* Lp;    // [n_l] planar padded
   const double2* Ef;   // fragment-ordered E^T
+  const unsigned* masks;  // tile-sparsity masks (dmma_masks_kernel)
 };
 
 template <int NT>
 struct DmmaState {
   typedef DmmaCfg<NT> C;
   double* Y; double* T; double* X0; double* X1; double* red; double* cval;
+  const unsigned* masks;   // smem copy: [(1 + n_l)][8]
   int tid, w, lane, g, tg, tr, tc0;
 };
 
@@ -102,23 +141,30 @@ struct DmmaState {
 //   P1 = Ar Br, P2 = Ai Bi, P3 = (Ar+Ai)(Br+Bi)      ->  Cr = P1 - P2,  Ci = P3 - P1 - P2
 //   B = conj(L)^T:            P3 = (Ar+Ai)(Lr-Li)      ->  Cr = P1 + P2,  Ci = P3 - P1 + P2
 // The operand sums run on the FP64 FMA pipe, which is otherwise idle while the tensor pipe is busy.
+// mask[t] bit ks: execute k-step ks for output tile t (0 = the operator fragment is exactly zero).
 template <int NT, bool BCONJT>
 __device__ __forceinline__ void warp_gemm(double (&acc)[DmmaCfg<NT>::TW][2][2], const double* __restrict__ A,
-                                          const double* __restrict__ Bm, int tr, int tc0, int g, int tg) {
+                                          const double* __restrict__ Bm, int tr, int tc0, int g, int tg,
+                                          const unsigned (&mask)[DmmaCfg<NT>::TW]) {
   typedef DmmaCfg<NT> C;
   const double* Are = A + (8 * tr + g) * C::LD + tg;
   const double* Aim = Are + C::PLANE;
   double P[C::TW][3][2];
+  unsigned any = 0;
 #pragma unroll
-  for (int t = 0; t < C::TW; t++)
+  for (int t = 0; t < C::TW; t++) {
+    any |= mask[t];
 #pragma unroll
     for (int i = 0; i < 3; i++) { P[t][i][0] = 0.0; P[t][i][1] = 0.0; }
+  }
 #pragma unroll
   for (int k0 = 0; k0 < C::NP; k0 += 4) {
+    if (!(any & (1u << (k0 >> 2)))) continue;
     const double ar = Are[k0], ai = Aim[k0];
     const double as = ar + ai;
 #pragma unroll
     for (int t = 0; t < C::TW; t++) {
+      if (!(mask[t] & (1u << (k0 >> 2)))) continue;
       const int n0 = 8 * (tc0 + t);
       double br, bi, bs;
       if (!BCONJT) {
@@ -218,7 +264,12 @@ __device__ __forceinline__ void dmma_rhs(const SolveParams& p, const DmmaExtra& 
   double W[C::TW][2][2];
 #pragma unroll
   for (int t = 0; t < C::TW; t++) { W[t][0][0] = W[t][0][1] = W[t][1][0] = W[t][1][1] = 0.0; }
-  warp_gemm<NT, false>(W, s.X0, s.Y, s.tr, s.tc0, s.g, s.tg);
+  {
+    unsigned mg[C::TW];
+#pragma unroll
+    for (int t = 0; t < C::TW; t++) mg[t] = s.masks[s.tr];
+    warp_gemm<NT, false>(W, s.X0, s.Y, s.tr, s.tc0, s.g, s.tg, mg);
+  }
   // A = -i W  -> T (planar): A_re = W_im, A_im = -W_re ; keep own A in K
 #pragma unroll
   for (int t = 0; t < C::TW; t++) {
@@ -245,7 +296,10 @@ __device__ __forceinline__ void dmma_rhs(const SolveParams& p, const DmmaExtra& 
     if (l + 1 < nL) prefetch_L<NT>((l & 1) ? s.X1 : s.X0, x.Lp + (long long)(l + 1) * C::MAT, s.tid);
 #pragma unroll
     for (int t = 0; t < C::TW; t++) { W[t][0][0] = W[t][0][1] = W[t][1][0] = W[t][1][1] = 0.0; }
-    warp_gemm<NT, false>(W, Lb, s.Y, s.tr, s.tc0, s.g, s.tg);
+    unsigned ma[C::TW], mb[C::TW];
+#pragma unroll
+    for (int t = 0; t < C::TW; t++) { ma[t] = s.masks[(l + 1) * 8 + s.tr]; mb[t] = s.masks[(l + 1) * 8 + s.tc0 + t]; }
+    warp_gemm<NT, false>(W, Lb, s.Y, s.tr, s.tc0, s.g, s.tg, ma);
     const double r_l = (l < p.n_c) ? 1.0 : s.cval[p.n_ch + (l - p.n_c)];
 #pragma unroll
     for (int t = 0; t < C::TW; t++) {
@@ -254,7 +308,7 @@ __device__ __forceinline__ void dmma_rhs(const SolveParams& p, const DmmaExtra& 
       *reinterpret_cast<double2*>(s.T + C::PLANE + r * C::LD + c0) = make_double2(r_l * W[t][1][0], r_l * W[t][1][1]);
     }
     __syncthreads();  // T = r_l L_l Y complete
-    warp_gemm<NT, true>(K, s.T, Lb, s.tr, s.tc0, s.g, s.tg);
+    warp_gemm<NT, true>(K, s.T, Lb, s.tr, s.tc0, s.g, s.tg, mb);
   }
 }
 
@@ -270,6 +324,11 @@ solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
   s.X1 = smem + 3 * C::MAT;
   s.red = smem + 4 * C::MAT;
   s.cval = s.red + 34;
+  {
+    unsigned* mk = reinterpret_cast<unsigned*>(s.cval + 64);
+    for (int i = threadIdx.x; i < (1 + p.n_c + p.n_ctd) * 8; i += C::NTHREADS) mk[i] = x.masks[i];
+    s.masks = mk;
+  }
   s.tid = threadIdx.x; s.w = s.tid >> 5; s.lane = s.tid & 31; s.g = s.lane >> 2; s.tg = s.lane & 3;
   s.tr = s.w / C::WPR; s.tc0 = (s.w % C::WPR) * C::TW;
   const int b = blockIdx.x, N = p.N, tid = s.tid;
@@ -489,7 +548,7 @@ static inline size_t dmma_pack_doubles(int N, int n_g, int n_l, int n_e) {
   int nt = dmma_nt(N), NP = 8 * nt, LD = NP + 4;
   size_t mat = 2 * (size_t)NP * LD;
   size_t slots_threads = dmma_ws_elems(N) / 9;  // SLOTS*NTHREADS
-  return (1 + (size_t)n_g + n_l) * mat + (size_t)n_e * slots_threads * 2 + 64;
+  return (1 + (size_t)n_g + n_l) * mat + (size_t)n_e * slots_threads * 2 + 64 + (size_t)(1 + n_l) * 8;
 }
 
 template <int NT>
@@ -508,7 +567,11 @@ static int launch_dmma_nt(const SolveParams& p, const cplx* G0, const cplx* Gk, 
   if (p.n_g > 0) { dmma_pack_planar_kernel<<<dim3(gx, p.n_g), blk, 0, st>>>(Gk, Gkp, N, C::NP, C::LD); (*launches)++; }
   if (n_l > 0) { dmma_pack_planar_kernel<<<dim3(gx, n_l), blk, 0, st>>>(p.L, Lp, N, C::NP, C::LD); (*launches)++; }
   if (p.n_e > 0) { dmma_pack_efrag_kernel<NT><<<p.n_e, C::NTHREADS, 0, st>>>(p.E, Ef, N); (*launches)++; }
-  x.G0p = G0p; x.Gkp = Gkp; x.Lp = Lp; x.Ef = Ef;
+  unsigned* masks = reinterpret_cast<unsigned*>(Ef + (size_t)p.n_e * C::SLOTS * C::NTHREADS);
+  dmma_masks_kernel<<<1 + n_l, 32, 0, st>>>(G0p, Gkp, p.n_g, Lp, n_l, NT, C::LD, 1, masks);
+  (*launches)++;
+  if (n_l > C::MAXL) return SEQ_ERR_UNSUPPORTED;
+  x.G0p = G0p; x.Gkp = Gkp; x.Lp = Lp; x.Ef = Ef; x.masks = masks;
   cudaError_t rc = cudaFuncSetAttribute(solve_dmma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   if (rc != cudaSuccess) return SEQ_ERR_CUDA;
   solve_dmma_kernel<NT><<<p.B, C::NTHREADS, C::SMEM, st>>>(p, x);

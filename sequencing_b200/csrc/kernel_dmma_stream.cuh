@@ -10,6 +10,10 @@
 // stage.  One __syncthreads per task.  Accumulators of a quadrant stay in registers over its two
 // K-blocks; finished quadrants go to L2: T (scratch, block images) or the thread-private k-stream.
 //
+// Operator tile sparsity (see kernel_dmma.cuh): block products whose operator block is entirely zero
+// are dropped from the task list (built once per launch from dmma_masks_kernel's masks), and inside
+// the remaining products the zero 8x4 fragments are skipped.
+//
 // One CTA still integrates one trajectory over the whole time span; step control, spline
 // evaluation, error norm, expectation values and state stores are fused exactly as in the
 // resident kernel.
@@ -26,8 +30,17 @@ template <int BT> struct StreamCfg {
   static constexpr int FULL = 4 * BLK;             // doubles per full matrix
   static constexpr int QSLOTS = 4 * C::SLOTS;      // double2 per thread per state vector
   static constexpr int NTHREADS = C::NTHREADS;
-  static constexpr size_t SMEM = (size_t)(4 * BLK + 34 + 64) * sizeof(double);
+  static constexpr int MAXL = 24;                  // collapse operators the task list has room for
+  static constexpr int MAXTASK = 8 + 16 * MAXL;
+  // + masks [(1 + MAXL)][4 images][8] (unsigned) + compact task list (unsigned short) + its length
+  static constexpr size_t SMEM = (size_t)(4 * BLK + 34 + 64) * sizeof(double) + (size_t)(1 + MAXL) * 32 * sizeof(unsigned)
+                                 + (size_t)MAXTASK * sizeof(unsigned short) + 16;
 };
+// task-list entry: id | flags
+#define STK_FIRST 0x1000u   // zero the accumulators before this product
+#define STK_LAST 0x2000u    // run the quadrant epilogue after it
+#define STK_NOGEMM 0x4000u  // operator block is zero: epilogue only
+#define STK_ADAG 0x8000u    // add A^dag (from T) into k before this task
 
 // interleaved complex [N,N] -> four block images (zero padded)
 __global__ void stream_pack_blocks_kernel(const cplx* __restrict__ src, double* __restrict__ dst, int N, int BS, int LD) {
@@ -88,6 +101,47 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
   const double2* tabc = p.tab + (long long)b * p.tab_bstride_c;
   const double2* tabr = p.tab_rate + (long long)b * p.tab_bstride_r;
   const double* cscale = p.coeff_scale ? p.coeff_scale + (long long)b * p.n_ch : nullptr;
+
+  unsigned* masks = reinterpret_cast<unsigned*>(cval + 64);
+  unsigned short* tlist = reinterpret_cast<unsigned short*>(masks + (1 + S::MAXL) * 32);
+  int* ntl_p = reinterpret_cast<int*>(tlist + S::MAXTASK);
+  for (int i = tid; i < (1 + nL) * 32; i += S::NTHREADS) masks[i] = x.masks[i];
+  __syncthreads();
+  if (tid == 0) {
+    // compact list of the block products that have a non-zero operator block
+    auto img_zero = [&](int op, int img) {
+      unsigned m = 0;
+      for (int t = 0; t < BT; t++) m |= masks[(op * 4 + img) * 8 + t];
+      return m == 0;
+    };
+    int n = 0;
+    bool adag_pending = false;
+    for (int grp = 0; grp < 4 + 8 * nL; grp++) {          // one group = the two K-blocks of one quadrant product
+      int id0 = 2 * grp, kind, l = -1, q;
+      if (id0 < 8) { kind = 0; q = id0 >> 1; }
+      else { int j = id0 - 8; l = j >> 4; int r = j & 15; kind = (r < 8) ? 1 : 2; q = (r & 7) >> 1; }
+      if (id0 == 8) adag_pending = true;
+      bool z[2];
+      for (int kb = 0; kb < 2; kb++) {
+        int img = (kind == 2) ? ((q & 1) * 2 + kb) : ((q >> 1) * 2 + kb);
+        z[kb] = img_zero(kind == 0 ? 0 : l + 1, img);
+      }
+      unsigned extra = adag_pending ? STK_ADAG : 0u;
+      if (z[0] && z[1]) {
+        if (kind == 2) continue;                            // nothing to add to k
+        tlist[n++] = (unsigned short)(id0 | STK_FIRST | STK_LAST | STK_NOGEMM | extra);   // T quadrant = 0
+      } else if (z[0] || z[1]) {
+        tlist[n++] = (unsigned short)((id0 + (z[0] ? 1 : 0)) | STK_FIRST | STK_LAST | extra);
+      } else {
+        tlist[n++] = (unsigned short)(id0 | STK_FIRST | extra);
+        tlist[n++] = (unsigned short)((id0 + 1) | STK_LAST);
+      }
+      adag_pending = false;
+    }
+    *ntl_p = n;
+  }
+  __syncthreads();
+  const int ntl = *ntl_p;
 
   // per-trajectory scratch: three block-image matrices, then 9 thread-private streams
   double* wsd = reinterpret_cast<double*>(p.ws + (long long)b * p.ws_stride);
@@ -202,8 +256,7 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
       }
     }
     __syncthreads();   // Gb complete
-    const int ntask = 8 + 16 * nL;
-    // task i -> operand block images, quadrant, K-block, kind (0: G*Y, 1: L*Y, 2: T*L^dag)
+    // task id -> operand block images, quadrant, K-block, kind (0: G*Y, 1: L*Y, 2: T*L^dag)
     auto task = [&](int i, const double*& A, const double*& B, int& q, int& kb, int& kind, int& l) {
       if (i < 8) {
         q = i >> 1; kb = i & 1; kind = 0; l = -1;
@@ -227,13 +280,17 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
       }
     };
     const double* A; const double* B; int q, kb, kind, l;
-    task(0, A, B, q, kb, kind, l);
-    stream_issue<BT>(smem, A, B, tid);
+    {
+      const unsigned e0 = tlist[0];
+      task(e0 & 0xfff, A, B, q, kb, kind, l);
+      if (!(e0 & STK_NOGEMM)) stream_issue<BT>(smem, A, B, tid); else cp_async_commit();
+    }
     double W[C::TW][2][2];
-    for (int i = 0; i < ntask; i++) {
+    for (int i = 0; i < ntl; i++) {
+      const unsigned ent = tlist[i];
       cp_async_wait<0>();
       __syncthreads();   // operands of task i landed; every warp finished task i-1 (its stage is free)
-      if (i == 8) {
+      if (ent & STK_ADAG) {
         // K += A1^dag, A1 = -iG rho sits complete in Tb:  K_re(r,c) += A_re(c,r), K_im(r,c) -= A_im(c,r)
         for (int qq = 0; qq < 4; qq++)
 #pragma unroll
@@ -251,18 +308,32 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
         __syncthreads();   // all A^dag reads done before any epilogue overwrites Tb
       }
       const double* cur = smem + (i & 1) * 2 * S::BLK;
-      int cq = q, ckb = kb, ckind = kind, cl_ = l;
-      if (i + 1 < ntask) {
-        task(i + 1, A, B, q, kb, kind, l);
-        stream_issue<BT>(smem + ((i + 1) & 1) * 2 * S::BLK, A, B, tid);
+      const int cq = q, ckb = kb, ckind = kind, cl_ = l;
+      if (i + 1 < ntl) {
+        const unsigned en = tlist[i + 1];
+        task(en & 0xfff, A, B, q, kb, kind, l);
+        if (!(en & STK_NOGEMM)) stream_issue<BT>(smem + ((i + 1) & 1) * 2 * S::BLK, A, B, tid); else cp_async_commit();
       }
-      if (ckb == 0) {
+      if (ent & STK_FIRST) {
 #pragma unroll
         for (int t = 0; t < C::TW; t++) { W[t][0][0] = W[t][0][1] = W[t][1][0] = W[t][1][1] = 0.0; }
       }
-      if (ckind == 2) warp_gemm<BT, true>(W, cur, cur + S::BLK, tr, tc0, g, tg);
-      else warp_gemm<BT, false>(W, cur, cur + S::BLK, tr, tc0, g, tg);
-      if (ckb == 1) {
+      if (!(ent & STK_NOGEMM)) {
+        unsigned mk[C::TW];
+        if (ckind == 2) {
+          const int img = (cq & 1) * 2 + ckb;
+#pragma unroll
+          for (int t = 0; t < C::TW; t++) mk[t] = masks[((cl_ + 1) * 4 + img) * 8 + tc0 + t];
+          warp_gemm<BT, true>(W, cur, cur + S::BLK, tr, tc0, g, tg, mk);
+        } else {
+          const int img = (cq >> 1) * 2 + ckb;
+          const unsigned m1 = masks[((ckind == 0 ? 0 : cl_ + 1) * 4 + img) * 8 + tr];
+#pragma unroll
+          for (int t = 0; t < C::TW; t++) mk[t] = m1;
+          warp_gemm<BT, false>(W, cur, cur + S::BLK, tr, tc0, g, tg, mk);
+        }
+      }
+      if (ent & STK_LAST) {
         if (ckind == 0) {
 #pragma unroll
           for (int t = 0; t < C::TW; t++) {
@@ -421,7 +492,7 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
 static inline int stream_bt(int N) { int nt = (N + 7) / 8; return (nt + 1) / 2; }   // tiles per block
 static inline bool stream_supported(int N, int max_smem) {
   int bt = stream_bt(N);
-  return N > 48 && bt >= 4 && bt <= 6 && StreamCfg<6>::SMEM <= (size_t)max_smem;
+  return N > 48 && bt >= 4 && bt <= 6 && StreamCfg<6>::SMEM <= (size_t)max_smem;   // (n_l <= MAXL is checked at launch)
 }
 template <int BT> static size_t stream_ws_elems_bt() {
   typedef StreamCfg<BT> S;
@@ -439,7 +510,7 @@ static inline size_t stream_pack_doubles(int N, int n_g, int n_l, int n_e) {
   int bt = stream_bt(N), BS = 8 * bt, LD = BS + 4;
   size_t full = 4 * 2 * (size_t)BS * LD;
   size_t qslots_threads = (stream_ws_elems(N) - (3 * full + 1) / 2 - 8) / 9;
-  return (1 + (size_t)n_g + n_l) * full + (size_t)n_e * qslots_threads * 2 + 64;
+  return (1 + (size_t)n_g + n_l) * full + (size_t)n_e * qslots_threads * 2 + 64 + (size_t)(1 + n_l) * 32;
 }
 
 template <int BT>
@@ -457,8 +528,12 @@ static int launch_stream_bt(const SolveParams& p, const cplx* G0, const cplx* Gk
   if (p.n_g > 0) { stream_pack_blocks_kernel<<<dim3(gx, p.n_g), blk, 0, st>>>(Gk, Gkp, N, S::BS, C::LD); (*launches)++; }
   if (n_l > 0) { stream_pack_blocks_kernel<<<dim3(gx, n_l), blk, 0, st>>>(p.L, Lp, N, S::BS, C::LD); (*launches)++; }
   if (p.n_e > 0) { stream_pack_efrag_kernel<BT><<<p.n_e, S::NTHREADS, 0, st>>>(p.E, Ef, N); (*launches)++; }
+  if (n_l > S::MAXL) return SEQ_ERR_UNSUPPORTED;
+  unsigned* masks = reinterpret_cast<unsigned*>(Ef + (size_t)p.n_e * S::QSLOTS * S::NTHREADS);
+  dmma_masks_kernel<<<1 + n_l, 32, 0, st>>>(G0p, Gkp, p.n_g, Lp, n_l, BT, C::LD, 4, masks);
+  (*launches)++;
   DmmaExtra x;
-  x.G0p = G0p; x.Gkp = Gkp; x.Lp = Lp; x.Ef = Ef;
+  x.G0p = G0p; x.Gkp = Gkp; x.Lp = Lp; x.Ef = Ef; x.masks = masks;
   cudaError_t rc = cudaFuncSetAttribute(solve_dmma_stream_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM);
   if (rc != cudaSuccess) return SEQ_ERR_CUDA;
   solve_dmma_stream_kernel<BT><<<p.B, S::NTHREADS, S::SMEM, st>>>(p, x);

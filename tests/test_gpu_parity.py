@@ -352,3 +352,41 @@ def test_rows_sharded_two_gpus():
            "--master-port", "29631", os.path.join(root, "tools", "mgpu_rows_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ROWS_SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def _sparsify(bp, seed):
+    """Zero random rectangles of every operator so that some (not all) 8x4 fragments / 48x48 blocks vanish."""
+    rng = np.random.default_rng(seed)
+    N = bp.N
+    def punch(op, herm):
+        keep = np.zeros((N, N), bool)
+        for _ in range(3):
+            i, j = rng.integers(0, N, 2)
+            h, w = rng.integers(1, max(2, N // 3), 2)
+            keep[i:i + h, j:j + w] = True
+        keep |= np.eye(N, dtype=bool) & (rng.random(N) < 0.5)[:, None]
+        if herm:
+            keep |= keep.T
+        return op * keep
+    bp.H0 = punch(bp.H0, True)
+    bp.Hk = np.stack([punch(h, True) for h in bp.Hk])
+    bp.Lc = np.stack([punch(L, False) for L in bp.Lc]) if bp.Lc.shape[0] else bp.Lc
+    bp.Ltd = np.stack([punch(L, False) for L in bp.Ltd]) if bp.Ltd.shape[0] else bp.Ltd
+    if bp.Lc.shape[0]:
+        bp.Lc[-1] = 0            # an all-zero collapse operator: every product is skipped
+    return bp
+
+
+def test_tensor_core_kernels_with_sparse_operators_match_generic(gpu_engine):
+    """Tile-sparsity skipping (zero 8x4 operator fragments, zero 48x48 operator blocks) is exact: the
+    tensor-core kernels agree with the FP64-FMA kernel on partially and fully empty operators."""
+    for N, method, name in ((13, _lib.METHOD_DMMA, "dmma"), (40, _lib.METHOD_DMMA, "dmma"), (48, _lib.METHOD_DMMA, "dmma"),
+                            (57, _lib.METHOD_DMMA_STREAM, "dmma_stream"), (90, _lib.METHOD_DMMA_STREAM, "dmma_stream")):
+        mk = lambda: _sparsify(random_problem(N=N, B=2, n_t=6, n_ch=2, n_c=3, n_ctd=1, n_e=2, seed=N, hscale=0.6, store_states=True), N)
+        a, g = mk(), mk()
+        a.method, g.method = method, _lib.METHOD_GENERIC
+        oa, og = gpu_engine.solve(a), gpu_engine.solve(g)
+        assert oa.method == name and np.all(oa.status == 0)
+        assert np.max(np.abs(oa.states - og.states)) < 1e-13, N
+        assert np.max(np.abs(oa.expect - og.expect)) < 1e-13, N
+        np.testing.assert_array_equal(oa.stats[:, :2], og.stats[:, :2])
