@@ -54,8 +54,11 @@ template <int NT> struct DmmaCfg {
   static constexpr int PLANE = NP * LD;          // doubles per plane
   static constexpr int MAT = 2 * PLANE;          // doubles per planar matrix
   static constexpr int SLOTS = TW * 2;           // double2 per thread per state vector
-  static constexpr int MAXL = 64;                // collapse operators whose masks fit the smem table
-  static constexpr size_t SMEM = (size_t)(4 * MAT + 34 + 64) * sizeof(double) + (size_t)(1 + MAXL) * 8 * sizeof(unsigned);
+  static constexpr int MAXL = 24;                // collapse operators whose masks / fragment lists fit the smem tables
+  static constexpr int MAXF = 2 * NT * NT;        // 8x4 fragments per operator
+  // 4 planar matrices + reduction scratch + coefficient values of the 7 stages + masks + fragment lists
+  static constexpr size_t SMEM = (size_t)(4 * MAT + 34 + 7 * 64) * sizeof(double) + (size_t)(1 + MAXL) * 8 * sizeof(unsigned)
+                                 + (size_t)(1 + MAXL) * (MAXF + 8);
 };
 
 // ---- prep: pack interleaved complex [N,N] into planar padded [2][NP][LD] (zero padded)
@@ -133,6 +136,7 @@ struct DmmaState {
   typedef DmmaCfg<NT> C;
   double* Y; double* T; double* X0; double* X1; double* red; double* cval;
   const unsigned* masks;   // smem copy: [(1 + n_l)][8]
+  const unsigned char* flist;   // [(1 + n_l)][MAXF + 8]: byte 0..3 = count (little endian), then (tr << 4 | ks) per non-zero fragment
   int tid, w, lane, g, tg, tr, tc0;
 };
 
@@ -150,35 +154,47 @@ __device__ __forceinline__ void warp_gemm(double (&acc)[DmmaCfg<NT>::TW][2][2], 
   const double* Are = A + (8 * tr + g) * C::LD + tg;
   const double* Aim = Are + C::PLANE;
   double P[C::TW][3][2];
-  unsigned any = 0;
 #pragma unroll
-  for (int t = 0; t < C::TW; t++) {
-    any |= mask[t];
+  for (int t = 0; t < C::TW; t++)
 #pragma unroll
     for (int i = 0; i < 3; i++) { P[t][i][0] = 0.0; P[t][i][1] = 0.0; }
-  }
+  // Loops over the SET BITS of the masks (dynamic trip counts: real warp-uniform branches - a static
+  // unrolled loop gets if-converted into predicated-off DMMAs that still occupy the tensor pipe).
+  if (!BCONJT) {
+    // the operator is the A operand: one mask (row tile tr) for the whole strip
+    unsigned m = mask[0];
+    while (m) {
+      const int k0 = 4 * (__ffs(m) - 1);
+      m &= m - 1;
+      const double ar = Are[k0], ai = Aim[k0];
+      const double as = ar + ai;
 #pragma unroll
-  for (int k0 = 0; k0 < C::NP; k0 += 4) {
-    if (!(any & (1u << (k0 >> 2)))) continue;
-    const double ar = Are[k0], ai = Aim[k0];
-    const double as = ar + ai;
+      for (int t = 0; t < C::TW; t++) {
+        const double* bp = Bm + (k0 + tg) * C::LD + 8 * (tc0 + t) + g;
+        const double br = bp[0], bi = bp[C::PLANE];
+        const double bs = br + bi;
+        dmma884(P[t][0][0], P[t][0][1], ar, br);
+        dmma884(P[t][1][0], P[t][1][1], ai, bi);
+        dmma884(P[t][2][0], P[t][2][1], as, bs);
+      }
+    }
+  } else {
+    // the operator is the B operand (conj-transpose): one mask per output tile (row tile tc0+t of L)
 #pragma unroll
     for (int t = 0; t < C::TW; t++) {
-      if (!(mask[t] & (1u << (k0 >> 2)))) continue;
-      const int n0 = 8 * (tc0 + t);
-      double br, bi, bs;
-      if (!BCONJT) {
-        const double* bp = Bm + (k0 + tg) * C::LD + n0 + g;
-        br = bp[0]; bi = bp[C::PLANE];
-        bs = br + bi;
-      } else {
-        const double* lp = Bm + (n0 + g) * C::LD + k0 + tg;   // B(k,n) = conj(L[n][k])
-        br = lp[0]; bi = lp[C::PLANE];
-        bs = br - bi;
+      unsigned m = mask[t];
+      const double* lrow = Bm + (8 * (tc0 + t) + g) * C::LD + tg;   // B(k,n) = conj(L[n][k])
+      while (m) {
+        const int k0 = 4 * (__ffs(m) - 1);
+        m &= m - 1;
+        const double ar = Are[k0], ai = Aim[k0];
+        const double as = ar + ai;
+        const double br = lrow[k0], bi = lrow[k0 + C::PLANE];
+        const double bs = br - bi;
+        dmma884(P[t][0][0], P[t][0][1], ar, br);
+        dmma884(P[t][1][0], P[t][1][1], ai, bi);
+        dmma884(P[t][2][0], P[t][2][1], as, bs);
       }
-      dmma884(P[t][0][0], P[t][0][1], ar, br);
-      dmma884(P[t][1][0], P[t][1][1], ai, bi);
-      dmma884(P[t][2][0], P[t][2][1], as, bs);
     }
   }
 #pragma unroll
@@ -195,70 +211,79 @@ __device__ __forceinline__ void warp_gemm(double (&acc)[DmmaCfg<NT>::TW][2][2], 
     }
 }
 
+// offset (doubles) inside a planar image of 16-byte chunk `w` (0..31) of fragment byte `fb` = (tr << 4 | ks):
+// 2 planes x 8 rows x 2 chunks
 template <int NT>
-__device__ __forceinline__ void prefetch_L(double* dst, const double* __restrict__ src, int tid) {
+__device__ __forceinline__ int frag_chunk_off(unsigned fb, int w) {
   typedef DmmaCfg<NT> C;
-  // planar padded matrix is a flat copy: MAT doubles = MAT/2 16-byte chunks
-  for (int c = tid; c < C::MAT / 2; c += C::NTHREADS) cp_async16(dst + 2 * c, src + 2 * c);
+  const int tr = fb >> 4, ks = fb & 15;
+  return (w >> 4) * C::PLANE + (8 * tr + ((w >> 1) & 7)) * C::LD + 4 * ks + 2 * (w & 1);
+}
+template <int NT>
+__device__ __forceinline__ int frag_count(const unsigned char* fl) {
+  return (int)fl[0] | ((int)fl[1] << 8);
+}
+
+// stream the NON-ZERO fragments of collapse operator `op` (1-based list index) into `dst`: the
+// other fragments of the buffer keep stale data that the masked product loops never read
+template <int NT>
+__device__ __forceinline__ void prefetch_L(const DmmaState<NT>& s, double* dst, const double* __restrict__ src, int op) {
+  typedef DmmaCfg<NT> C;
+  const unsigned char* fl = s.flist + op * (C::MAXF + 8);
+  const int n = frag_count<NT>(fl) * 32;
+  for (int c = s.tid; c < n; c += C::NTHREADS) {
+    const int off = frag_chunk_off<NT>(fl[8 + (c >> 5)], c & 31);
+    cp_async16(dst + off, src + off);
+  }
   cp_async_commit();
 }
 
 // K (registers) <- RHS(t, Y in smem).  On exit no thread is still reading Y/T/X buffers is NOT
 // guaranteed: callers must barrier before overwriting Y.
 template <int NT>
-__device__ __forceinline__ void dmma_rhs(const SolveParams& p, const DmmaExtra& x, DmmaState<NT>& s, double t,
-                                         const double2* __restrict__ tabc, const double2* __restrict__ tabr,
-                                         const double* __restrict__ cscale, double (&K)[DmmaCfg<NT>::TW][2][2]) {
+__device__ __forceinline__ void dmma_rhs(const SolveParams& p, const DmmaExtra& x, DmmaState<NT>& s, const double* __restrict__ cv,
+                                         double (&K)[DmmaCfg<NT>::TW][2][2]) {
   typedef DmmaCfg<NT> C;
   const int nL = p.n_c + p.n_ctd;
   // stream the first collapse operator behind the G products
-  if (nL > 0) prefetch_L<NT>(s.X1, x.Lp, s.tid);
-  if (s.tid < p.n_g) {
-    int m = s.tid;
-    double v;
-    if (m < p.n_ch) {
-      v = spline_eval(tabc + (long long)m * p.n_t, p.n_t, p.t0, p.dt, t);
-      if (cscale) v *= cscale[m];
-    } else {
-      v = spline_eval(tabr + (long long)(m - p.n_ch) * p.n_t, p.n_t, p.t0, p.dt, t);
-    }
-    s.cval[m] = v;
-  }
-  __syncthreads();  // cval visible; also: every warp finished the previous RHS (X0/T free), Y written
-  // G(t) = G0 + sum_m c_m Gk[m]  -> X0 (flat elementwise over the padded planar image).
-  // Operator-outer / chunk-inner with the chunk loop unrolled: CH independent 16-byte L2 loads
-  // are in flight per operator instead of one dependent load per element.
+  if (nL > 0) prefetch_L<NT>(s, s.X1, x.Lp, 1);
+  __syncthreads();  // every warp finished the previous RHS (X0/T free), Y written, cv visible
+  // G(t) = G0 + sum_m c_m Gk[m]  -> X0, only on the fragments of the union pattern.  Operators are
+  // taken two at a time with every 16-byte L2 load of the pair in flight together.
   {
-    constexpr int NCHUNK = C::MAT / 2;                                   // double2 chunks
-    constexpr int CH = (NCHUNK + C::NTHREADS - 1) / C::NTHREADS;           // chunks per thread
+    constexpr int CH = (C::MAXF * 32 + C::NTHREADS - 1) / C::NTHREADS;     // chunks per thread (dense worst case)
+    const unsigned char* fl = s.flist;
+    const int n = frag_count<NT>(fl) * 32;
+    int off[CH];
     double2 acc[CH];
-    const double2* g0 = reinterpret_cast<const double2*>(x.G0p);
 #pragma unroll
     for (int i = 0; i < CH; i++) {
-      int c = s.tid + i * C::NTHREADS;
-      acc[i] = (c < NCHUNK) ? g0[c] : make_double2(0.0, 0.0);
+      const int c = s.tid + i * C::NTHREADS;
+      off[i] = (c < n) ? frag_chunk_off<NT>(fl[8 + (c >> 5)], c & 31) : -1;
     }
-    for (int m = 0; m < p.n_g; m++) {
-      const double2* gm = reinterpret_cast<const double2*>(x.Gkp + (long long)m * C::MAT);
-      const double cv = s.cval[m];
-      double2 a[CH];
+#pragma unroll
+    for (int i = 0; i < CH; i++)
+      acc[i] = (off[i] >= 0) ? *reinterpret_cast<const double2*>(x.G0p + off[i]) : make_double2(0.0, 0.0);
+    for (int m = 0; m < p.n_g; m += 2) {
+      const bool two = m + 1 < p.n_g;
+      const double* g0 = x.Gkp + (long long)m * C::MAT;
+      const double* g1 = g0 + C::MAT;
+      const double c0 = cv[m], c1 = two ? cv[m + 1] : 0.0;
+      double2 a0[CH], a1[CH];
 #pragma unroll
       for (int i = 0; i < CH; i++) {
-        int c = s.tid + i * C::NTHREADS;
-        a[i] = (c < NCHUNK) ? gm[c] : make_double2(0.0, 0.0);
+        a0[i] = (off[i] >= 0) ? *reinterpret_cast<const double2*>(g0 + off[i]) : make_double2(0.0, 0.0);
+        a1[i] = (two && off[i] >= 0) ? *reinterpret_cast<const double2*>(g1 + off[i]) : make_double2(0.0, 0.0);
       }
 #pragma unroll
       for (int i = 0; i < CH; i++) {
-        acc[i].x = fma(cv, a[i].x, acc[i].x);
-        acc[i].y = fma(cv, a[i].y, acc[i].y);
+        acc[i].x = fma(c0, a0[i].x, acc[i].x); acc[i].y = fma(c0, a0[i].y, acc[i].y);
+        acc[i].x = fma(c1, a1[i].x, acc[i].x); acc[i].y = fma(c1, a1[i].y, acc[i].y);
       }
     }
-    double2* dst = reinterpret_cast<double2*>(s.X0);
 #pragma unroll
-    for (int i = 0; i < CH; i++) {
-      int c = s.tid + i * C::NTHREADS;
-      if (c < NCHUNK) dst[c] = acc[i];
-    }
+    for (int i = 0; i < CH; i++)
+      if (off[i] >= 0) *reinterpret_cast<double2*>(s.X0 + off[i]) = acc[i];
   }
   __syncthreads();
   double W[C::TW][2][2];
@@ -293,14 +318,14 @@ __device__ __forceinline__ void dmma_rhs(const SolveParams& p, const DmmaExtra& 
     double* Lb = (l & 1) ? s.X0 : s.X1;
     cp_async_wait<0>();
     __syncthreads();  // L_l landed for everyone; all reads of T and of the other X buffer are finished
-    if (l + 1 < nL) prefetch_L<NT>((l & 1) ? s.X1 : s.X0, x.Lp + (long long)(l + 1) * C::MAT, s.tid);
+    if (l + 1 < nL) prefetch_L<NT>(s, (l & 1) ? s.X1 : s.X0, x.Lp + (long long)(l + 1) * C::MAT, l + 2);
 #pragma unroll
     for (int t = 0; t < C::TW; t++) { W[t][0][0] = W[t][0][1] = W[t][1][0] = W[t][1][1] = 0.0; }
     unsigned ma[C::TW], mb[C::TW];
 #pragma unroll
     for (int t = 0; t < C::TW; t++) { ma[t] = s.masks[(l + 1) * 8 + s.tr]; mb[t] = s.masks[(l + 1) * 8 + s.tc0 + t]; }
     warp_gemm<NT, false>(W, Lb, s.Y, s.tr, s.tc0, s.g, s.tg, ma);
-    const double r_l = (l < p.n_c) ? 1.0 : s.cval[p.n_ch + (l - p.n_c)];
+    const double r_l = (l < p.n_c) ? 1.0 : cv[p.n_ch + (l - p.n_c)];
 #pragma unroll
     for (int t = 0; t < C::TW; t++) {
       int r = 8 * s.tr + s.g, c0 = 8 * (s.tc0 + t) + 2 * s.tg;
@@ -325,9 +350,22 @@ solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
   s.red = smem + 4 * C::MAT;
   s.cval = s.red + 34;
   {
-    unsigned* mk = reinterpret_cast<unsigned*>(s.cval + 64);
-    for (int i = threadIdx.x; i < (1 + p.n_c + p.n_ctd) * 8; i += C::NTHREADS) mk[i] = x.masks[i];
+    const int nops = 1 + p.n_c + p.n_ctd;
+    unsigned* mk = reinterpret_cast<unsigned*>(s.cval + 7 * 64);
+    unsigned char* fl = reinterpret_cast<unsigned char*>(mk + (1 + C::MAXL) * 8);
+    for (int i = threadIdx.x; i < nops * 8; i += C::NTHREADS) mk[i] = x.masks[i];
+    __syncthreads();
+    // one thread per operator lists its non-zero fragments (tr << 4 | ks)
+    for (int op = threadIdx.x; op < nops; op += C::NTHREADS) {
+      unsigned char* l = fl + op * (C::MAXF + 8);
+      int n = 0;
+      for (int tr = 0; tr < NT; tr++)
+        for (int ks = 0; ks < 2 * NT; ks++)
+          if (mk[op * 8 + tr] & (1u << ks)) l[8 + n++] = (unsigned char)((tr << 4) | ks);
+      l[0] = (unsigned char)(n & 255); l[1] = (unsigned char)(n >> 8);
+    }
     s.masks = mk;
+    s.flist = fl;
   }
   s.tid = threadIdx.x; s.w = s.tid >> 5; s.lane = s.tid & 31; s.g = s.lane >> 2; s.tg = s.lane & 3;
   s.tr = s.w / C::WPR; s.tc0 = (s.w % C::WPR) * C::TW;
@@ -385,19 +423,27 @@ solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
     double2 acc[C::TW][2];
 #pragma unroll
     for (int t = 0; t < C::TW; t++) { acc[t][0] = make_double2(0.0, 0.0); acc[t][1] = make_double2(0.0, 0.0); }
-    for (int j = 0; j < n; j++) {
-      const double aj = a[j];
-      const double2* kj = ks[j];
-      double2 kv[C::TW][2];
+    // three streams per round: their 6*TW 16-byte L2 loads are issued together
+    for (int j0 = 0; j0 < n; j0 += 3) {
+      double2 kv[3][C::TW][2];
+      double aj[3];
 #pragma unroll
-      for (int t = 0; t < C::TW; t++) { kv[t][0] = SLOT(kj, t, 0); kv[t][1] = SLOT(kj, t, 1); }
+      for (int u = 0; u < 3; u++) {
+        const bool on = j0 + u < n;
+        aj[u] = on ? a[j0 + u] : 0.0;
+        const double2* kj = ks[on ? j0 + u : j0];
 #pragma unroll
-      for (int t = 0; t < C::TW; t++)
+        for (int t = 0; t < C::TW; t++) { kv[u][t][0] = SLOT(kj, t, 0); kv[u][t][1] = SLOT(kj, t, 1); }
+      }
 #pragma unroll
-        for (int pl = 0; pl < 2; pl++) {
-          acc[t][pl].x = fma(aj, kv[t][pl].x, acc[t][pl].x);
-          acc[t][pl].y = fma(aj, kv[t][pl].y, acc[t][pl].y);
-        }
+      for (int u = 0; u < 3; u++)
+#pragma unroll
+        for (int t = 0; t < C::TW; t++)
+#pragma unroll
+          for (int pl = 0; pl < 2; pl++) {
+            acc[t][pl].x = fma(aj[u], kv[u][t][pl].x, acc[t][pl].x);
+            acc[t][pl].y = fma(aj[u], kv[u][t][pl].y, acc[t][pl].y);
+          }
     }
 #pragma unroll
     for (int t = 0; t < C::TW; t++)
@@ -421,13 +467,27 @@ solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       bool landing, capped;
       while (ctl.status == SEQ_STATUS_OK && ctl_next(ctl, p, t_target, htry, landing, capped)) {
         const int pair = ctl.pair, S = RK_STAGES[pair];
+        // spline values of every time-dependent term at every stage time of this step (one L2 round
+        // trip per step instead of one per RHS); made visible by the barrier inside the first dmma_rhs
+        for (int i = tid; i < S * p.n_g; i += C::NTHREADS) {
+          const int st = i / p.n_g, m = i - st * p.n_g;
+          const double ts = ctl.t + RK_C[pair][st] * htry;
+          double v;
+          if (m < p.n_ch) {
+            v = spline_eval(tabc + (long long)m * p.n_t, p.n_t, p.t0, p.dt, ts);
+            if (cscale) v *= cscale[m];
+          } else {
+            v = spline_eval(tabr + (long long)(m - p.n_ch) * p.n_t, p.n_t, p.t0, p.dt, ts);
+          }
+          s.cval[st * 64 + m] = v;
+        }
         for (int st = ctl.have_k1 ? 1 : 0; st < S; st++) {
           double v[C::TW][2][2];
           combine(v, htry, st, RK_A[pair][st], kp);    // st == S-1: v = y_new
           __syncthreads();                             // every warp is out of the previous RHS
           put_Y(v);
           if (st == S - 1) store_stream(syn, v);
-          dmma_rhs<NT>(p, x, s, ctl.t + RK_C[pair][st] * htry, tabc, tabr, cscale, K);
+          dmma_rhs<NT>(p, x, s, s.cval + st * 64, K);
           store_stream(kp[st], K);
           ctl.nrhs++;
         }

@@ -271,8 +271,9 @@ static int pick_method(const seq_engine* e, const seq_solve_desc* d) {
   if (d->method != SEQ_METHOD_AUTO) return d->method;
   const bool ket = d->flags & SEQ_FLAG_KET;
   if (!ket && d->H0_batch_stride == 0 && small_supported(d->N, d->n_ch + d->n_ctd, d->n_e)) return SEQ_METHOD_SMALL;
-  if (!ket && d->H0_batch_stride == 0 && dmma_supported(d->N, e ? e->max_smem_optin : 232448)) return SEQ_METHOD_DMMA;
-  if (!ket && d->H0_batch_stride == 0 && stream_supported(d->N, e ? e->max_smem_optin : 232448)) return SEQ_METHOD_DMMA_STREAM;
+  const int n_l = d->n_c + d->n_ctd;
+  if (!ket && d->H0_batch_stride == 0 && n_l <= DmmaCfg<6>::MAXL && dmma_supported(d->N, e ? e->max_smem_optin : 232448)) return SEQ_METHOD_DMMA;
+  if (!ket && d->H0_batch_stride == 0 && n_l <= StreamCfg<6>::MAXL && stream_supported(d->N, e ? e->max_smem_optin : 232448)) return SEQ_METHOD_DMMA_STREAM;
   if (!ket && d->H0_batch_stride == 0 && d->N > 96) return SEQ_METHOD_LARGE;
   return SEQ_METHOD_GENERIC;
 }

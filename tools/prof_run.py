@@ -16,4 +16,5 @@ elif which == "c1":
     bp = w.c1_rabi(16384)
 for _ in range(2):
     out = eng.solve(bp)
-print(which, "method", out.method, "kernel_ms", out.kernel_ms, "ok", bool(np.all(out.status == 0)), "steps", out.stats[:, 0].mean())
+print(which, "method", out.method, "kernel_ms", out.kernel_ms, "ok", bool(np.all(out.status == 0)), "steps", out.stats[:, 0].mean(),
+      "rejected", out.stats[:, 1].mean(), "rhs_total", int(out.stats[:, 2].sum()), "B", bp.B)
