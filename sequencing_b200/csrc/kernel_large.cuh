@@ -12,6 +12,11 @@
 //    contiguous ranges, so the SMs stay evenly loaded whatever the tile count is (row-sharded C5 has
 //    5 x 20 = 100 tiles for 148 SMs).  Partial tiles are combined with FP64 reductions (red.add.f64)
 //    into a pre-initialised C, which is also how the products accumulate into K.
+//  * operator CHUNK SPARSITY: every product has an operator (G or L_l) as its A operand (NN) or as its
+//    conj-transposed B operand (NH).  large_sched_kernel lists, per operator row tile, the K chunks
+//    (16 columns) that hold a non-zero; the stream-K iteration space is built from those lists only, so
+//    Kronecker-structured operators (C5: ~4 of 118 chunks per tile) cost what they contain.  Dense
+//    operators list every chunk.
 // The Runge-Kutta driver (host loop, one device sync per step for the error norm) and the
 // row-sharding exchange (all-gather of the stage state per RHS) live in seq_engine.cu.
 #pragma once
@@ -43,6 +48,10 @@ struct ZgemmArgs {
   int M, Ncols, K;                                     // K multiple of 16; Ncols even
   double alpha_r, alpha_i;
   const double* scale;                                 // optional device scalar (time-dependent collapse rate)
+  // chunk schedule of the operator operand (A for NN: per 48-row tile; B for NH: per 96-row tile):
+  // pref[t] = number of listed chunks in tiles < t (pref[tiles] = all), idx[t * kchunks + i] = i-th listed chunk of tile t
+  const int* pref;
+  const unsigned short* idx;
 };
 
 template <bool BH>
@@ -53,7 +62,11 @@ __global__ void __launch_bounds__(LargeGemmCfg::NTHREADS, 1) zgemm_dmma_kernel(c
   const int wr = w / 6, wc = w % 6;   // warp grid 2 x 6 -> rows 24*wr, cols 16*wc
   const int tiles_m = (a.M + C::TM - 1) / C::TM, tiles_n = (a.Ncols + C::TN - 1) / C::TN;
   const int kchunks = a.K / C::KC;
-  const long long total = (long long)tiles_m * tiles_n * kchunks;
+  // iteration space: tiles ordered tm-fastest; a tile owns the listed chunks of its operator row tile
+  // (NN: row tile tm of A; NH: row tile tn of B)
+  const int nsched = BH ? tiles_n : tiles_m;
+  const long long listed = a.pref[nsched];
+  const long long total = listed * (BH ? tiles_m : tiles_n);
   const long long per = (total + gridDim.x - 1) / gridDim.x;
   long long it = per * blockIdx.x;
   const long long it_end = (it + per < total) ? it + per : total;
@@ -61,16 +74,34 @@ __global__ void __launch_bounds__(LargeGemmCfg::NTHREADS, 1) zgemm_dmma_kernel(c
   const double alr = a.alpha_r * sc, ali = a.alpha_i * sc;
 
   while (it < it_end) {
-    const int tile = (int)(it / kchunks);
-    const int kc0 = (int)(it - (long long)tile * kchunks);
-    const int kc1 = (int)((it_end - (long long)tile * kchunks < kchunks) ? (it_end - (long long)tile * kchunks) : kchunks);
-    const int tn = tile / tiles_m, tm = tile - tn * tiles_m;
+    int tm, tn, pos0, cnt;
+    if (BH) {
+      // per tn: tiles_m * cnt[tn] iterations
+      tn = 0;
+      while (tn + 1 < tiles_n && (long long)a.pref[tn + 1] * tiles_m <= it) tn++;
+      cnt = a.pref[tn + 1] - a.pref[tn];
+      const long long r = it - (long long)a.pref[tn] * tiles_m;
+      tm = (int)(r / cnt);
+      pos0 = (int)(r - (long long)tm * cnt);
+    } else {
+      // per tn: listed iterations, split over tm by pref
+      tn = (int)(it / listed);
+      const int r = (int)(it - (long long)tn * listed);
+      tm = 0;
+      while (tm + 1 < tiles_m && a.pref[tm + 1] <= r) tm++;
+      cnt = a.pref[tm + 1] - a.pref[tm];
+      pos0 = r - a.pref[tm];
+    }
+    const long long left = it_end - it;
+    const int pos1 = (int)((cnt - pos0 < left) ? cnt : pos0 + left);
+    const unsigned short* list = a.idx + (long long)(BH ? tn : tm) * kchunks;
+    const int kc0 = pos0, kc1 = pos1;    // positions in the chunk list
     const int m0 = tm * C::TM, n0 = tn * C::TN;
 
     auto load_stage = [&](int stage, int kc) {
       double* As = smem_large + stage * C::STAGE;
       double* Bs = As + 2 * C::A_PLANE;
-      const int k0 = kc * C::KC;
+      const int k0 = (int)list[kc] * C::KC;
       // A: 2 planes x 48 rows x 8 chunks
       for (int c = tid; c < 2 * C::TM * (C::KC / 2); c += C::NTHREADS) {
         const int pl = c / (C::TM * (C::KC / 2)), rem = c - pl * (C::TM * (C::KC / 2));
@@ -286,6 +317,48 @@ __global__ void large_expect_kernel(const cplx* __restrict__ E, const double* __
   if (threadIdx.x == 0) { atomicAdd(&out[e].x, acc.x); atomicAdd(&out[e].y, acc.y); }
 }
 
+// ---- chunk schedule of an operator (or of the union pattern of `nsrc` consecutive operators):
+// block t lists the K chunks whose tile_rows x 16 window (rows row_begin + t*tile_rows ...) holds a non-zero
+__global__ void large_sched_kernel(const double* __restrict__ base, long long op_stride, int nsrc, int NP, long long plane,
+                                   long long row_begin, int rows_total, int tile_rows, int kchunks,
+                                   unsigned short* __restrict__ idx, int* __restrict__ cnt) {
+  extern __shared__ unsigned char sched_flags[];
+  const int t = blockIdx.x;
+  const long long r0 = row_begin + (long long)t * tile_rows;
+  long long r1 = r0 + tile_rows;
+  if (r1 > row_begin + rows_total) r1 = row_begin + rows_total;
+  for (int kc = threadIdx.x; kc < kchunks; kc += blockDim.x) {
+    bool nz = false;
+    for (int sidx = 0; sidx < nsrc && !nz; sidx++) {
+      const double* re = base + sidx * op_stride;
+      const double* im = re + plane;
+      for (long long r = r0; r < r1 && !nz; r++) {
+        const double2* pr = reinterpret_cast<const double2*>(re + r * NP + 16 * kc);
+        const double2* pi = reinterpret_cast<const double2*>(im + r * NP + 16 * kc);
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const double2 a = pr[c], b = pi[c];
+          nz = nz || a.x != 0.0 || a.y != 0.0 || b.x != 0.0 || b.y != 0.0;
+        }
+      }
+    }
+    sched_flags[kc] = nz ? 1 : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int kc = 0; kc < kchunks; kc++)
+      if (sched_flags[kc]) idx[(long long)t * kchunks + n++] = (unsigned short)kc;
+    cnt[t] = n;
+  }
+}
+__global__ void large_pref_kernel(const int* __restrict__ cnt, int ntiles, int* __restrict__ pref) {
+  if (blockIdx.x || threadIdx.x) return;
+  int acc = 0;
+  for (int t = 0; t < ntiles; t++) { pref[t] = acc; acc += cnt[t]; }
+  pref[ntiles] = acc;
+}
+
 static inline int large_np(int N) { return (N + 15) / 16 * 16; }
 
 template <bool BH>
@@ -296,11 +369,8 @@ static int launch_zgemm(const ZgemmArgs& a, int sms, cudaStream_t st) {
       return SEQ_ERR_CUDA;
     configured = true;
   }
-  const long long tiles = (long long)((a.M + LargeGemmCfg::TM - 1) / LargeGemmCfg::TM) * ((a.Ncols + LargeGemmCfg::TN - 1) / LargeGemmCfg::TN);
-  const long long total = tiles * (a.K / LargeGemmCfg::KC);
-  int grid = sms;
-  if (total < grid) grid = (int)total;
-  if (grid < 1) return SEQ_OK;
+  const int grid = sms;   // stream-K: one CTA per SM (the listed iteration count lives on the device)
+  if (a.M < 1 || a.Ncols < 1) return SEQ_OK;
   zgemm_dmma_kernel<BH><<<grid, LargeGemmCfg::NTHREADS, LargeGemmCfg::SMEM, st>>>(a);
   return SEQ_OK;
 }

@@ -33,7 +33,7 @@ struct seq_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
-  DevBuf ws, gbuf, tab, cprime, pack, stage_in, stage_out, large;
+  DevBuf ws, gbuf, tab, cprime, pack, stage_in, stage_out, large, sched;
   const seq_comm* comm = nullptr;   // set for the duration of seq_engine_solve_sharded
   double* host_err = nullptr;       // pinned: error norm read back once per step by the large-N stepper
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -322,7 +322,7 @@ int seq_engine_destroy(seq_engine* e) {
   if (!e) return SEQ_OK;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  DevBuf* bufs[] = {&e->ws, &e->gbuf, &e->tab, &e->cprime, &e->pack, &e->stage_in, &e->stage_out, &e->large};
+  DevBuf* bufs[] = {&e->ws, &e->gbuf, &e->tab, &e->cprime, &e->pack, &e->stage_in, &e->stage_out, &e->large, &e->sched};
   for (DevBuf* b : bufs) if (b->ptr) cudaFree(b->ptr);
   if (e->host_err) cudaFreeHost(e->host_err);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -454,6 +454,36 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
   for (int g = 0; g < n_g; g++) { large_pack_kernel<<<grid_for(oplane, sms), 256, 0, st>>>(Gk + (size_t)g * N * N, Gkp + (size_t)g * opsz, N, NP, NP); e->launches++; }
   for (int l = 0; l < n_l; l++) { large_pack_kernel<<<grid_for(oplane, sms), 256, 0, st>>>(p.L + (size_t)l * N * N, Lp + (size_t)l * opsz, N, NP, NP); e->launches++; }
 
+  // chunk schedules: per operator (0: union pattern of G0 and every Gk; 1..: L_l) one list for its use as
+  // the A operand (48-row tiles of this rank's rows) and one for its use as the B^H operand (96-row tiles)
+  const int kchunks = NP / LargeGemmCfg::KC;
+  const int tilesA = (Mrows + LargeGemmCfg::TM - 1) / LargeGemmCfg::TM, tilesB = (NP + LargeGemmCfg::TN - 1) / LargeGemmCfg::TN;
+  const int nops = 1 + n_l;
+  const size_t idx_per_op = (size_t)(tilesA + tilesB) * kchunks;          // unsigned short
+  const size_t int_per_op = (size_t)2 * (tilesA + tilesB) + 4;            // cnt + pref
+  rc = reserve(e, e->sched, nops * (idx_per_op * sizeof(unsigned short) + int_per_op * sizeof(int)) + 256);
+  if (rc) return rc;
+  int* s_int = (int*)e->sched.ptr;
+  unsigned short* s_idx = (unsigned short*)(s_int + nops * int_per_op);
+  auto idxA = [&](int op) { return s_idx + (size_t)op * idx_per_op; };
+  auto idxB = [&](int op) { return idxA(op) + (size_t)tilesA * kchunks; };
+  auto prefA = [&](int op) { return s_int + (size_t)op * int_per_op + (tilesA + tilesB); };
+  auto prefB = [&](int op) { return prefA(op) + tilesA + 1; };
+  for (int op = 0; op < nops; op++) {
+    const double* src = (op == 0) ? G0p : Lp + (size_t)(op - 1) * opsz;
+    const int nsrc = (op == 0) ? 1 + n_g : 1;     // G0p and Gkp are contiguous
+    int* cntA = s_int + (size_t)op * int_per_op;
+    int* cntB = cntA + tilesA;
+    if (tilesA > 0) {
+      large_sched_kernel<<<tilesA, 128, kchunks, st>>>(src, opsz, nsrc, NP, oplane, row0, Mrows, LargeGemmCfg::TM, kchunks, idxA(op), cntA);
+      e->launches++;
+    }
+    large_sched_kernel<<<tilesB, 128, kchunks, st>>>(src, opsz, nsrc, NP, oplane, 0, NP, LargeGemmCfg::TN, kchunks, idxB(op), cntB);
+    large_pref_kernel<<<1, 32, 0, st>>>(cntA, tilesA, prefA(op));
+    large_pref_kernel<<<1, 32, 0, st>>>(cntB, tilesB, prefB(op));
+    e->launches += 3;
+  }
+
   std::vector<int> out_idx(d->n_out);
   CUDA_TRY(e, cudaMemcpyAsync(out_idx.data(), d->out_idx, sizeof(int) * d->n_out, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(e, cudaStreamSynchronize(st));
@@ -477,11 +507,13 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
       a.Br = Yfull; a.Bi = Yfull + yplane; a.ldb = NP;
       a.Cr = kout; a.Ci = kout + mplane; a.ldc = NP;
       a.M = Mrows; a.Ncols = NP; a.K = NP; a.alpha_r = 0.0; a.alpha_i = -1.0; a.scale = nullptr;
+      a.pref = prefA(0); a.idx = idxA(0);
       int r2 = launch_zgemm<false>(a, sms, st); if (r2) return r2; e->launches++;
       // K += i Y[R,:] G^dag
       a.Ar = Yfull + row0 * NP; a.Ai = Yfull + yplane + row0 * NP;
       a.Br = Gt; a.Bi = Gt + oplane;
       a.alpha_i = 1.0;
+      a.pref = prefB(0); a.idx = idxB(0);
       r2 = launch_zgemm<true>(a, sms, st); if (r2) return r2; e->launches++;
       for (int l = 0; l < n_l; l++) {
         const double* Ll = Lp + (size_t)l * opsz;
@@ -489,11 +521,13 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
         a.Ar = Ll + row0 * NP; a.Ai = Ll + oplane + row0 * NP;
         a.Br = Yfull; a.Bi = Yfull + yplane;
         a.Cr = T; a.Ci = T + mplane; a.alpha_r = 1.0; a.alpha_i = 0.0; a.scale = nullptr;
+        a.pref = prefA(l + 1); a.idx = idxA(l + 1);
         r2 = launch_zgemm<false>(a, sms, st); if (r2) return r2; e->launches++;
         a.Ar = T; a.Ai = T + mplane;
         a.Br = Ll; a.Bi = Ll + oplane;
         a.Cr = kout; a.Ci = kout + mplane;
         a.scale = (l < p.n_c) ? nullptr : cval + p.n_ch + (l - p.n_c);
+        a.pref = prefB(l + 1); a.idx = idxB(l + 1);
         r2 = launch_zgemm<true>(a, sms, st); if (r2) return r2; e->launches++;
       }
       return SEQ_OK;
