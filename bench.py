@@ -80,6 +80,11 @@ def build_workload(name):
     elif name == "c4":
         bp = w.c4_two_transmons_bus(512)
         desc = "C4 two transmons(3) + bus cavity(10), full collapse-operator set, batch 512"
+    elif name == "c5":
+        n_ops = int(os.environ.get("SEQ_C5_OPS", "5"))
+        bp = w.c5_transmon_two_cavities(n_ops=n_ops)
+        desc = (f"C5 transmon(3) x cavity(25) x cavity(25), N=1875, ONE system, first {n_ops} of the sequence's operations "
+                f"({bp.coeff.shape[-1]} samples); rho row-sharded over the GPUs (strong scaling)")
     elif name == "c2small":
         bp = w.c2_selective(4, 4, sigma=25)
         desc = "C2-small (smoke) transmon(3)x cavity(15), 4x4 sweep, n_t=100"
@@ -269,7 +274,8 @@ def ours(args):
     from sequencing_b200.solver import Engine
 
     bp, desc = build_workload(args.workload)   # every rank integrates its own shard of this size (weak scaling)
-    if world > 1:
+    rows_mode = args.workload == "c5"              # ONE system, rho row-sharded: strong scaling, collectives inside the solve
+    if world > 1 and not rows_mode:
         # rank-dependent sweep values: scale the amplitudes a little so shards are distinct units
         bp.coeff = bp.coeff * (1.0 + 1e-3 * rank)
     eng = Engine.get(local)
@@ -281,8 +287,13 @@ def ours(args):
         if world > 1:
             dist.barrier()
 
+    comm = keep = None
+    if rows_mode and world > 1:
+        from sequencing_b200.distributed import make_comm
+        comm, keep = make_comm()
+
     def gather(outs):
-        if world == 1:
+        if world == 1 or rows_mode:
             return
         for key in ("expect", "final_state"):
             t = outs[key]
@@ -293,8 +304,13 @@ def ours(args):
     tens = eng.to_device(bp)
     torch.cuda.synchronize()
     kernel_ms, step_ms, launches = [], [], 0
+    def solve_dev():
+        if rows_mode:
+            return eng.solve_rows_sharded(bp, comm, tens=tens, to_host=False)
+        return eng.solve_device(tens, bp)
+
     for w in range(args.warmup):
-        res = eng.solve_device(tens, bp)
+        res = solve_dev()
         gather(res["out"])
         torch.cuda.synchronize()
     sampler = ClockSampler(local)
@@ -306,7 +322,7 @@ def ours(args):
         flush_buf.fill_(k)            # L2 flush between timed iterations (outside the events)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        res = eng.solve_device(tens, bp)
+        res = solve_dev()
         gather(res["out"])
         e1.record()
         torch.cuda.synchronize()
@@ -323,7 +339,8 @@ def ours(args):
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     total_ms = float(t_dev.item())
-    value = bp.B * world * args.steps / (total_ms * 1e-3)
+    n_units = bp.B if rows_mode else bp.B * world      # rows mode: the ranks share ONE trajectory
+    value = n_units * args.steps / (total_ms * 1e-3)
 
     # ---- end-to-end through the C ABI on pinned host buffers ---------------------------------
     host = eng._host_arrays(bp)
@@ -337,28 +354,34 @@ def ours(args):
         if name in pinned:
             setattr(bp_h, name, pinned[name].numpy())
     h2d = sum(int(v.numel() * v.element_size()) for v in pinned.values())
-    eng.solve_host_abi(bp_h)  # warm the staging buffers
+    def solve_host():
+        if rows_mode:                      # public API of the sharded mode: host arrays in, host arrays out
+            return eng.solve_rows_sharded(bp_h, comm)
+        return eng.solve_host_abi(bp_h)    # returns after D2H + stream sync
+
+    solve_host()  # warm the staging buffers
     barrier()
     e2e_t = []
     for k in range(max(1, min(args.steps, 3))):
         flush_buf.fill_(k)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        out_h = eng.solve_host_abi(bp_h)   # returns after D2H + stream sync
+        out_h = solve_host()
         e2e_t.append(time.perf_counter() - t0)
         launches += eng.last_launches
     d2h = int(out_h.expect.nbytes + out_h.final_state.nbytes + out_h.status.nbytes + out_h.stats.nbytes)
     t_e2e = torch.tensor([sum(e2e_t)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = bp.B * world * len(e2e_t) / float(t_e2e.item())
+    e2e_value = n_units * len(e2e_t) / float(t_e2e.item())
 
     if rank == 0:
         flops, bytes_alg, f_rhs = algorithmic(bp, stats)
         k_ms = float(np.mean(kernel_ms))
         achieved = flops / (k_ms * 1e-3) / 1e12
         s = shape_of(bp)
-        kname = f"solve_{out_h.method}_kernel"
+        kname = "zgemm_dmma_kernel" if out_h.method == "large" else f"solve_{out_h.method}_kernel"
+        peak_scale = world if rows_mode else 1     # rows mode: the algorithmic flops of the ONE system are spread over all GPUs
         if out_h.method == "small":
             # N <= 6: below one DMMA tile -> the HBM roofline, FP64-FMA ceiling noted
             peak, src = hbm_peak()
@@ -370,8 +393,8 @@ def ours(args):
                     "note": "FP64-FMA-issue bound, not HBM bound: the kernel executes (1+n_g) N^4 real FMAs per RHS "
                             "(real superoperator form) instead of the 8 N^3 (1+2 n_c) algorithmic flops"}
         else:
-            roof = {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                    "frac": achieved / FP64_DMMA_PEAK_TFLOPS, "traffic": ncu_traffic(kname),
+            roof = {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS * peak_scale, "unit": "TFLOP/s",
+                    "frac": achieved / (FP64_DMMA_PEAK_TFLOPS * peak_scale), "traffic": ncu_traffic(kname),
                     "kernel": kname, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (total_ms / args.steps),
                     "flops_per_rhs": f_rhs, "rhs_evals_per_launch": float(np.sum(stats[:, 2])),
                     "peak_source": "FP64 DMMA.8x8x4 issue-rate microbenchmark tools/fp64_peak.cu on this pool's B200 "
@@ -394,10 +417,10 @@ def ours(args):
                              "(oracle/qutip4_oracle.py: CSR Liouvillian + scipy ZVODE-Adams, reference options)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if rows_mode else "weak", "vs_baseline": None,
             "dtype": "c128 (f64)", "data": "synthetic",
             "config": {"workload": desc, **s, "B_per_gpu": bp.B, "atol": bp.atol, "rtol": bp.rtol, "max_step": bp.max_step,
-                       "parallelism": f"batch-sharded x{world}", "l2": "256 MiB L2 flush between timed steps; per-step scratch 300 MB > L2",
+                       "parallelism": (f"rho row-sharded x{world}, all-gather of the stage state per RHS" if rows_mode else f"batch-sharded x{world}"), "l2": "256 MiB L2 flush between timed steps; per-step scratch 300 MB > L2",
                        "method": out_h.method, "steps_accepted_mean": float(stats[:, 0].mean()), "steps_rejected_mean": float(stats[:, 1].mean())},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,

@@ -246,11 +246,13 @@ class Engine:
         self._last_method = self.lib.seq_engine_select_method(self.handle, C.byref(desc))
         return self._finish(bp, outs)
 
-    def solve_rows_sharded(self, bp: BatchProblem, comm: "_lib.Comm") -> BatchOutput:
+    def solve_rows_sharded(self, bp: BatchProblem, comm: "_lib.Comm", tens=None, to_host=True):
         """ONE large system with rho row-sharded across the ranks of ``comm`` (C5): every rank calls
         this with the same ``bp`` and gets the full result.  ``comm`` carries the all-gather /
-        all-reduce hooks (``sequencing_b200.distributed.make_comm``); device-resident operands."""
-        tens = self.to_device(bp)
+        all-reduce hooks (``sequencing_b200.distributed.make_comm``).  ``tens``: operands already staged
+        by ``to_device``; ``to_host=False`` returns the device output tensors instead of a BatchOutput."""
+        if tens is None:
+            tens = self.to_device(bp)
         torch = self.torch
         with torch.cuda.device(self.device):
             outs = {}
@@ -265,6 +267,8 @@ class Engine:
             self.total_launches += self.last_launches
             self._last_method = _lib.METHOD_LARGE if (comm is not None and comm.world > 1) else self.lib.seq_engine_select_method(self.handle, C.byref(desc))
             torch.cuda.synchronize(self.device)
+        if not to_host:
+            return {"out": outs, "in": tens}
         return self._finish(bp, {k: v.cpu().numpy() for k, v in outs.items()})
 
     def _finish(self, bp, out) -> BatchOutput:
