@@ -30,6 +30,21 @@
 
 namespace seq {
 
+// Optional region timers (build with -DSEQ_PROFILE_REGIONS; read back with cudaMemcpyFromSymbol via
+// tools/region_prof.py): thread 0 of CTA 0 accumulates clock64() deltas per region of the step loop.
+#ifdef SEQ_PROFILE_REGIONS
+__device__ unsigned long long seq_prof[16];
+#define PROF_DECL unsigned long long _pt = clock64();
+#define PROF(r) do { if (threadIdx.x == 0 && blockIdx.x == 0) { unsigned long long _n = clock64(); seq_prof[r] += _n - _pt; _pt = _n; } } while (0)
+#define PROF_ARG , unsigned long long& _pt
+#define PROF_PASS , _pt
+#else
+#define PROF_DECL
+#define PROF(r)
+#define PROF_ARG
+#define PROF_PASS
+#endif
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -57,8 +72,14 @@ template <int NT> struct DmmaCfg {
   static constexpr int MAXL = 24;                // collapse operators whose masks / fragment lists fit the smem tables
   static constexpr int MAXF = 2 * NT * NT;        // 8x4 fragments per operator
   // 4 planar matrices + reduction scratch + coefficient values of the 7 stages + masks + fragment lists
-  static constexpr size_t SMEM = (size_t)(4 * MAT + 34 + 7 * 64) * sizeof(double) + (size_t)(1 + MAXL) * 8 * sizeof(unsigned)
-                                 + (size_t)(1 + MAXL) * (MAXF + 8);
+  static constexpr size_t SMEM_BASE = (size_t)(4 * MAT + 34 + 7 * 64) * sizeof(double) + (size_t)(1 + MAXL) * 8 * sizeof(unsigned)
+                                      + (size_t)(((1 + MAXL) * (MAXF + 8) + 15) / 16 * 16);
+  // the rest of the SM's shared memory keeps the non-zero fragments of G0 and every Gk resident
+  // (512 B per fragment), so the per-RHS G(t) assembly never leaves the SM when they fit
+  static constexpr size_t SMEM_LIMIT = 227 * 1024;
+  // (only where the CTA already owns the SM: smaller NT keep several CTAs per SM instead)
+  static constexpr int GRES_FRAGS = (NT == 6) ? (int)((SMEM_LIMIT - SMEM_BASE) / 512) : 0;
+  static constexpr size_t SMEM = SMEM_BASE + (size_t)GRES_FRAGS * 512;
 };
 
 // ---- prep: pack interleaved complex [N,N] into planar padded [2][NP][LD] (zero padded)
@@ -137,6 +158,7 @@ struct DmmaState {
   double* Y; double* T; double* X0; double* X1; double* red; double* cval;
   const unsigned* masks;   // smem copy: [(1 + n_l)][8]
   const unsigned char* flist;   // [(1 + n_l)][MAXF + 8]: byte 0..3 = count (little endian), then (tr << 4 | ks) per non-zero fragment
+  const double* gres;           // resident fragments of G0, Gk[0..n_g): [(1 + n_g)][nfrag][64] (nullptr: they do not fit)
   int tid, w, lane, g, tg, tr, tc0;
 };
 
@@ -242,15 +264,29 @@ __device__ __forceinline__ void prefetch_L(const DmmaState<NT>& s, double* dst, 
 // guaranteed: callers must barrier before overwriting Y.
 template <int NT>
 __device__ __forceinline__ void dmma_rhs(const SolveParams& p, const DmmaExtra& x, DmmaState<NT>& s, const double* __restrict__ cv,
-                                         double (&K)[DmmaCfg<NT>::TW][2][2]) {
+                                         double (&K)[DmmaCfg<NT>::TW][2][2] PROF_ARG) {
   typedef DmmaCfg<NT> C;
   const int nL = p.n_c + p.n_ctd;
   // stream the first collapse operator behind the G products
   if (nL > 0) prefetch_L<NT>(s, s.X1, x.Lp, 1);
   __syncthreads();  // every warp finished the previous RHS (X0/T free), Y written, cv visible
+  PROF(1);
   // G(t) = G0 + sum_m c_m Gk[m]  -> X0, only on the fragments of the union pattern.  Operators are
   // taken two at a time with every 16-byte L2 load of the pair in flight together.
-  {
+  if (s.gres) {
+    // resident fragments: shared memory -> shared memory
+    const unsigned char* fl = s.flist;
+    const int n = frag_count<NT>(fl) * 32;
+    const double2* gr = reinterpret_cast<const double2*>(s.gres);
+    for (int c = s.tid; c < n; c += C::NTHREADS) {
+      double2 acc = gr[c];
+      for (int m = 0; m < p.n_g; m++) {
+        const double2 a = gr[(m + 1) * n + c];
+        acc.x = fma(cv[m], a.x, acc.x); acc.y = fma(cv[m], a.y, acc.y);
+      }
+      *reinterpret_cast<double2*>(s.X0 + frag_chunk_off<NT>(fl[8 + (c >> 5)], c & 31)) = acc;
+    }
+  } else {
     constexpr int CH = (C::MAXF * 32 + C::NTHREADS - 1) / C::NTHREADS;     // chunks per thread (dense worst case)
     const unsigned char* fl = s.flist;
     const int n = frag_count<NT>(fl) * 32;
@@ -286,6 +322,7 @@ __device__ __forceinline__ void dmma_rhs(const SolveParams& p, const DmmaExtra& 
       if (off[i] >= 0) *reinterpret_cast<double2*>(s.X0 + off[i]) = acc[i];
   }
   __syncthreads();
+  PROF(2);
   double W[C::TW][2][2];
 #pragma unroll
   for (int t = 0; t < C::TW; t++) { W[t][0][0] = W[t][0][1] = W[t][1][0] = W[t][1][1] = 0.0; }
@@ -305,6 +342,7 @@ __device__ __forceinline__ void dmma_rhs(const SolveParams& p, const DmmaExtra& 
     K[t][0][0] = are0; K[t][0][1] = are1; K[t][1][0] = aim0; K[t][1][1] = aim1;
   }
   __syncthreads();  // A complete; X0 (G) no longer needed
+  PROF(3);
   // K += A^dag : K_re(i,j) += A_re(j,i) ; K_im(i,j) -= A_im(j,i)
 #pragma unroll
   for (int t = 0; t < C::TW; t++) {
@@ -317,7 +355,9 @@ __device__ __forceinline__ void dmma_rhs(const SolveParams& p, const DmmaExtra& 
   for (int l = 0; l < nL; l++) {
     double* Lb = (l & 1) ? s.X0 : s.X1;
     cp_async_wait<0>();
+    if (l == 0) PROF(4);
     __syncthreads();  // L_l landed for everyone; all reads of T and of the other X buffer are finished
+    PROF(5);
     if (l + 1 < nL) prefetch_L<NT>(s, (l & 1) ? s.X1 : s.X0, x.Lp + (long long)(l + 1) * C::MAT, l + 2);
 #pragma unroll
     for (int t = 0; t < C::TW; t++) { W[t][0][0] = W[t][0][1] = W[t][1][0] = W[t][1][1] = 0.0; }
@@ -333,7 +373,9 @@ __device__ __forceinline__ void dmma_rhs(const SolveParams& p, const DmmaExtra& 
       *reinterpret_cast<double2*>(s.T + C::PLANE + r * C::LD + c0) = make_double2(r_l * W[t][1][0], r_l * W[t][1][1]);
     }
     __syncthreads();  // T = r_l L_l Y complete
+    PROF(6);
     warp_gemm<NT, true>(K, s.T, Lb, s.tr, s.tc0, s.g, s.tg, mb);
+    PROF(7);
   }
 }
 
@@ -366,6 +408,20 @@ solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
     }
     s.masks = mk;
     s.flist = fl;
+    __syncthreads();
+    double* gres = smem + C::SMEM_BASE / sizeof(double);
+    const int nfg = (int)fl[0] | ((int)fl[1] << 8);
+    s.gres = nullptr;
+    if ((1 + p.n_g) * nfg <= C::GRES_FRAGS) {
+      for (int m = 0; m <= p.n_g; m++) {
+        const double* src = (m == 0) ? x.G0p : x.Gkp + (long long)(m - 1) * C::MAT;
+        for (int c = threadIdx.x; c < nfg * 32; c += C::NTHREADS) {
+          const int off = frag_chunk_off<NT>(fl[8 + (c >> 5)], c & 31);
+          *reinterpret_cast<double2*>(gres + ((long long)m * nfg * 32 + c) * 2) = *reinterpret_cast<const double2*>(src + off);
+        }
+      }
+      s.gres = gres;
+    }
   }
   s.tid = threadIdx.x; s.w = s.tid >> 5; s.lane = s.tid & 31; s.g = s.lane >> 2; s.tg = s.lane & 3;
   s.tr = s.w / C::WPR; s.tc0 = (s.w % C::WPR) * C::TW;
@@ -455,9 +511,25 @@ solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       }
   };
 
+  // CTA-wide sum with ONE barrier: warp partials into one of two alternating slots, every thread adds
+  // the NW partials itself in the same order (so the result - and the step decision - is CTA-uniform)
+  int red_parity = 0;
+  auto block_sum_1b = [&](double v) {
+    v = warp_sum(v);
+    double* slot = s.red + 16 * red_parity;
+    red_parity ^= 1;
+    if (s.lane == 0) slot[s.w] = v;
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int i = 0; i < C::NW; i++) tot += slot[i];
+    return tot;
+  };
+
   StepCtl ctl;
   ctl_init(ctl, p);
   double K[C::TW][2][2];
+  PROF_DECL
 
   for (int o = 0; o < p.n_out; o++) {
     if (o > 0) {
@@ -481,14 +553,19 @@ solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
           }
           s.cval[st * 64 + m] = v;
         }
+        PROF(15);
         for (int st = ctl.have_k1 ? 1 : 0; st < S; st++) {
           double v[C::TW][2][2];
+          PROF(10);
           combine(v, htry, st, RK_A[pair][st], kp);    // st == S-1: v = y_new
+          PROF(0);
           __syncthreads();                             // every warp is out of the previous RHS
+          PROF(8);
           put_Y(v);
           if (st == S - 1) store_stream(syn, v);
-          dmma_rhs<NT>(p, x, s, s.cval + st * 64, K);
+          dmma_rhs<NT>(p, x, s, s.cval + st * 64, K PROF_PASS);
           store_stream(kp[st], K);
+          PROF(9);
           ctl.nrhs++;
         }
         ctl.have_k1 = true;
@@ -498,19 +575,26 @@ solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
           double2 e[C::TW][2];
 #pragma unroll
           for (int tt = 0; tt < C::TW; tt++) { e[tt][0] = make_double2(0.0, 0.0); e[tt][1] = make_double2(0.0, 0.0); }
-          for (int j = 0; j < S; j++) {
-            const double ej = RK_E[pair][j];
-            const double2* kj = kp[j];
-            double2 kv[C::TW][2];
+          for (int j0 = 0; j0 < S; j0 += 3) {
+            double2 kv[3][C::TW][2];
+            double ej[3];
 #pragma unroll
-            for (int tt = 0; tt < C::TW; tt++) { kv[tt][0] = SLOT(kj, tt, 0); kv[tt][1] = SLOT(kj, tt, 1); }
+            for (int u = 0; u < 3; u++) {
+              const bool on = j0 + u < S;
+              ej[u] = on ? RK_E[pair][j0 + u] : 0.0;
+              const double2* kj = kp[on ? j0 + u : j0];
 #pragma unroll
-            for (int tt = 0; tt < C::TW; tt++)
+              for (int tt = 0; tt < C::TW; tt++) { kv[u][tt][0] = SLOT(kj, tt, 0); kv[u][tt][1] = SLOT(kj, tt, 1); }
+            }
 #pragma unroll
-              for (int pl = 0; pl < 2; pl++) {
-                e[tt][pl].x = fma(ej, kv[tt][pl].x, e[tt][pl].x);
-                e[tt][pl].y = fma(ej, kv[tt][pl].y, e[tt][pl].y);
-              }
+            for (int u = 0; u < 3; u++)
+#pragma unroll
+              for (int tt = 0; tt < C::TW; tt++)
+#pragma unroll
+                for (int pl = 0; pl < 2; pl++) {
+                  e[tt][pl].x = fma(ej[u], kv[u][tt][pl].x, e[tt][pl].x);
+                  e[tt][pl].y = fma(ej[u], kv[u][tt][pl].y, e[tt][pl].y);
+                }
           }
 #pragma unroll
           for (int tt = 0; tt < C::TW; tt++) {
@@ -522,12 +606,15 @@ solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
             es += e0 / (sc0 * sc0) + e1 / (sc1 * sc1);
           }
         }
-        es = block_sum(es, s.red);
+        PROF(11);
+        es = block_sum_1b(es);
+        PROF(12);
         double err = sqrt(es / (double)(N * N));
         if (ctl_update(ctl, p, err, htry, landing, capped, t_target, nst)) {
           double2* tmp = sy; sy = syn; syn = tmp;
           tmp = kp[0]; kp[0] = kp[S - 1]; kp[S - 1] = tmp;
         }
+        PROF(13);
       }
       if (ctl.status != SEQ_STATUS_OK) break;
     }
@@ -537,24 +624,44 @@ solve_dmma_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       double2 a = SLOT(sy, tt, 0), bb = SLOT(sy, tt, 1);
       yv[tt][0][0] = a.x; yv[tt][0][1] = a.y; yv[tt][1][0] = bb.x; yv[tt][1][1] = bb.y;
     }
-    for (int e = 0; e < p.n_e; e++) {
-      // Tr(E rho) = sum_ij E_ji^T ... with Ef holding E[c][r] for the owned (r,c)
-      cplx acc = cmake(0, 0);
+    // Tr(E rho) for up to EC operators per round: thread partials -> the (idle) T buffer, one barrier,
+    // then warp v adds column v and writes the result.  Ef holds E[c][r] for the owned (r,c).
+    {
+      constexpr int EC = (C::MAT / (2 * C::NTHREADS) < 8) ? C::MAT / (2 * C::NTHREADS) : 8;
+      for (int e0 = 0; e0 < p.n_e; e0 += EC) {
+        const int ne = (p.n_e - e0 < EC) ? p.n_e - e0 : EC;
+        if (e0 > 0) __syncthreads();
+        for (int ei_ = 0; ei_ < ne; ei_++) {
+          const int e = e0 + ei_;
+          cplx acc = cmake(0, 0);
 #pragma unroll
-      for (int tt = 0; tt < C::TW; tt++) {
-        double2 er = x.Ef[((long long)e * C::SLOTS + tt * 2 + 0) * C::NTHREADS + tid];
-        double2 ei = x.Ef[((long long)e * C::SLOTS + tt * 2 + 1) * C::NTHREADS + tid];
-        // (er + i ei) * (yr + i yi)
-        acc.x += er.x * yv[tt][0][0] - ei.x * yv[tt][1][0] + er.y * yv[tt][0][1] - ei.y * yv[tt][1][1];
-        acc.y += er.x * yv[tt][1][0] + ei.x * yv[tt][0][0] + er.y * yv[tt][1][1] + ei.y * yv[tt][0][1];
+          for (int tt = 0; tt < C::TW; tt++) {
+            double2 er = x.Ef[((long long)e * C::SLOTS + tt * 2 + 0) * C::NTHREADS + tid];
+            double2 ei = x.Ef[((long long)e * C::SLOTS + tt * 2 + 1) * C::NTHREADS + tid];
+            // (er + i ei) * (yr + i yi)
+            acc.x += er.x * yv[tt][0][0] - ei.x * yv[tt][1][0] + er.y * yv[tt][0][1] - ei.y * yv[tt][1][1];
+            acc.y += er.x * yv[tt][1][0] + ei.x * yv[tt][0][0] + er.y * yv[tt][1][1] + ei.y * yv[tt][0][1];
+          }
+          s.T[(2 * ei_ + 0) * C::NTHREADS + tid] = acc.x;
+          s.T[(2 * ei_ + 1) * C::NTHREADS + tid] = acc.y;
+        }
+        __syncthreads();
+        for (int v = s.w; v < 2 * ne; v += C::NW) {
+          double part = 0.0;
+#pragma unroll
+          for (int j = 0; j < C::NW; j++) part += s.T[v * C::NTHREADS + j * 32 + s.lane];
+          part = warp_sum(part);
+          if (s.lane == 0) {
+            const int e = e0 + (v >> 1);
+            long long off = ((long long)b * p.n_e + e) * p.n_out + o;
+            if (p.flags & SEQ_FLAG_EXPECT_COMPLEX) ((double*)p.expect)[2 * off + (v & 1)] = part;
+            else if (!(v & 1)) ((double*)p.expect)[off] = part;
+          }
+        }
       }
-      acc = block_sum_c(acc, s.red);
-      if (tid == 0) {
-        long long off = ((long long)b * p.n_e + e) * p.n_out + o;
-        if (p.flags & SEQ_FLAG_EXPECT_COMPLEX) ((cplx*)p.expect)[off] = acc;
-        else ((double*)p.expect)[off] = acc.x;
-      }
+      if (p.n_e > 0) __syncthreads();   // T is scratch again
     }
+    PROF(14);
     if (p.flags & SEQ_FLAG_STORE_STATES) {
       cplx* dst = p.states + ((long long)b * p.n_out + o) * N * N;
 #pragma unroll

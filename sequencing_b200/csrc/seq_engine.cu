@@ -846,6 +846,18 @@ int seq_engine_solve_sharded(seq_engine* e, const seq_solve_desc* d, const seq_c
   return rc;
 }
 
+#ifdef SEQ_PROFILE_REGIONS
+// profiling builds only (tools/region_prof.py): cycles per region of solve_dmma_kernel's step loop
+int seq_engine_debug_regions(unsigned long long* out16, int reset) {
+  if (out16 && cudaMemcpyFromSymbol(out16, seq::seq_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return SEQ_ERR_CUDA;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(seq::seq_prof, z, sizeof(z)) != cudaSuccess) return SEQ_ERR_CUDA;
+  }
+  return SEQ_OK;
+}
+#endif
+
 int seq_engine_apply_unitary(seq_engine* e, const void* U, void* states, int32_t N, int32_t B, int is_ket) {
   if (!e) return SEQ_ERR_INVALID;
   if (!U || !states || N < 1 || B < 0) return fail(e, SEQ_ERR_INVALID, "bad apply_unitary arguments");
