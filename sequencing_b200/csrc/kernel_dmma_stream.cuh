@@ -33,7 +33,7 @@ template <int BT> struct StreamCfg {
   static constexpr int MAXL = 24;                  // collapse operators the task list has room for
   static constexpr int MAXTASK = 8 + 16 * MAXL;
   // + masks [(1 + MAXL)][4 images][8] (unsigned) + compact task list (unsigned short) + its length
-  static constexpr size_t SMEM = (size_t)(4 * BLK + 34 + 64) * sizeof(double) + (size_t)(1 + MAXL) * 32 * sizeof(unsigned)
+  static constexpr size_t SMEM = (size_t)(4 * BLK + 34 + 7 * 64) * sizeof(double) + (size_t)(1 + MAXL) * 32 * sizeof(unsigned)
                                  + (size_t)MAXTASK * sizeof(unsigned short) + 16;
 };
 // task-list entry: id | flags
@@ -102,7 +102,7 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
   const double2* tabr = p.tab_rate + (long long)b * p.tab_bstride_r;
   const double* cscale = p.coeff_scale ? p.coeff_scale + (long long)b * p.n_ch : nullptr;
 
-  unsigned* masks = reinterpret_cast<unsigned*>(cval + 64);
+  unsigned* masks = reinterpret_cast<unsigned*>(cval + 7 * 64);
   unsigned short* tlist = reinterpret_cast<unsigned short*>(masks + (1 + S::MAXL) * 32);
   int* ntl_p = reinterpret_cast<int*>(tlist + S::MAXTASK);
   for (int i = tid; i < (1 + nL) * 32; i += S::NTHREADS) masks[i] = x.masks[i];
@@ -211,18 +211,7 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
   };
 
   // kout (thread-private stream) <- RHS(t, Yb)
-  auto rhs = [&](double t, double2* kout) {
-    if (tid < p.n_g) {
-      int m = tid;
-      double v;
-      if (m < p.n_ch) {
-        v = spline_eval(tabc + (long long)m * p.n_t, p.n_t, p.t0, p.dt, t);
-        if (cscale) v *= cscale[m];
-      } else {
-        v = spline_eval(tabr + (long long)(m - p.n_ch) * p.n_t, p.n_t, p.t0, p.dt, t);
-      }
-      cval[m] = v;
-    }
+  auto rhs = [&](const double* __restrict__ cv, double2* kout) {
     __syncthreads();   // cval visible; Yb complete; every warp is out of the previous RHS
     {
       // G(t) = G0 + sum_m c_m Gk[m] over the block images, 8 independent 16-byte loads in flight
@@ -238,7 +227,7 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
         }
         for (int m = 0; m < p.n_g; m++) {
           const double2* gm = reinterpret_cast<const double2*>(x.Gkp + (long long)m * S::FULL);
-          const double cv = cval[m];
+          const double cvm = cv[m];
           double2 a[UN];
 #pragma unroll
           for (int i = 0; i < UN; i++) {
@@ -246,7 +235,7 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
             a[i] = (c < NCHUNK) ? gm[c] : make_double2(0.0, 0.0);
           }
 #pragma unroll
-          for (int i = 0; i < UN; i++) { acc[i].x = fma(cv, a[i].x, acc[i].x); acc[i].y = fma(cv, a[i].y, acc[i].y); }
+          for (int i = 0; i < UN; i++) { acc[i].x = fma(cvm, a[i].x, acc[i].x); acc[i].y = fma(cvm, a[i].y, acc[i].y); }
         }
 #pragma unroll
         for (int i = 0; i < UN; i++) {
@@ -345,7 +334,7 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
             QSLOT(kout, cq, t, 1) = aim;
           }
         } else if (ckind == 1) {
-          const double r_l = (cl_ < p.n_c) ? 1.0 : cval[p.n_ch + (cl_ - p.n_c)];
+          const double r_l = (cl_ < p.n_c) ? 1.0 : cv[p.n_ch + (cl_ - p.n_c)];
 #pragma unroll
           for (int t = 0; t < C::TW; t++) {
             double* dst = Tb + cq * S::BLK + blk_off(t);
@@ -381,6 +370,19 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
     }
   };
 
+  int red_parity = 0;
+  auto block_sum_1b = [&](double v) {
+    v = warp_sum(v);
+    double* slot = red + 16 * red_parity;
+    red_parity ^= 1;
+    if (lane == 0) slot[w] = v;
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int i = 0; i < C::NW; i++) tot += slot[i];
+    return tot;
+  };
+
   StepCtl ctl;
   ctl_init(ctl, p);
 
@@ -392,10 +394,23 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
       bool landing, capped;
       while (ctl.status == SEQ_STATUS_OK && ctl_next(ctl, p, t_target, htry, landing, capped)) {
         const int pair = ctl.pair, S_ = RK_STAGES[pair];
+        // spline values of every time-dependent term at every stage time of this step
+        for (int i = tid; i < S_ * p.n_g; i += S::NTHREADS) {
+          const int st = i / p.n_g, m = i - st * p.n_g;
+          const double ts = ctl.t + RK_C[pair][st] * htry;
+          double v;
+          if (m < p.n_ch) {
+            v = spline_eval(tabc + (long long)m * p.n_t, p.n_t, p.t0, p.dt, ts);
+            if (cscale) v *= cscale[m];
+          } else {
+            v = spline_eval(tabr + (long long)(m - p.n_ch) * p.n_t, p.n_t, p.t0, p.dt, ts);
+          }
+          cval[st * 64 + m] = v;
+        }
         for (int st = ctl.have_k1 ? 1 : 0; st < S_; st++) {
           __syncthreads();
           stage_state(htry, st, RK_A[pair][st], kp, st == S_ - 1 ? syn : nullptr);
-          rhs(ctl.t + RK_C[pair][st] * htry, kp[st]);
+          rhs(cval + st * 64, kp[st]);
           ctl.nrhs++;
         }
         ctl.have_k1 = true;
@@ -428,7 +443,7 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
             es += e0 / (sc0 * sc0) + e1 / (sc1 * sc1);
           }
         }
-        es = block_sum(es, red);
+        es = block_sum_1b(es);
         double err = sqrt(es / (double)(N * N));
         if (ctl_update(ctl, p, err, htry, landing, capped, t_target, nst)) {
           double2* tmp = sy; sy = syn; syn = tmp;
@@ -448,7 +463,8 @@ solve_dmma_stream_kernel(const __grid_constant__ SolveParams p, const __grid_con
           acc.x += er.x * yr.x - ei.x * yi.x + er.y * yr.y - ei.y * yi.y;
           acc.y += er.x * yi.x + ei.x * yr.x + er.y * yi.y + ei.y * yr.y;
         }
-      acc = block_sum_c(acc, red);
+      acc.x = block_sum_1b(acc.x);
+      acc.y = block_sum_1b(acc.y);
       if (tid == 0) {
         long long off = ((long long)b * p.n_e + e) * p.n_out + o;
         if (p.flags & SEQ_FLAG_EXPECT_COMPLEX) ((cplx*)p.expect)[off] = acc;
