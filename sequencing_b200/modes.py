@@ -35,6 +35,9 @@ def sort_modes(modes):
     return sorted(modes, key=lambda m: (m.name, m.levels), reverse=True)
 
 
+_EMBED_CACHE = {}
+
+
 @attr.s
 class Mode(Parameterized):
     """One oscillator, embeddable in the product space ``self.space``."""
@@ -80,6 +83,20 @@ class Mode(Parameterized):
         factors[self.index] = operator
         return self.tensor(*factors)
 
+    def _embedded(self, name, build):
+        """Kronecker-embedded elementary operator, memoised on (operator, levels, position, space
+        dimensions).  The reference rebuilds these on every property access (modes.py:292-305); in a
+        sweep that is the dominant host cost, and the result only depends on the dimensions."""
+        key = (name, self.levels, self.index, tuple(m.levels for m in self.space))
+        hit = _EMBED_CACHE.get(key)
+        if hit is None:
+            hit = self.tensor_with_I(build(self.levels))
+            hit._a.flags.writeable = False
+            if len(_EMBED_CACHE) > 512:
+                _EMBED_CACHE.clear()
+            _EMBED_CACHE[key] = hit
+        return hit
+
     def tensor_with_zero(self, state):
         """``state`` on this mode, vacuum on every other mode of ``self.space``."""
         factors = [qt.basis(m.levels, 0) for m in self.space]
@@ -100,11 +117,11 @@ class Mode(Parameterized):
     # -- operators -----------------------------------------------------------------------
     @property
     def I(self):  # noqa: E741, E743
-        return self.tensor_with_I(qt.qeye(self.levels))
+        return self._embedded("I", qt.qeye)
 
     @property
     def a(self):
-        return self.tensor_with_I(qt.destroy(self.levels))
+        return self._embedded("a", qt.destroy)
 
     @property
     def ad(self):
