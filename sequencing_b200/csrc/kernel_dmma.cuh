@@ -182,7 +182,35 @@ __device__ __forceinline__ void warp_gemm(double (&acc)[DmmaCfg<NT>::TW][2][2], 
     for (int i = 0; i < 3; i++) { P[t][i][0] = 0.0; P[t][i][1] = 0.0; }
   // Loops over the SET BITS of the masks (dynamic trip counts: real warp-uniform branches - a static
   // unrolled loop gets if-converted into predicated-off DMMAs that still occupy the tensor pipe).
-  if (!BCONJT) {
+  constexpr unsigned FULL = (1u << (C::NP / 4)) - 1u;
+  unsigned all = FULL;
+#pragma unroll
+  for (int t = 0; t < C::TW; t++) all &= mask[t];
+  if (all == FULL) {
+    // dense operator rows: the statically unrolled loop (the compiler software-pipelines the fragment loads)
+#pragma unroll
+    for (int k0 = 0; k0 < C::NP; k0 += 4) {
+      const double ar = Are[k0], ai = Aim[k0];
+      const double as = ar + ai;
+#pragma unroll
+      for (int t = 0; t < C::TW; t++) {
+        const int n0 = 8 * (tc0 + t);
+        double br, bi, bs;
+        if (!BCONJT) {
+          const double* bp = Bm + (k0 + tg) * C::LD + n0 + g;
+          br = bp[0]; bi = bp[C::PLANE];
+          bs = br + bi;
+        } else {
+          const double* lp = Bm + (n0 + g) * C::LD + k0 + tg;   // B(k,n) = conj(L[n][k])
+          br = lp[0]; bi = lp[C::PLANE];
+          bs = br - bi;
+        }
+        dmma884(P[t][0][0], P[t][0][1], ar, br);
+        dmma884(P[t][1][0], P[t][1][1], ai, bi);
+        dmma884(P[t][2][0], P[t][2][1], as, bs);
+      }
+    }
+  } else if (!BCONJT) {
     // the operator is the A operand: one mask (row tile tr) for the whole strip
     unsigned m = mask[0];
     while (m) {
