@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SEQ_ENGINE_ABI_VERSION 2
+#define SEQ_ENGINE_ABI_VERSION 3
 
 /* return codes */
 #define SEQ_OK 0
@@ -61,7 +61,7 @@ extern "C" {
                                           controller may drop to a 4-stage RK4(3) pair while steps
                                           are capped by max_step and the error estimate is tiny)   */
 
-/* kernel selection (0 = let the engine choose by N) */
+/* kernel selection (0 = let the engine choose by N and by the sparsity of the operators) */
 #define SEQ_METHOD_AUTO 0
 #define SEQ_METHOD_GENERIC 1   /* FP64-FMA, one CTA per trajectory, any N                    */
 #define SEQ_METHOD_DMMA 2      /* FP64 tensor-core (DMMA.8x8x4) tiles, rho resident in smem  */
@@ -69,6 +69,11 @@ extern "C" {
 #define SEQ_METHOD_DMMA_STREAM 4 /* DMMA with operands streamed through smem (N too big to stay resident) */
 #define SEQ_METHOD_LARGE 5     /* one big system (N > 96): every SM works on ONE right-hand side through a
                                   stream-K DMMA ZGEMM; optionally rho row-sharded over the GPUs of the box */
+
+#define SEQ_METHOD_SPARSE 6    /* row-sparse operators (the reference's Kronecker-embedded ladder / number operators,
+                                  modes.py:125-207): ELL operator rows, FP64 FMA, one CTA per trajectory with the
+                                  upper triangle of rho in registers.  AUTO picks it when every operator row holds
+                                  only a few non-zeros; dense operators go to the tensor-core kernels */
 
 typedef struct seq_engine seq_engine;
 
@@ -164,6 +169,10 @@ int seq_engine_solve_sharded(seq_engine* eng, const seq_solve_desc* desc, const 
 
 /* Method the engine would pick for this descriptor (SEQ_METHOD_*), without running it. */
 int seq_engine_select_method(const seq_engine* eng, const seq_solve_desc* desc);
+
+/* Method the last seq_engine_solve on this handle actually ran (SEQ_METHOD_*): AUTO looks at the
+ * operators' sparsity on the device, which seq_engine_select_method (shape only) cannot. */
+int seq_engine_last_method(const seq_engine* eng);
 
 /* Number of kernel launches issued by the last seq_engine_solve on this handle, and the
  * duration in milliseconds of its integration kernel measured with CUDA events on the

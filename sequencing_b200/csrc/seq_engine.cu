@@ -18,6 +18,7 @@
 #include "kernel_dmma_stream.cuh"
 #include "kernel_small.cuh"
 #include "kernel_large.cuh"
+#include "kernel_sparse.cuh"
 
 using namespace seq;
 
@@ -33,12 +34,13 @@ struct seq_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
-  DevBuf ws, gbuf, tab, cprime, pack, stage_in, stage_out, large, sched;
+  DevBuf ws, gbuf, tab, cprime, pack, stage_in, stage_out, large, sched, spinfo;
   const seq_comm* comm = nullptr;   // set for the duration of seq_engine_solve_sharded
   double* host_err = nullptr;       // pinned: error norm read back once per step by the large-N stepper
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   int launches = 0;
+  int last_method = 0;
   int sm_count = 0;
   int max_smem_optin = 0;
 };
@@ -298,7 +300,7 @@ extern "C" {
 int seq_engine_abi_version(void) { return SEQ_ENGINE_ABI_VERSION; }
 
 const char* seq_engine_build_info(void) {
-  return "seq_engine abi=2 arch=sm_100a kernels=generic(fma),dmma(8x8x4 resident),dmma_stream(8x8x4 blocked),small(thread-per-trajectory real superoperator),large(stream-K DMMA ZGEMM, row-sharded) built " __DATE__;
+  return "seq_engine abi=3 arch=sm_100a kernels=sparse(ELL operators, fma, rho upper triangle in registers),generic(fma),dmma(8x8x4 resident),dmma_stream(8x8x4 blocked),small(thread-per-trajectory real superoperator),large(stream-K DMMA ZGEMM, row-sharded) built " __DATE__;
 }
 
 int seq_engine_create(int device, void* stream, seq_engine** out) {
@@ -322,7 +324,7 @@ int seq_engine_destroy(seq_engine* e) {
   if (!e) return SEQ_OK;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  DevBuf* bufs[] = {&e->ws, &e->gbuf, &e->tab, &e->cprime, &e->pack, &e->stage_in, &e->stage_out, &e->large, &e->sched};
+  DevBuf* bufs[] = {&e->ws, &e->gbuf, &e->tab, &e->cprime, &e->pack, &e->stage_in, &e->stage_out, &e->large, &e->sched, &e->spinfo};
   for (DevBuf* b : bufs) if (b->ptr) cudaFree(b->ptr);
   if (e->host_err) cudaFreeHost(e->host_err);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -353,6 +355,8 @@ int64_t seq_engine_workspace_bytes(const seq_engine* e, const seq_solve_desc* d)
 }
 
 int seq_engine_last_launch_count(const seq_engine* e) { return e ? e->launches : 0; }
+
+int seq_engine_last_method(const seq_engine* e) { return e ? e->last_method : 0; }
 
 float seq_engine_last_kernel_ms(seq_engine* e) {
   if (!e || !e->timed) return -1.0f;
@@ -611,12 +615,87 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
   return SEQ_OK;
 }
 
+// Row statistics of the operators (device) -> ELL widths; decides whether SEQ_METHOD_SPARSE applies.
+// One small D2H copy + stream synchronisation.
+struct SparseInfo {
+  bool usable = false;       // widths within the kernel's limits and a launch plan exists
+  bool worthwhile = false;   // fewer multiply-adds than the dense tensor-core formulation by a wide margin
+  SparsePlan plan;
+  int* rowcnt = nullptr;     // device: [n_ops][N]
+};
+
+static int sparse_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, const cplx* Gk, const cplx* Lall, SparseInfo* info) {
+  const int N = d->N, n_g = d->n_ch + d->n_ctd, n_l = d->n_c + d->n_ctd, n_e = d->n_e;
+  const int n_ops = 1 + n_l + n_e;
+  size_t ints = (size_t)n_ops * N + 2 * (size_t)n_ops + (size_t)(n_e > 0 ? n_e : 1) * N + 16;
+  int rc = reserve(e, e->spinfo, ints * sizeof(int));
+  if (rc) return rc;
+  int* rowcnt = (int*)e->spinfo.ptr;
+  int* maxw = rowcnt + (size_t)n_ops * N;
+  int* total = maxw + n_ops;
+  CUDA_TRY(e, cudaMemsetAsync(maxw, 0, 2 * (size_t)n_ops * sizeof(int), e->stream));
+  dim3 grid(N, n_ops);
+  sparse_count_kernel<<<grid, 32, 0, e->stream>>>(G0, Gk, n_g, Lall, n_l, (const cplx*)d->E, N, rowcnt, maxw, total);
+  e->launches++;
+  std::vector<int> h(2 * (size_t)n_ops);
+  CUDA_TRY(e, cudaMemcpyAsync(h.data(), maxw, h.size() * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  int wL = 1;
+  for (int l = 0; l < n_l; l++) wL = h[1 + l] > wL ? h[1 + l] : wL;
+  long long nnzE = 0;
+  for (int q = 0; q < n_e; q++) nnzE += h[n_ops + 1 + n_l + q];
+  info->rowcnt = rowcnt;
+  const int wG = h[0] < 1 ? 1 : h[0];
+  info->worthwhile = sparse_worthwhile(N, n_l, wG, h.data() + 1);
+  info->usable = wG <= SPARSE_MAX_WG && wL <= SPARSE_MAX_WL && nnzE < (1LL << 30) &&
+                 sparse_plan(N, n_g, n_l, wG, wL, (int)nnzE, e->max_smem_optin, &info->plan);
+  return SEQ_OK;
+}
+
+static int launch_sparse(seq_engine* e, const seq_solve_desc* d, SolveParams& p, const cplx* G0, const cplx* Gk, const SparseInfo& info) {
+  const int N = d->N, n_g = p.n_g, n_l = p.n_c + p.n_ctd, n_e = p.n_e;
+  const SparsePlan& pl = info.plan;
+  SparsePack pk = sparse_pack_layout(N, n_g, n_l, n_e, pl);
+  int rc = reserve(e, e->pack, pk.bytes);
+  if (rc) return rc;
+  rc = reserve(e, e->ws, sparse_ws_elems(pl) * (size_t)d->B * sizeof(cplx) + 256);
+  if (rc) return rc;
+  char* base = (char*)e->pack.ptr;
+  SparseOps sp;
+  sp.wG = pl.wG; sp.wL = pl.wL; sp.n_el = N * (N + 1) / 2; sp.ld = pl.ld; sp.ybufs = pl.ybufs;
+  sp.gcol = (int*)(base + pk.o_gcol); sp.g0 = (cplx*)(base + pk.o_g0); sp.gk = (cplx*)(base + pk.o_gk);
+  sp.lcol = (int*)(base + pk.o_lcol); sp.lval = (cplx*)(base + pk.o_lval); sp.ij = (unsigned*)(base + pk.o_ij);
+  sp.e_off = (int*)(base + pk.o_eoff); sp.e_ij = (unsigned*)(base + pk.o_eij); sp.e_val = (cplx*)(base + pk.o_eval);
+  const int n_ops = 1 + n_l + n_e;
+  int* rowoff = info.rowcnt + (size_t)n_ops * N + 2 * (size_t)n_ops;
+  sparse_escan_kernel<<<1, 32, 0, e->stream>>>(info.rowcnt, n_l, n_e, N, rowoff, (int*)sp.e_off);
+  dim3 grid(N, n_ops);
+  sparse_fill_kernel<<<grid, 32, 0, e->stream>>>(G0, Gk, n_g, p.L, n_l, p.E, N, pl.wG, pl.wL, (int*)sp.gcol, (cplx*)sp.g0, (cplx*)sp.gk,
+                                                   (int*)sp.lcol, (cplx*)sp.lval, rowoff, (unsigned*)sp.e_ij, (cplx*)sp.e_val);
+  sparse_ij_kernel<<<(N * N + 255) / 256, 256, 0, e->stream>>>((unsigned*)sp.ij, N);
+  e->launches += 3;
+  p.ws = (cplx*)e->ws.ptr;
+  p.ws_stride = (long long)sparse_ws_elems(pl);
+  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  rc = launch_sparse_kernel(p, sp, pl, e->stream);
+  if (rc) return fail(e, rc, "sparse kernel launch configuration failed for N=%d", N);
+  e->launches++;
+  return SEQ_OK;
+}
+
 static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   const int N = d->N, B = d->B;
   const size_t N2 = (size_t)N * N;
   const int n_g = d->n_ch + d->n_ctd;
   const bool ket = d->flags & SEQ_FLAG_KET;
-  const int method = pick_method(e, d);
+  int method = pick_method(e, d);
+  const bool sharded = e->comm && e->comm->world > 1;
+  // the sparse kernel is tried for density matrices with a shared H0 whenever the choice is the engine's
+  const bool try_sparse = !ket && !d->H0_batch_stride && !sharded &&
+                          (method == SEQ_METHOD_SPARSE ||
+                           (d->method == SEQ_METHOD_AUTO && method != SEQ_METHOD_SMALL));
+  if (method == SEQ_METHOD_SPARSE && !try_sparse)
+    return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_SPARSE covers density matrices with a shared H0 on one GPU (N=%d ket=%d)", N, (int)ket);
   if (method == SEQ_METHOD_DMMA && (ket || !dmma_supported(N, e->max_smem_optin) || d->H0_batch_stride))
     return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_DMMA does not cover N=%d ket=%d h0_stride=%lld", N, (int)ket, (long long)d->H0_batch_stride);
   if (method == SEQ_METHOD_SMALL && (ket || d->H0_batch_stride || !small_supported(N, n_g, d->n_e)))
@@ -625,34 +704,19 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
     return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_DMMA_STREAM does not cover N=%d ket=%d h0_stride=%lld", N, (int)ket, (long long)d->H0_batch_stride);
   if (method == SEQ_METHOD_LARGE && (ket || d->H0_batch_stride))
     return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_LARGE covers density matrices with a shared H0 only (N=%d ket=%d)", N, (int)ket);
-  if (method < SEQ_METHOD_GENERIC || method > SEQ_METHOD_LARGE)
+  if (method < SEQ_METHOD_GENERIC || method > SEQ_METHOD_SPARSE)
     return fail(e, SEQ_ERR_UNSUPPORTED, "method %d is not implemented", method);
-  if (e->comm && e->comm->world > 1 && method != SEQ_METHOD_LARGE)
+  if (sharded && method != SEQ_METHOD_LARGE)
     return fail(e, SEQ_ERR_UNSUPPORTED, "row-sharded solves run SEQ_METHOD_LARGE only (got method %d for N=%d)", method, N);
 
   // ---- scratch
   const size_t nG0 = d->H0_batch_stride ? (size_t)B : 1;
   int rc = reserve(e, e->gbuf, (nG0 + n_g) * N2 * sizeof(cplx));
   if (rc) return rc;
-  const size_t ws_per = ws_elems_per_traj(d, method);
-  rc = reserve(e, e->ws, ws_per * (size_t)B * sizeof(cplx) + 256);
-  if (rc) return rc;
   const long long series_c = (long long)(d->coeff_batch_stride ? B : 1) * d->n_ch;
   const long long series_r = (long long)(d->rate_batch_stride ? B : 1) * d->n_ctd;
   rc = reserve(e, e->tab, (size_t)(series_c + series_r) * d->n_t * sizeof(double2) + 256);
   if (rc) return rc;
-  if (method == SEQ_METHOD_DMMA) {
-    rc = reserve(e, e->pack, dmma_pack_doubles(N, n_g, d->n_c + d->n_ctd, d->n_e) * sizeof(double));
-    if (rc) return rc;
-  }
-  if (method == SEQ_METHOD_DMMA_STREAM) {
-    rc = reserve(e, e->pack, stream_pack_doubles(N, n_g, d->n_c + d->n_ctd, d->n_e) * sizeof(double));
-    if (rc) return rc;
-  }
-  if (method == SEQ_METHOD_SMALL) {
-    rc = reserve(e, e->pack, small_pack_doubles(N, n_g, d->n_e) * sizeof(double));
-    if (rc) return rc;
-  }
   if (d->coeff_batch_stride && d->coeff_batch_stride != (int64_t)d->n_ch * d->n_t)
     return fail(e, SEQ_ERR_UNSUPPORTED, "coeff_batch_stride must be 0 or n_ch*n_t");
   if (d->rate_batch_stride && d->rate_batch_stride != (int64_t)d->n_ctd * d->n_t)
@@ -696,6 +760,34 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
     }
   }
 
+  // ---- operator sparsity decides between the sparse (FMA) and the dense (tensor-core) formulation
+  SparseInfo spi;
+  if (try_sparse) {
+    rc = sparse_analyze(e, d, G0, Gk, Lall, &spi);
+    if (rc) return rc;
+    if (method == SEQ_METHOD_SPARSE) {
+      if (!spi.usable) return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_SPARSE: operator rows too dense or N=%d too large for one CTA", N);
+    } else if (spi.usable && spi.worthwhile) {
+      method = SEQ_METHOD_SPARSE;
+    }
+  }
+  e->last_method = method;
+
+  const size_t ws_per = ws_elems_per_traj(d, method);
+  rc = reserve(e, e->ws, ws_per * (size_t)B * sizeof(cplx) + 256);
+  if (rc) return rc;
+  if (method == SEQ_METHOD_DMMA) {
+    rc = reserve(e, e->pack, dmma_pack_doubles(N, n_g, d->n_c + d->n_ctd, d->n_e) * sizeof(double));
+    if (rc) return rc;
+  }
+  if (method == SEQ_METHOD_DMMA_STREAM) {
+    rc = reserve(e, e->pack, stream_pack_doubles(N, n_g, d->n_c + d->n_ctd, d->n_e) * sizeof(double));
+    if (rc) return rc;
+  }
+  if (method == SEQ_METHOD_SMALL) {
+    rc = reserve(e, e->pack, small_pack_doubles(N, n_g, d->n_e) * sizeof(double));
+    if (rc) return rc;
+  }
   SolveParams p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.B = B; p.n_t = d->n_t; p.n_g = n_g; p.n_ch = d->n_ch; p.n_c = d->n_c; p.n_ctd = d->n_ctd;
@@ -714,8 +806,11 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   p.status = d->status; p.stats = d->stats;
   p.ws = (cplx*)e->ws.ptr; p.ws_stride = (long long)ws_per;
 
-  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
-  if (method == SEQ_METHOD_GENERIC) {
+  if (method != SEQ_METHOD_SPARSE) CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  if (method == SEQ_METHOD_SPARSE) {
+    rc = launch_sparse(e, d, p, G0, Gk, spi);
+    if (rc) return rc;
+  } else if (method == SEQ_METHOD_GENERIC) {
     size_t elems = ket ? (size_t)N : N2;
     int threads = (int)((elems + 31) / 32 * 32);
     if (threads < 32) threads = 32;

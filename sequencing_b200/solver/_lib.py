@@ -10,19 +10,20 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "_seq_engine.so")
 
 # mirrors of the #defines in include/seq_engine.h
-ABI_VERSION = 2
+ABI_VERSION = 3
 SEQ_OK = 0
 STATUS_OK, STATUS_MAX_STEPS, STATUS_NONFINITE, STATUS_STEP_UNDERFLOW = 0, 1, 2, 3
 FLAG_KET, FLAG_NORMALIZE, FLAG_STORE_STATES, FLAG_EXPECT_COMPLEX, FLAG_HOST_POINTERS = 0x1, 0x2, 0x4, 0x8, 0x10
 FLAG_NO_ORDER_SWITCH = 0x20
-METHOD_AUTO, METHOD_GENERIC, METHOD_DMMA, METHOD_SMALL, METHOD_DMMA_STREAM, METHOD_LARGE = 0, 1, 2, 3, 4, 5
-METHOD_NAMES = {0: "auto", 1: "generic", 2: "dmma", 3: "small", 4: "dmma_stream", 5: "large"}
+METHOD_AUTO, METHOD_GENERIC, METHOD_DMMA, METHOD_SMALL, METHOD_DMMA_STREAM, METHOD_LARGE, METHOD_SPARSE = 0, 1, 2, 3, 4, 5, 6
+METHOD_NAMES = {0: "auto", 1: "generic", 2: "dmma", 3: "small", 4: "dmma_stream", 5: "large", 6: "sparse"}
 
 EXPORTS = (
     "seq_engine_abi_version", "seq_engine_build_info", "seq_engine_create", "seq_engine_destroy",
     "seq_engine_last_error", "seq_engine_workspace_bytes", "seq_engine_solve",
     "seq_engine_select_method", "seq_engine_last_launch_count", "seq_engine_last_kernel_ms",
     "seq_engine_spline_prep", "seq_engine_apply_unitary", "seq_engine_expect", "seq_engine_solve_sharded",
+    "seq_engine_last_method",
 )
 
 
@@ -92,6 +93,7 @@ def load():
     lib.seq_engine_select_method.argtypes = [vp, C.POINTER(SolveDesc)]
     lib.seq_engine_solve_sharded.argtypes = [vp, C.POINTER(SolveDesc), C.POINTER(Comm)]
     lib.seq_engine_last_launch_count.argtypes = [vp]
+    lib.seq_engine_last_method.argtypes = [vp]
     lib.seq_engine_last_kernel_ms.argtypes = [vp]
     lib.seq_engine_last_kernel_ms.restype = C.c_float
     lib.seq_engine_spline_prep.argtypes = [vp, vp, vp, i64, i32, C.c_double]

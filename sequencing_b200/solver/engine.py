@@ -229,7 +229,7 @@ class Engine:
             self._check(self.lib.seq_engine_solve(self.handle, C.byref(desc)))
             self.last_launches = self.lib.seq_engine_last_launch_count(self.handle)
             self.total_launches += self.last_launches
-            self._last_method = self.lib.seq_engine_select_method(self.handle, C.byref(desc))
+            self._last_method = self.lib.seq_engine_last_method(self.handle)
         return {"out": outs, "in": tens}
 
     def solve_host_abi(self, bp: BatchProblem) -> BatchOutput:
@@ -243,7 +243,7 @@ class Engine:
         self._check(self.lib.seq_engine_solve(self.handle, C.byref(desc)))
         self.last_launches = self.lib.seq_engine_last_launch_count(self.handle)
         self.total_launches += self.last_launches
-        self._last_method = self.lib.seq_engine_select_method(self.handle, C.byref(desc))
+        self._last_method = self.lib.seq_engine_last_method(self.handle)
         return self._finish(bp, outs)
 
     def solve_rows_sharded(self, bp: BatchProblem, comm: "_lib.Comm", tens=None, to_host=True):
@@ -265,7 +265,7 @@ class Engine:
             self._check(self.lib.seq_engine_solve_sharded(self.handle, C.byref(desc), C.byref(comm) if comm is not None else None))
             self.last_launches = self.lib.seq_engine_last_launch_count(self.handle)
             self.total_launches += self.last_launches
-            self._last_method = _lib.METHOD_LARGE if (comm is not None and comm.world > 1) else self.lib.seq_engine_select_method(self.handle, C.byref(desc))
+            self._last_method = self.lib.seq_engine_last_method(self.handle)
             torch.cuda.synchronize(self.device)
         if not to_host:
             return {"out": outs, "in": tens}

@@ -119,3 +119,41 @@ def random_problem(N, B, n_t, n_ch=2, n_c=2, n_ctd=0, n_e=2, seed=0, ket=False, 
                 Lc=Lc, Ltd=Ltd, rate=rate, E=E, is_ket=ket, max_step=dt)
     args.update(kw)
     return BatchProblem(**args)
+
+
+def row_sparse_problem(N, B, n_t, w_h=3, w_l=1, seed=0, **kw):
+    """``random_problem`` with row-sparse operators: every Hamiltonian term keeps ``w_h`` random
+    (Hermitian-symmetrised) off-diagonals plus the diagonal, every collapse operator keeps ``w_l``
+    entries per row on shifted diagonals with wrap-around holes - the structure of the reference's
+    Kronecker-embedded ladder / number operators (modes.py:125-207), at random values."""
+    bp = random_problem(N=N, B=B, n_t=n_t, seed=seed, **kw)
+    rng = np.random.default_rng(1000 + seed)
+    i, j = np.indices((N, N))
+
+    def band_mask(offsets):
+        m = np.zeros((N, N), bool)
+        for o in offsets:
+            m |= (j - i) == o
+        return m
+
+    offs = [int(o) for o in rng.choice(np.arange(1, max(2, N)), size=min(max(w_h // 2, 0), N - 1), replace=False)]
+    hmask = band_mask([0] + offs + [-o for o in offs])
+    bp.H0 = bp.H0 * hmask * np.sqrt(N)
+    bp.Hk = bp.Hk * hmask * np.sqrt(N)
+    if bp.H0.ndim == 2 and w_h % 2 == 0:
+        bp.H0 = bp.H0 * (1 - np.eye(N)) + np.diag(np.zeros(N))     # even width: no diagonal
+
+    def lmask():
+        lo = [int(o) for o in rng.choice(np.arange(-(N - 1), N), size=w_l, replace=False)]
+        m = band_mask(lo)
+        m &= rng.random((N, N)) < 0.8      # some rows lose entries (ragged ELL rows)
+        return m
+
+    if bp.Lc is not None and bp.Lc.shape[0]:
+        bp.Lc = np.stack([L * lmask() * np.sqrt(N) for L in bp.Lc])
+    if bp.Ltd is not None and bp.Ltd.shape[0]:
+        bp.Ltd = np.stack([L * lmask() * np.sqrt(N) for L in bp.Ltd])
+    if bp.E is not None and bp.E.shape[0] > 1:
+        v = np.zeros(N); v[seed % N] = 1.0
+        bp.E[0] = np.outer(v, v)           # a projector (1 non-zero), as the sweeps use
+    return bp

@@ -239,7 +239,7 @@ def test_abi_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.seq_engine_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.seq_engine_abi_version() == _lib.ABI_VERSION == 3
     assert b"sm_100a" in lib.seq_engine_build_info()
 
 
