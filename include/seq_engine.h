@@ -74,6 +74,9 @@ extern "C" {
                                   modes.py:125-207): ELL operator rows, FP64 FMA, one CTA per trajectory with the
                                   upper triangle of rho in registers.  AUTO picks it when every operator row holds
                                   only a few non-zeros; dense operators go to the tensor-core kernels */
+#define SEQ_METHOD_DIAG 7      /* operators that are sums of a few shifted diagonals (every Kronecker-embedded ladder /
+                                  number operator of the reference is): as SEQ_METHOD_SPARSE but every term is "own
+                                  element + constant offset", no index tables.  AUTO prefers it over SPARSE */
 
 typedef struct seq_engine seq_engine;
 

@@ -89,6 +89,44 @@ __constant__ double RK_E[2][7] = {{DP_E1, 0.0, DP_E3, DP_E4, DP_E5, DP_E6, DP_E7
 __constant__ int RK_STAGES[2] = {7, 5};
 __constant__ double RK_EXPO[2] = {-0.2, -0.25};
 
+// The same tableaus as compile-time functions: kernels that unroll the stage loop statically get the
+// coefficients as immediates and drop the zero entries.
+__host__ __device__ constexpr double rk_a_c(int pair, int s, int j) {
+  if (pair == 0) {
+    switch (s * 8 + j) {
+      case 1 * 8 + 0: return DP_A21;
+      case 2 * 8 + 0: return DP_A31; case 2 * 8 + 1: return DP_A32;
+      case 3 * 8 + 0: return DP_A41; case 3 * 8 + 1: return DP_A42; case 3 * 8 + 2: return DP_A43;
+      case 4 * 8 + 0: return DP_A51; case 4 * 8 + 1: return DP_A52; case 4 * 8 + 2: return DP_A53; case 4 * 8 + 3: return DP_A54;
+      case 5 * 8 + 0: return DP_A61; case 5 * 8 + 1: return DP_A62; case 5 * 8 + 2: return DP_A63; case 5 * 8 + 3: return DP_A64;
+      case 5 * 8 + 4: return DP_A65;
+      case 6 * 8 + 0: return DP_B1; case 6 * 8 + 2: return DP_B3; case 6 * 8 + 3: return DP_B4; case 6 * 8 + 4: return DP_B5;
+      case 6 * 8 + 5: return DP_B6;
+      default: return 0.0;
+    }
+  }
+  switch (s * 8 + j) {
+    case 1 * 8 + 0: return 1.0 / 3.0;
+    case 2 * 8 + 0: return -1.0 / 3.0; case 2 * 8 + 1: return 1.0;
+    case 3 * 8 + 0: return 1.0; case 3 * 8 + 1: return -1.0; case 3 * 8 + 2: return 1.0;
+    case 4 * 8 + 0: return 1.0 / 8.0; case 4 * 8 + 1: return 3.0 / 8.0; case 4 * 8 + 2: return 3.0 / 8.0; case 4 * 8 + 3: return 1.0 / 8.0;
+    default: return 0.0;
+  }
+}
+__host__ __device__ constexpr double rk_e_c(int pair, int j) {
+  if (pair == 0) {
+    switch (j) {
+      case 0: return DP_E1; case 2: return DP_E3; case 3: return DP_E4; case 4: return DP_E5; case 5: return DP_E6; case 6: return DP_E7;
+      default: return 0.0;
+    }
+  }
+  switch (j) {
+    case 0: return 1.0 / 24.0; case 1: return -1.0 / 8.0; case 2: return 1.0 / 8.0; case 3: return 1.0 / 8.0; case 4: return -1.0 / 6.0;
+    default: return 0.0;
+  }
+}
+template <int V> struct IntTag { static constexpr int value = V; };
+
 // step-size controller (same constants as scipy's RK45 / Hairer's DOPRI5)
 #define SEQ_SAFETY 0.9
 #define SEQ_MIN_FACTOR 0.2

@@ -94,8 +94,8 @@ __global__ void sparse_fill_kernel(const cplx* __restrict__ G0, const cplx* __re
                                    const cplx* __restrict__ L, int n_l, const cplx* __restrict__ E, int N, int wG, int wL,
                                    int* __restrict__ gcol, cplx* __restrict__ g0, cplx* __restrict__ gk,
                                    int* __restrict__ lcol, cplx* __restrict__ lval, const int* __restrict__ rowoff,
-                                   unsigned* __restrict__ e_ij, cplx* __restrict__ e_val) {
-  const int i = blockIdx.x, op = blockIdx.y, lane = threadIdx.x;
+                                   unsigned* __restrict__ e_ij, cplx* __restrict__ e_val, int op0) {
+  const int i = blockIdx.x, op = blockIdx.y + op0, lane = threadIdx.x;
   const long long N2 = (long long)N * N;
   int base = 0;
   for (int j0 = 0; j0 < N; j0 += 32) {
@@ -487,6 +487,7 @@ solve_sparse_kernel(const __grid_constant__ SolveParams p, const __grid_constant
 // ---------------------------------------------------------------------------------------------------
 struct SparsePlan {
   int wG, wL, nnzE;      // from the device analysis
+  long long macs;        // complex multiply-adds per element (cost model)
   int ept, threads;      // launch shape
   bool kreg;
   int ld, ybufs;

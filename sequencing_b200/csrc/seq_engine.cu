@@ -19,6 +19,7 @@
 #include "kernel_small.cuh"
 #include "kernel_large.cuh"
 #include "kernel_sparse.cuh"
+#include "kernel_diag.cuh"
 
 using namespace seq;
 
@@ -34,7 +35,7 @@ struct seq_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
-  DevBuf ws, gbuf, tab, cprime, pack, stage_in, stage_out, large, sched, spinfo;
+  DevBuf ws, gbuf, tab, cprime, pack, stage_in, stage_out, large, sched, spinfo, dflags;
   const seq_comm* comm = nullptr;   // set for the duration of seq_engine_solve_sharded
   double* host_err = nullptr;       // pinned: error norm read back once per step by the large-N stepper
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -300,7 +301,7 @@ extern "C" {
 int seq_engine_abi_version(void) { return SEQ_ENGINE_ABI_VERSION; }
 
 const char* seq_engine_build_info(void) {
-  return "seq_engine abi=3 arch=sm_100a kernels=sparse(ELL operators, fma, rho upper triangle in registers),generic(fma),dmma(8x8x4 resident),dmma_stream(8x8x4 blocked),small(thread-per-trajectory real superoperator),large(stream-K DMMA ZGEMM, row-sharded) built " __DATE__;
+  return "seq_engine abi=3 arch=sm_100a kernels=diag(operators by diagonals, fma, rho upper triangle in registers),sparse(ELL operator rows, fma),generic(fma),dmma(8x8x4 resident),dmma_stream(8x8x4 blocked),small(thread-per-trajectory real superoperator),large(stream-K DMMA ZGEMM, row-sharded) built " __DATE__;
 }
 
 int seq_engine_create(int device, void* stream, seq_engine** out) {
@@ -324,7 +325,7 @@ int seq_engine_destroy(seq_engine* e) {
   if (!e) return SEQ_OK;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  DevBuf* bufs[] = {&e->ws, &e->gbuf, &e->tab, &e->cprime, &e->pack, &e->stage_in, &e->stage_out, &e->large, &e->sched, &e->spinfo};
+  DevBuf* bufs[] = {&e->ws, &e->gbuf, &e->tab, &e->cprime, &e->pack, &e->stage_in, &e->stage_out, &e->large, &e->sched, &e->spinfo, &e->dflags};
   for (DevBuf* b : bufs) if (b->ptr) cudaFree(b->ptr);
   if (e->host_err) cudaFreeHost(e->host_err);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -647,8 +648,12 @@ static int sparse_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0
   info->rowcnt = rowcnt;
   const int wG = h[0] < 1 ? 1 : h[0];
   info->worthwhile = sparse_worthwhile(N, n_l, wG, h.data() + 1);
+  info->plan.nnzE = (int)nnzE;
   info->usable = wG <= SPARSE_MAX_WG && wL <= SPARSE_MAX_WL && nnzE < (1LL << 30) &&
                  sparse_plan(N, n_g, n_l, wG, wL, (int)nnzE, e->max_smem_optin, &info->plan);
+  info->plan.nnzE = (int)nnzE;
+  info->plan.macs = 2LL * wG;
+  for (int l = 0; l < n_l; l++) info->plan.macs += (long long)h[1 + l] * h[1 + l];
   return SEQ_OK;
 }
 
@@ -671,7 +676,7 @@ static int launch_sparse(seq_engine* e, const seq_solve_desc* d, SolveParams& p,
   sparse_escan_kernel<<<1, 32, 0, e->stream>>>(info.rowcnt, n_l, n_e, N, rowoff, (int*)sp.e_off);
   dim3 grid(N, n_ops);
   sparse_fill_kernel<<<grid, 32, 0, e->stream>>>(G0, Gk, n_g, p.L, n_l, p.E, N, pl.wG, pl.wL, (int*)sp.gcol, (cplx*)sp.g0, (cplx*)sp.gk,
-                                                   (int*)sp.lcol, (cplx*)sp.lval, rowoff, (unsigned*)sp.e_ij, (cplx*)sp.e_val);
+                                                   (int*)sp.lcol, (cplx*)sp.lval, rowoff, (unsigned*)sp.e_ij, (cplx*)sp.e_val, 0);
   sparse_ij_kernel<<<(N * N + 255) / 256, 256, 0, e->stream>>>((unsigned*)sp.ij, N);
   e->launches += 3;
   p.ws = (cplx*)e->ws.ptr;
@@ -679,6 +684,71 @@ static int launch_sparse(seq_engine* e, const seq_solve_desc* d, SolveParams& p,
   CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
   rc = launch_sparse_kernel(p, sp, pl, e->stream);
   if (rc) return fail(e, rc, "sparse kernel launch configuration failed for N=%d", N);
+  e->launches++;
+  return SEQ_OK;
+}
+
+// Diagonal structure of the operators (device flags -> host plan).  One D2H copy + synchronisation.
+static int diag_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, const cplx* Gk, const cplx* Lall, int nnzE, DiagPlan* pl, bool* usable) {
+  const int N = d->N, n_g = d->n_ch + d->n_ctd, n_l = d->n_c + d->n_ctd;
+  const size_t W = 2 * (size_t)N - 1, nflag = (size_t)(1 + n_l) * W;
+  *usable = false;
+  int rc = reserve(e, e->dflags, nflag * sizeof(int) + 64);
+  if (rc) return rc;
+  int* flags = (int*)e->dflags.ptr;
+  CUDA_TRY(e, cudaMemsetAsync(flags, 0, nflag * sizeof(int), e->stream));
+  dim3 grid((unsigned)grid_for((long long)N * N, e->sm_count), 1 + n_l);
+  diag_flags_kernel<<<grid, 256, 0, e->stream>>>(G0, Gk, n_g, Lall, N, flags);
+  e->launches++;
+  std::vector<int> h(nflag);
+  CUDA_TRY(e, cudaMemcpyAsync(h.data(), flags, nflag * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  const char* env = getenv("SEQ_DIAG_EPT");
+  *usable = diag_plan(N, n_g, d->n_c, d->n_ctd, d->n_ch, d->n_t, nnzE, h.data(), e->max_smem_optin, env ? atoi(env) : 0, pl);
+  return SEQ_OK;
+}
+
+static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, const cplx* G0, const cplx* Gk, const SparseInfo& info, DiagPlan& pl) {
+  const int N = d->N, n_g = p.n_g, n_l = p.n_c + p.n_ctd, n_e = p.n_e;
+  // expectation operators as COO lists (layout shared with the ELL kernel), operator diagonals behind them
+  SparsePlan epl;
+  memset(&epl, 0, sizeof(epl));
+  epl.wG = 1; epl.wL = 1; epl.nnzE = info.plan.nnzE;
+  SparsePack pk = sparse_pack_layout(N, 0, 0, n_e, epl);
+  DiagPack dk = diag_pack_layout(N, n_g, pl);
+  int rc = reserve(e, e->pack, pk.bytes + dk.bytes);
+  if (rc) return rc;
+  rc = reserve(e, e->ws, diag_ws_elems(pl) * (size_t)d->B * sizeof(cplx) + 256);
+  if (rc) return rc;
+  char* base = (char*)e->pack.ptr;
+  char* dbase = base + pk.bytes / 16 * 16;
+  DiagOps& sp = pl.ops;
+  sp.ij = (unsigned*)(base + pk.o_ij); sp.e_off = (int*)(base + pk.o_eoff); sp.e_ij = (unsigned*)(base + pk.o_eij); sp.e_val = (cplx*)(base + pk.o_eval);
+  sp.g0 = (cplx*)(dbase + dk.o_g0); sp.gk = (cplx*)(dbase + dk.o_gk); sp.lam = (cplx*)(dbase + dk.o_lam);
+  int* any_imag = (int*)(dbase + dk.o_flag);
+  const int n_ops = 1 + n_l + n_e;
+  int* rowoff = info.rowcnt + (size_t)n_ops * N + 2 * (size_t)n_ops;
+  sparse_escan_kernel<<<1, 32, 0, e->stream>>>(info.rowcnt, n_l, n_e, N, rowoff, (int*)sp.e_off);
+  e->launches++;
+  if (n_e > 0) {
+    dim3 ge(N, n_e);
+    sparse_fill_kernel<<<ge, 32, 0, e->stream>>>(G0, Gk, n_g, p.L, n_l, p.E, N, 1, 1, nullptr, nullptr, nullptr, nullptr, nullptr, rowoff,
+                                               (unsigned*)sp.e_ij, (cplx*)sp.e_val, 1 + n_l);
+    e->launches++;
+  }
+  sparse_ij_kernel<<<(N * N + 255) / 256, 256, 0, e->stream>>>((unsigned*)sp.ij, N);
+  CUDA_TRY(e, cudaMemsetAsync(any_imag, 0, sizeof(int), e->stream));
+  dim3 gf((N + 127) / 128, pl.fill.nD + pl.fill.nT);
+  diag_fill_kernel<<<gf, 128, 0, e->stream>>>(pl.fill, G0, Gk, n_g, p.L, N, (cplx*)sp.g0, (cplx*)sp.gk, (cplx*)sp.lam, any_imag);
+  e->launches += 2;
+  int h_imag = 0;
+  CUDA_TRY(e, cudaMemcpyAsync(&h_imag, any_imag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  p.ws = (cplx*)e->ws.ptr;
+  p.ws_stride = (long long)diag_ws_elems(pl);
+  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  rc = launch_diag_kernel(p, sp, pl, h_imag == 0, e->stream);
+  if (rc) return fail(e, rc, "diagonal kernel launch configuration failed for N=%d", N);
   e->launches++;
   return SEQ_OK;
 }
@@ -692,10 +762,10 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   const bool sharded = e->comm && e->comm->world > 1;
   // the sparse kernel is tried for density matrices with a shared H0 whenever the choice is the engine's
   const bool try_sparse = !ket && !d->H0_batch_stride && !sharded &&
-                          (method == SEQ_METHOD_SPARSE ||
+                          (method == SEQ_METHOD_SPARSE || method == SEQ_METHOD_DIAG ||
                            (d->method == SEQ_METHOD_AUTO && method != SEQ_METHOD_SMALL));
-  if (method == SEQ_METHOD_SPARSE && !try_sparse)
-    return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_SPARSE covers density matrices with a shared H0 on one GPU (N=%d ket=%d)", N, (int)ket);
+  if ((method == SEQ_METHOD_SPARSE || method == SEQ_METHOD_DIAG) && !try_sparse)
+    return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_SPARSE / SEQ_METHOD_DIAG cover density matrices with a shared H0 on one GPU (N=%d ket=%d)", N, (int)ket);
   if (method == SEQ_METHOD_DMMA && (ket || !dmma_supported(N, e->max_smem_optin) || d->H0_batch_stride))
     return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_DMMA does not cover N=%d ket=%d h0_stride=%lld", N, (int)ket, (long long)d->H0_batch_stride);
   if (method == SEQ_METHOD_SMALL && (ket || d->H0_batch_stride || !small_supported(N, n_g, d->n_e)))
@@ -704,7 +774,7 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
     return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_DMMA_STREAM does not cover N=%d ket=%d h0_stride=%lld", N, (int)ket, (long long)d->H0_batch_stride);
   if (method == SEQ_METHOD_LARGE && (ket || d->H0_batch_stride))
     return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_LARGE covers density matrices with a shared H0 only (N=%d ket=%d)", N, (int)ket);
-  if (method < SEQ_METHOD_GENERIC || method > SEQ_METHOD_SPARSE)
+  if (method < SEQ_METHOD_GENERIC || method > SEQ_METHOD_DIAG)
     return fail(e, SEQ_ERR_UNSUPPORTED, "method %d is not implemented", method);
   if (sharded && method != SEQ_METHOD_LARGE)
     return fail(e, SEQ_ERR_UNSUPPORTED, "row-sharded solves run SEQ_METHOD_LARGE only (got method %d for N=%d)", method, N);
@@ -762,13 +832,24 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
 
   // ---- operator sparsity decides between the sparse (FMA) and the dense (tensor-core) formulation
   SparseInfo spi;
+  DiagPlan dpl;
   if (try_sparse) {
     rc = sparse_analyze(e, d, G0, Gk, Lall, &spi);
     if (rc) return rc;
+    bool diag_ok = false;
+    if (method != SEQ_METHOD_SPARSE) {
+      rc = diag_analyze(e, d, G0, Gk, Lall, spi.plan.nnzE, &dpl, &diag_ok);
+      if (rc) return rc;
+    }
     if (method == SEQ_METHOD_SPARSE) {
       if (!spi.usable) return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_SPARSE: operator rows too dense or N=%d too large for one CTA", N);
-    } else if (spi.usable && spi.worthwhile) {
-      method = SEQ_METHOD_SPARSE;
+    } else if (method == SEQ_METHOD_DIAG) {
+      if (!diag_ok) return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_DIAG: operators have too many diagonals or N=%d too large for one CTA", N);
+    } else {
+      const int n_l = d->n_c + d->n_ctd;
+      const bool diag_worth = diag_ok && dpl.macs * 6 <= (long long)N * (1 + 2 * n_l);
+      if (diag_worth && (!(spi.usable && spi.worthwhile) || dpl.macs <= 2 * spi.plan.macs)) method = SEQ_METHOD_DIAG;
+      else if (spi.usable && spi.worthwhile) method = SEQ_METHOD_SPARSE;
     }
   }
   e->last_method = method;
@@ -806,9 +887,12 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   p.status = d->status; p.stats = d->stats;
   p.ws = (cplx*)e->ws.ptr; p.ws_stride = (long long)ws_per;
 
-  if (method != SEQ_METHOD_SPARSE) CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  if (method != SEQ_METHOD_SPARSE && method != SEQ_METHOD_DIAG) CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
   if (method == SEQ_METHOD_SPARSE) {
     rc = launch_sparse(e, d, p, G0, Gk, spi);
+    if (rc) return rc;
+  } else if (method == SEQ_METHOD_DIAG) {
+    rc = launch_diag(e, d, p, G0, Gk, spi, dpl);
     if (rc) return rc;
   } else if (method == SEQ_METHOD_GENERIC) {
     size_t elems = ket ? (size_t)N : N2;

@@ -15,8 +15,8 @@ SEQ_OK = 0
 STATUS_OK, STATUS_MAX_STEPS, STATUS_NONFINITE, STATUS_STEP_UNDERFLOW = 0, 1, 2, 3
 FLAG_KET, FLAG_NORMALIZE, FLAG_STORE_STATES, FLAG_EXPECT_COMPLEX, FLAG_HOST_POINTERS = 0x1, 0x2, 0x4, 0x8, 0x10
 FLAG_NO_ORDER_SWITCH = 0x20
-METHOD_AUTO, METHOD_GENERIC, METHOD_DMMA, METHOD_SMALL, METHOD_DMMA_STREAM, METHOD_LARGE, METHOD_SPARSE = 0, 1, 2, 3, 4, 5, 6
-METHOD_NAMES = {0: "auto", 1: "generic", 2: "dmma", 3: "small", 4: "dmma_stream", 5: "large", 6: "sparse"}
+METHOD_AUTO, METHOD_GENERIC, METHOD_DMMA, METHOD_SMALL, METHOD_DMMA_STREAM, METHOD_LARGE, METHOD_SPARSE, METHOD_DIAG = 0, 1, 2, 3, 4, 5, 6, 7
+METHOD_NAMES = {0: "auto", 1: "generic", 2: "dmma", 3: "small", 4: "dmma_stream", 5: "large", 6: "sparse", 7: "diag"}
 
 EXPORTS = (
     "seq_engine_abi_version", "seq_engine_build_info", "seq_engine_create", "seq_engine_destroy",
