@@ -140,6 +140,31 @@ def tile_sparsity(bp, method):
                     "complex products use 3 real DMMA chains (Karatsuba) instead of 4"}
 
 
+def structured_work(bp, method):
+    """What the structure-exploiting kernels (diag / sparse) really execute per RHS: complex multiply-adds per
+    owned element = 2 (diagonals | row width of G) + sum_l (diagonals | row width of L_l)^2, over the N (N+1) / 2
+    elements of the upper triangle, 8 real flops each.  Reported next to the algorithmic (dense) figure so that
+    frac > 1 is not misread as tensor-pipe utilisation."""
+    if method not in ("diag", "sparse"):
+        return None
+    N = bp.N
+    Ls = list(bp.Lc if bp.Lc is not None else []) + list(bp.Ltd if bp.Ltd is not None else [])
+    G = np.abs(bp.H0 if bp.H0.ndim == 2 else bp.H0[0]) + sum(np.abs(h) for h in bp.Hk) + sum(np.abs(L.conj().T @ L) for L in Ls)
+
+    def width(M):
+        if method == "diag":
+            i, j = np.nonzero(M)
+            return len(set((j - i).tolist()))
+        return int((M != 0).sum(axis=1).max())
+
+    wg, wl = width(G), [width(np.abs(L)) for L in Ls]
+    macs = 2 * wg + sum(w * w for w in wl)
+    flops = 8.0 * macs * N * (N + 1) / 2
+    return {"G_terms": wg, "L_terms": wl, "complex_macs_per_element": macs, "executed_flops_per_rhs": flops,
+            "note": ("operators stored by diagonals" if method == "diag" else "operators stored as ELL rows")
+                    + "; rho Hermitian -> upper triangle only; FP64 FMA pipe, no tensor cores"}
+
+
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -273,7 +298,10 @@ def ours(args):
 
     from sequencing_b200.solver import Engine
 
+    from sequencing_b200.solver import _lib as seqlib
     bp, desc = build_workload(args.workload)   # every rank integrates its own shard of this size (weak scaling)
+    if args.method != "auto":
+        bp.method = {v: k for k, v in seqlib.METHOD_NAMES.items()}[args.method]
     rows_mode = args.workload == "c5"              # ONE system, rho row-sharded: strong scaling, collectives inside the solve
     if world > 1 and not rows_mode:
         # rank-dependent sweep values: scale the amplitudes a little so shards are distinct units
@@ -405,6 +433,38 @@ def ours(args):
                 roof["tile_sparsity"] = sp
                 roof["executed_dmma_TFLOPs"] = achieved * sp["executed_over_algorithmic_flops"]
                 roof["executed_dmma_frac_of_peak"] = roof["executed_dmma_TFLOPs"] / FP64_DMMA_PEAK_TFLOPS
+            sw = structured_work(bp, out_h.method)
+            if sw:
+                ex = sw["executed_flops_per_rhs"] * float(np.sum(stats[:, 2])) / (k_ms * 1e-3) / 1e12
+                roof["structured"] = sw
+                roof["executed_fp64_TFLOPs"] = ex
+                roof["executed_fp64_frac_of_fma_peak"] = ex / FP64_FMA_PEAK_TFLOPS
+                roof["note"] = ("`achieved` counts the ALGORITHMIC dense flops 8 N^3 (1 + 2 n_c) per RHS (SURVEY.md 8(d)); the kernel "
+                                "AUTO picked exploits the operators' diagonal / row-sparse structure on the FP64 FMA pipe, so frac is "
+                                "a speed-up over a dense tensor-core evaluation at peak, not a pipe utilisation - see `dense_kernel` "
+                                "for the tensor-core kernel on the same inputs")
+                if world == 1 and not args.no_dense and not rows_mode:
+                    # the dense tensor-core formulation on the same workload (a quarter of the batch), for the DMMA roofline
+                    import copy as _copy
+                    nb = max(1, bp.B // 4)
+                    bpd = _copy.copy(bp)
+                    for name in ("coeff", "rate", "state0", "coeff_scale"):
+                        a = getattr(bpd, name)
+                        if a is not None and a.shape[0] == bp.B:
+                            setattr(bpd, name, a[:nb])
+                    bpd.method = seqlib.METHOD_DMMA if bp.N <= 48 else (seqlib.METHOD_DMMA_STREAM if bp.N <= 96 else seqlib.METHOD_LARGE)
+                    tens_d = eng.to_device(bpd)
+                    eng.solve_device(tens_d, bpd); torch.cuda.synchronize()
+                    rd = eng.solve_device(tens_d, bpd); torch.cuda.synchronize()
+                    launches += 2 * eng.last_launches
+                    kd = eng.kernel_ms()
+                    std = rd["out"]["stats"].cpu().numpy()
+                    fd = f_rhs * float(np.sum(std[:, 2])) / (kd * 1e-3) / 1e12
+                    dname = seqlib.METHOD_NAMES[bpd.method]
+                    dsp = tile_sparsity(bpd, dname)
+                    roof["dense_kernel"] = {"method": dname, "trajectories": nb, "kernel_ms": kd, "trajectories_per_s": nb / (kd * 1e-3),
+                                            "algorithmic_TFLOPs": fd, "frac_of_dmma_peak": fd / FP64_DMMA_PEAK_TFLOPS,
+                                            "executed_dmma_frac_of_peak": (fd * dsp["executed_over_algorithmic_flops"] / FP64_DMMA_PEAK_TFLOPS) if dsp else None}
         cpu = None
         if world == 1 and not args.no_cpu:
             pool = OraclePool(args.workload)
@@ -442,6 +502,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense tensor-core kernel run reported in roofline.dense_kernel")
+    ap.add_argument("--method", default="auto", help="force an engine kernel: auto|generic|dmma|dmma_stream|small|large|sparse|diag")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -157,3 +157,28 @@ def row_sparse_problem(N, B, n_t, w_h=3, w_l=1, seed=0, **kw):
         v = np.zeros(N); v[seed % N] = 1.0
         bp.E[0] = np.outer(v, v)           # a projector (1 non-zero), as the sweeps use
     return bp
+
+
+def scattered_sparse_problem(N, B, n_t, seed=0, **kw):
+    """Row-sparse operators WITHOUT diagonal structure: every Hamiltonian term is P + P^dag for a random
+    weighted permutation P plus a diagonal (<= 3 non-zeros per row on ~N different diagonals), every
+    collapse operator a random weighted permutation (1 non-zero per row)."""
+    bp = random_problem(N=N, B=B, n_t=n_t, seed=seed, **kw)
+    rng = np.random.default_rng(2000 + seed)
+
+    def perm():
+        P = np.zeros((N, N), complex)
+        P[np.arange(N), rng.permutation(N)] = rng.normal(size=N) + 1j * rng.normal(size=N)
+        return P
+
+    def herm():
+        P = perm()
+        return 0.3 * (P + P.conj().T) + np.diag(rng.normal(size=N))
+
+    bp.H0 = herm()
+    bp.Hk = np.stack([herm() for _ in bp.Hk]) if bp.Hk.shape[0] else bp.Hk
+    if bp.Lc is not None and bp.Lc.shape[0]:
+        bp.Lc = np.stack([0.2 * perm() for _ in bp.Lc])
+    if bp.Ltd is not None and bp.Ltd.shape[0]:
+        bp.Ltd = np.stack([0.2 * perm() for _ in bp.Ltd])
+    return bp

@@ -9,7 +9,7 @@ tolerances (1e-10/1e-8) and (c) against a converged DOP853 "truth" run, which at
 import numpy as np
 import pytest
 
-from helpers import oracle_solve, random_problem, trace_distance
+from helpers import oracle_solve, random_problem, row_sparse_problem, scattered_sparse_problem, trace_distance
 from sequencing_b200.solver import _lib
 
 pytestmark = pytest.mark.gpu
@@ -206,7 +206,8 @@ def test_workload_c2_selective_full_length(gpu_engine):
     and vs the oracle / a very tight oracle run as truth."""
     from sequencing_b200 import workloads
     make = lambda: workloads.c2_selective(2, 2)
-    _check_problem(gpu_engine, make, [_lib.METHOD_DMMA], n_check=2, truth=False)
+    _check_problem(gpu_engine, make, [_lib.METHOD_DMMA, _lib.METHOD_AUTO], n_check=2, truth=False)
+    assert gpu_engine.solve(make()).method == "diag"        # what AUTO runs for the reference's operators
     a = make(); a.method = _lib.METHOD_DMMA
     g = make(); g.method = _lib.METHOD_GENERIC
     oa, og = gpu_engine.solve(a), gpu_engine.solve(g)
@@ -390,3 +391,64 @@ def test_tensor_core_kernels_with_sparse_operators_match_generic(gpu_engine):
         assert np.max(np.abs(oa.states - og.states)) < 1e-13, N
         assert np.max(np.abs(oa.expect - og.expect)) < 1e-13, N
         np.testing.assert_array_equal(oa.stats[:, :2], og.stats[:, :2])
+
+
+def _match_generic(gpu_engine, mk, method, name, tol=1e-12):
+    a, g = mk(), mk()
+    a.method, g.method = method, _lib.METHOD_GENERIC
+    oa, og = gpu_engine.solve(a), gpu_engine.solve(g)
+    assert oa.method == name and np.all(oa.status == 0)
+    assert np.max(np.abs(oa.states - og.states)) < tol
+    assert np.max(np.abs(oa.final_state - og.final_state)) < tol
+    assert np.max(np.abs(oa.expect - og.expect)) < tol
+    np.testing.assert_array_equal(oa.stats[:, :2], og.stats[:, :2])
+
+
+def test_diag_and_sparse_kernels_match_generic(gpu_engine):
+    """The structure-exploiting FP64-FMA kernels (operators by diagonals / ELL rows, upper triangle of rho in
+    registers) against the dense FP64-FMA kernel: every launch shape (elements per thread, register and
+    streamed stage vectors, guard bands / clamped gathers, one and two Y buffers), ragged rows, several
+    diagonals per collapse operator, constant + time-dependent collapse terms, no collapse terms."""
+    for N, w_h, w_l, n_c, n_ctd in ((7, 3, 1, 2, 0), (12, 3, 1, 2, 1), (20, 5, 2, 2, 1), (31, 3, 1, 3, 0), (45, 3, 1, 4, 0), (46, 5, 1, 2, 0),
+                                    (47, 3, 2, 2, 0), (48, 3, 1, 1, 1), (63, 5, 3, 1, 0), (64, 3, 1, 2, 0), (79, 3, 1, 2, 1), (90, 5, 1, 3, 0),
+                                    (45, 3, 1, 0, 0)):
+        mk = lambda: row_sparse_problem(N=N, B=3, n_t=8, w_h=w_h, w_l=w_l, n_ch=2, n_c=n_c, n_ctd=n_ctd, n_e=2, seed=N, hscale=0.3, store_states=True)
+        _match_generic(gpu_engine, mk, _lib.METHOD_DIAG, "diag")
+        _match_generic(gpu_engine, mk, _lib.METHOD_SPARSE, "sparse")
+    for N in (100, 112):      # beyond one CTA for the diagonal kernel's shapes; the ELL kernel streams its stage vectors
+        mk = lambda: row_sparse_problem(N=N, B=2, n_t=6, w_h=3, w_l=1, n_ch=2, n_c=2, n_e=2, seed=N, hscale=0.3, store_states=True)
+        _match_generic(gpu_engine, mk, _lib.METHOD_SPARSE, "sparse")
+
+
+def test_diag_and_sparse_kernels_rejections_complex_expect_scale(gpu_engine):
+    """Uncapped steps (rejections), non-Hermitian e_ops, one shared coefficient table with per-trajectory scale."""
+    def mk():
+        bp = row_sparse_problem(N=24, B=4, n_t=12, w_h=3, w_l=1, n_ch=2, n_c=2, n_e=2, seed=5, hscale=3.0, store_states=True)
+        rng = np.random.default_rng(2)
+        bp.E = bp.E + 0.3 * (rng.normal(size=bp.E.shape) + 1j * rng.normal(size=bp.E.shape))
+        bp.expect_complex = True
+        bp.coeff = bp.coeff[:1]
+        bp.coeff_scale = rng.uniform(0.2, 3.0, size=(4, 2))
+        bp.max_step = 0.0
+        return bp
+    for method, name in ((_lib.METHOD_DIAG, "diag"), (_lib.METHOD_SPARSE, "sparse")):
+        _match_generic(gpu_engine, mk, method, name, tol=1e-11)
+    out = gpu_engine.solve(mk())
+    assert out.stats[:, 1].max() > 0          # at least one rejected step
+
+
+def test_auto_method_follows_operator_structure(gpu_engine):
+    """AUTO looks at the operators on the device: diagonals -> diag, scattered sparse rows -> sparse (ELL),
+    dense -> the tensor-core kernels; kets and N <= 6 keep their kernels."""
+    from sequencing_b200 import workloads
+    assert gpu_engine.solve(workloads.c4_two_transmons_bus(1)).method == "diag"
+    assert gpu_engine.solve(workloads.c2_selective(1, 2, sigma=10, cavity_levels=4)).method == "diag"
+    mk = lambda: scattered_sparse_problem(N=40, B=2, n_t=6, n_ch=2, n_c=2, n_e=2, seed=3, store_states=True)
+    assert gpu_engine.solve(mk()).method == "sparse"
+    _match_generic(gpu_engine, mk, _lib.METHOD_SPARSE, "sparse")
+    assert gpu_engine.solve(random_problem(N=40, B=1, n_t=3, n_ch=1, n_c=1, n_e=1, seed=1)).method == "dmma"
+    assert gpu_engine.solve(workloads.c1_rabi(3)).method == "small"
+    with pytest.raises(RuntimeError):          # dense operators cannot be forced onto the diagonal kernel
+        bp = random_problem(N=40, B=1, n_t=3, n_ch=1, n_c=1, n_e=1, seed=1)
+        bp.method = _lib.METHOD_DIAG
+        gpu_engine.solve(bp)
