@@ -9,19 +9,30 @@
 //     (L rho L^dag)_ij = sum_{a,b} lam_a[i] conj(lam_b[j]) rho[i + o_a, j + o_b]
 //
 // so every term is "own element + constant offset" in the row-major stage matrix: no index tables, no
-// address arithmetic per term (the host precomputes every offset in bytes), and the terms with offset zero
-// (detunings, Kerr terms, dephasing) use the thread's own registers.  A coefficient is zero wherever its
-// source would fall outside the matrix, so an out-of-range address only has to be readable and finite: Y
-// sits between zero guard bands when they fit in shared memory (GUARD), otherwise the address is clamped.
+// address arithmetic per term (the host precomputes every offset in bytes).  Everything static that acts on
+// the own element (G0's main diagonal: detunings, Kerr and dispersive shifts; constant-rate dephasing pairs)
+// is folded into ONE complex weight per element at kernel start.  A coefficient is zero wherever its source
+// would fall outside the matrix, so an out-of-range address only has to be readable and finite: Y sits
+// between zero guard bands when they fit in shared memory (GUARD), otherwise the address is clamped.
 //
-// Work decomposition: one CTA per trajectory, each thread owns EPT elements of the upper triangle (y, RK
-// stages, accumulators in registers), the full stage matrix Y double-buffered in shared memory, one barrier
-// per right-hand side.  Step control (the shared StepCtl: identical decisions to every other kernel), the
-// spline evaluation of all stage times of the next step and the output bookkeeping run on warp 0 only and
-// reach the other warps through a small control block in shared memory - the scalar pow()/ceil()/division
-// chains would otherwise be re-executed by every warp.  Operators that are row-sparse but not
-// diagonal-structured take the ELL kernel (SEQ_METHOD_SPARSE), dense ones the tensor-core kernels.
+// Work decomposition ("band" ownership).  rho is Hermitian, so of every pair (i,j), (j,i) only one element
+// is integrated: row i owns the cyclic band j = i, i+1, .., i + N/2 (mod N) - every row the same length
+// L = N/2 + 1, unlike the rows of a triangle.  One quarter-warp (8 lanes) owns one row, lane q the elements
+// d = q, q + 8, ..: every shared-memory gather of a quarter-warp is 8 consecutive complex numbers (one
+// conflict-free 128-byte wavefront) and the row coefficient v_d[i] is loaded once per thread.  y, the RK stage
+// derivatives and the accumulators live in registers; the full stage matrix Y is in shared memory (owners
+// write Y_ij and its mirror Y_ji), double-buffered when it fits; one barrier per right-hand side.
+//   N <= 48: one CTA per trajectory.   48 < N <= 94: a cluster of two CTAs per trajectory - each owns every
+//   other row, writes its elements into BOTH CTAs' shared memory (DSMEM stores) and the per-RHS barrier is a
+//   cluster barrier; the error norm is exchanged the same way, the scalar control runs redundantly.
+// Step control (the shared StepCtl: identical decisions to every other kernel), the spline values of all stage
+// times of the next step and the output bookkeeping run on warp 0 only and reach the other warps through a
+// small control block - the scalar pow()/ceil()/division chains would otherwise be re-executed by every warp.
+// The stage loop is unrolled at compile time per embedded pair (static register indices, tableau entries as
+// immediates).  Operators that are row-sparse but not diagonal-structured take the ELL kernel
+// (SEQ_METHOD_SPARSE), dense ones the tensor-core kernels.
 #pragma once
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace seq {
@@ -37,17 +48,20 @@ struct DiagOps {
   int go_tab[DIAG_MAX_GD];    // table of diagonal d inside a Gt buffer
   int go_offL[DIAG_MAX_GD];   // o_d * ld * 16: source of the left term  rho[i + o_d, j]
   int go_offR[DIAG_MAX_GD];   // o_d * 16:      source of the right term rho[i, j + o_d]
-  // --- collapse pair terms on the own element / on a gathered element
-  int nLo, nLg;
-  int lo_a[DIAG_MAX_LT], lo_b[DIAG_MAX_LT], lo_r[DIAG_MAX_LT];   // table a, table b (bytes inside lam); rate index or -1
+  // --- collapse pair terms on the own element (constant rate: folded into a static weight at kernel start;
+  // time-dependent rate: evaluated per RHS) / on a gathered element
+  int nLs, nLo, nLg;
+  int ls_a[DIAG_MAX_LT], ls_b[DIAG_MAX_LT];
+  int lo_a[DIAG_MAX_LT], lo_b[DIAG_MAX_LT], lo_r[DIAG_MAX_LT];   // table a, table b (bytes inside lam); rate index
   int lg_a[DIAG_MAX_LT], lg_b[DIAG_MAX_LT], lg_r[DIAG_MAX_LT], lg_off[DIAG_MAX_LT];
   int nT;                     // collapse diagonals (tables)
   int n_el, ld, ybufs, guard; // owned elements, leading dimension, Y buffers, guard band (elements)
   int stage_g, stage_e, stage_tab, nnzE;   // what is staged in shared memory
+  int lreal;                  // every collapse diagonal is real
   const cplx* g0;             // [nD][N]
   const cplx* gk;             // [n_g][nD][N]
   const cplx* lam;            // [nT][N]
-  const unsigned* ij;         // [n_el]
+  const cplx* gdiag;          // [N]: static main diagonal of G0 (folded into the own-element weight)
   const int* e_off;           // COO lists of the expectation operators (layout shared with the ELL kernel)
   const unsigned* e_ij;
   const cplx* e_val;
@@ -56,15 +70,15 @@ struct DiagOps {
 // ---------------------------------------------------------------------------------------------------
 // preparation
 // ---------------------------------------------------------------------------------------------------
-// flags[op][o + N - 1] = 1 if operator `op` (0: union of G0, Gk; 1..n_l: L_l) has a non-zero on diagonal o
+// flags[op][o + N - 1] = 1 if operator `op` (0: union of G0, Gk; 1..n_l: L_l; 1+n_l: union of Gk) has a non-zero on diagonal o
 __global__ void diag_flags_kernel(const cplx* __restrict__ G0, const cplx* __restrict__ Gk, int n_g,
                                   const cplx* __restrict__ L, int N, int* __restrict__ flags) {
   const int op = blockIdx.y;
   const long long N2 = (long long)N * N;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < N2; t += (long long)gridDim.x * blockDim.x) {
     bool nz;
-    if (op == 0) {
-      cplx v = G0[t];
+    if (op == 0 || op == gridDim.y - 1) {      // 0: G0 and every Gk; last: the time-dependent part (Gk) only
+      cplx v = (op == 0) ? G0[t] : cmake(0, 0);
       nz = (v.x != 0.0 || v.y != 0.0);
       for (int m = 0; m < n_g && !nz; m++) { cplx w = Gk[m * N2 + t]; nz = (w.x != 0.0 || w.y != 0.0); }
     } else {
@@ -88,15 +102,17 @@ struct DiagFill {
 // grid.x over rows, grid.y = nD + nT: extract one diagonal
 __global__ void diag_fill_kernel(const __grid_constant__ DiagFill f, const cplx* __restrict__ G0, const cplx* __restrict__ Gk, int n_g,
                                  const cplx* __restrict__ L, int N, cplx* __restrict__ g0, cplx* __restrict__ gk,
-                                 cplx* __restrict__ lam, int* __restrict__ any_imag) {
+                                 cplx* __restrict__ lam, cplx* __restrict__ gdiag, int* __restrict__ any_imag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, d = blockIdx.y;
   if (i >= N) return;
   const long long N2 = (long long)N * N;
+  if (d == 0) gdiag[i] = G0[(long long)i * N + i];
   if (d < f.nD) {
     const int j = i + f.goff[d];
-    const bool in = j >= 0 && j < N;
+    const bool in = j >= 0 && j < N && f.goff[d] != 0;     // the static main diagonal lives in gdiag
     g0[(long long)d * N + i] = in ? G0[(long long)i * N + j] : cmake(0, 0);
-    for (int m = 0; m < n_g; m++) gk[((long long)m * f.nD + d) * N + i] = in ? Gk[m * N2 + (long long)i * N + j] : cmake(0, 0);
+    const bool ink = j >= 0 && j < N;
+    for (int m = 0; m < n_g; m++) gk[((long long)m * f.nD + d) * N + i] = ink ? Gk[m * N2 + (long long)i * N + j] : cmake(0, 0);
   } else {
     const int t = d - f.nD;
     const int j = i + f.t_off[t];
@@ -122,7 +138,7 @@ struct DiagCtrl {
 struct DiagCtlState {
   StepCtl ctl;
   double htry, target;
-  int o, nst, landing, capped;
+  int o, nst, landing, capped, dbg;
 };
 
 struct DiagLayout {
@@ -143,7 +159,7 @@ __host__ __device__ inline DiagLayout diag_layout(int N, int n_g, int n_t, const
   L.off_tab = L.off_e + (o.stage_e ? (o.nnzE > 0 ? o.nnzE : 1) * 32 : 0);   // 16 B value + 4 B index, padded
   L.off_cv = L.off_tab + (o.stage_tab ? n_g * n_t * (int)sizeof(double2) : 0);
   L.off_red = L.off_cv + 7 * (n_g > 0 ? n_g : 1) * (int)sizeof(double);
-  L.off_ctrl = L.off_red + 64 * (int)sizeof(double);
+  L.off_ctrl = L.off_red + 128 * (int)sizeof(double);
   L.total = L.off_ctrl + 64 + 192;   // DiagCtrl + DiagCtlState
   return L;
 }
@@ -177,6 +193,9 @@ __device__ __noinline__ void diag_controller(const SolveParams& p, DiagCtlState*
     ctl.nrhs += nrhs;
     ctl.have_k1 = true;
     const double err = sqrt(es / ((double)p.N * (double)p.N));
+#ifdef SEQ_PROFILE_REGIONS
+    if (lane == 0) { if (err <= 2.9e-6) S->dbg += 1; if (err <= 2.9e-7) S->dbg += 1 << 16; }   // instrumentation only
+#endif
     accepted = ctl_update(ctl, p, err, c_htry, c_landing, c_capped, c_target, c_nst);
   }
   const int emit_lo = c_o;
@@ -218,24 +237,33 @@ __device__ __noinline__ void diag_controller(const SolveParams& p, DiagCtlState*
   __syncwarp();
 }
 
-#define DIAG_MAXT(EPT, KREG) ((KREG) ? ((EPT) <= 2 ? 544 : ((EPT) == 3 ? 384 : 512)) : ((EPT) <= 4 ? 1024 : ((EPT) <= 6 ? 704 : 512)))
+// threads per CTA by (elements per thread, stage vectors in registers): 65536 registers / threads, allocated per 4 warps
+#define DIAG_MAX_EPT 6
+#define DIAG_MAXT 384       // 168 registers per thread
 
-template <int EPT, bool KREG, bool GUARD, bool LREAL>
-__global__ void __launch_bounds__(DIAG_MAXT(EPT, KREG), 1)
+namespace cg = cooperative_groups;
+
+template <int EPT, int CL, bool GUARD>
+__global__ void __launch_bounds__(DIAG_MAXT, 1)
 solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__ DiagOps sp) {
   extern __shared__ __align__(16) unsigned char smem_diag[];
+  constexpr int C = (int)sizeof(cplx);
   const int N = p.N, ld = sp.ld, n_g = p.n_g;
-  const int tid = threadIdx.x, nth = blockDim.x, b = blockIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nw = (nth + 31) >> 5;
+  const int rank = (CL > 1) ? (int)(blockIdx.x % CL) : 0;      // CTA inside the cluster
+  const int b = blockIdx.x / CL;                                // trajectory
   const DiagLayout L = diag_layout(N, n_g, p.n_t, sp);
   double* cv = (double*)(smem_diag + L.off_cv);
   double* red = (double*)(smem_diag + L.off_red);
   DiagCtrl* ctrl = (DiagCtrl*)(smem_diag + L.off_ctrl);
+  unsigned char* peer = nullptr;                                // the other CTA's shared memory (same layout)
+  if (CL > 1) peer = (unsigned char*)cg::this_cluster().map_shared_rank((void*)smem_diag, rank ^ 1);
+  auto sync_all = [&]() { if (CL > 1) cg::this_cluster().sync(); else __syncthreads(); };
 
   const double2* tabc = p.tab + (long long)b * p.tab_bstride_c;
   const double2* tabr = p.tab_rate + (long long)b * p.tab_bstride_r;
   const double* cscale = p.coeff_scale ? p.coeff_scale + (long long)b * p.n_ch : nullptr;
-  cplx* kst = KREG ? nullptr : p.ws + (long long)b * p.ws_stride;   // [6][EPT][nth]
 
   // ---- stage shared tables: zero guard bands / Y padding, collapse diagonals, G diagonals, E, spline tables
   for (int q = tid; q < L.off_Gt / 16; q += nth) ((cplx*)smem_diag)[q] = cmake(0, 0);
@@ -264,40 +292,65 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
     tabc = ts; tabr = ts + p.n_ch * p.n_t;
   }
 
-  // ---- owned elements: byte offsets of Y_ij inside a buffer, of row-table entry i and of entry j.  The
-  // offsets are laundered through an empty asm so that they stay in registers as they are instead of being
-  // re-derived from (i, j) at every use.
-  int oy[EPT], oi[EPT], oj[EPT];
-  unsigned vmask = 0;
-  cplx y[EPT], ys[EPT], kout[EPT];
-  cplx k[KREG ? 6 : 1][EPT];
-  const cplx* y0 = p.state0 + (long long)b * N * N;
+  // ---- owned elements: row i = (tid / 8) * CL + rank, band positions d = (tid % 8) + 8 e.  oy[e]: byte offset of
+  // Y[i, j_e] inside a buffer; oi: of entry i of a diagonal table; rowb: of Y[i, 0] (so that oy[e] - rowb is the
+  // offset of entry j_e of a table).  Laundered through an empty asm so that they stay in registers as computed.
+  int oy[EPT], oi, rowb;
+  unsigned vmask = 0, dmask = 0;      // valid elements; elements on the main diagonal
+  cplx y[EPT], ys[EPT], kout[EPT], W[EPT];
+  cplx k[6][EPT];
+  {
+    const int i_raw = (tid >> 3) * CL + rank, q8 = tid & 7;
+    const bool rowok = i_raw < N;
+    const int i = rowok ? i_raw : 0;
+    const int Lb = N / 2 + 1;
+    oi = i * C;
+    rowb = i * ld * C;
+    const cplx* y0 = p.state0 + (long long)b * N * N;
+    const cplx gi = sp.gdiag[i];
 #pragma unroll
-  for (int e = 0; e < EPT; e++) {
-    const int idx = tid + e * nth;
-    const bool v = idx < sp.n_el;
-    const unsigned code = v ? sp.ij[idx] : 0u;
-    const int i = code & 0xffffu, j = code >> 16;
-    if (v) vmask |= 1u << e;
-    oy[e] = (i * ld + j) * (int)sizeof(cplx);
-    oi[e] = i * (int)sizeof(cplx);
-    oj[e] = j * (int)sizeof(cplx);
-    y[e] = v ? y0[i * N + j] : cmake(0, 0);
-    asm volatile("" : "+r"(oy[e]), "+r"(oi[e]), "+r"(oj[e]));
-    ys[e] = y[e];
-    kout[e] = cmake(0, 0);
+    for (int e = 0; e < EPT; e++) {
+      const int d = q8 + 8 * e;
+      const bool v = rowok && d < Lb && !((N & 1) == 0 && d == N / 2 && i >= N / 2);
+      int j = i + (v ? d : 0);
+      if (j >= N) j -= N;
+      if (v) vmask |= 1u << e;
+      if (v && d == 0) dmask |= 1u << e;
+      oy[e] = (i * ld + j) * C;
+      y[e] = v ? y0[i * N + j] : cmake(0, 0);
+      ys[e] = y[e];
+      kout[e] = cmake(0, 0);
 #pragma unroll
-    for (int q = 0; q < (KREG ? 6 : 1); q++) k[q][e] = cmake(0, 0);
+      for (int q = 0; q < 6; q++) k[q][e] = cmake(0, 0);
+      // static own-element weight: -i (G0_ii - conj(G0_jj)) + sum over constant-rate pairs lam_a[i] conj(lam_b[j])
+      const cplx gj = sp.gdiag[j];
+      cplx w = cmake(gi.y + gj.y, -(gi.x - gj.x));
+      for (int t = 0; t < sp.nLs; t++) {
+        const cplx a = sp.lam[sp.ls_a[t] / C + i], c = sp.lam[sp.ls_b[t] / C + j];
+        w.x += a.x * c.x + a.y * c.y;
+        w.y += a.y * c.x - a.x * c.y;
+      }
+      W[e] = w;
+      asm volatile("" : "+r"(oy[e]));
+    }
+    asm volatile("" : "+r"(oi), "+r"(rowb));
   }
-  __syncthreads();   // guard bands zeroed before anything is written into Y
+  sync_all();   // guard bands zeroed (in both CTAs) before anything is written into Y
 
   int yb = 0, gb = 0, tog = 0, ycur = 0;
-  auto write_Y = [&](unsigned char* Yb, const cplx (&v)[EPT]) {
+  PROF_DECL
+  // owner writes Y_ij and the mirror Y_ji, into every CTA of the cluster
+  auto write_Y = [&](int boff, const cplx (&v)[EPT]) {
 #pragma unroll
     for (int e = 0; e < EPT; e++) {
       if (vmask & (1u << e)) {
-        *(cplx*)(Yb + oy[e]) = v[e];
-        if (oi[e] != oj[e]) *(cplx*)(Yb + oj[e] * ld + oi[e]) = cconj(v[e]);
+        const int ot = (oy[e] - rowb) * ld + oi;          // (j ld + i) 16
+        *(cplx*)(smem_diag + boff + oy[e]) = v[e];
+        if (CL > 1) *(cplx*)(peer + boff + oy[e]) = v[e];
+        if (!(dmask & (1u << e))) {
+          *(cplx*)(smem_diag + boff + ot) = cconj(v[e]);
+          if (CL > 1) *(cplx*)(peer + boff + ot) = cconj(v[e]);
+        }
       }
     }
   };
@@ -313,83 +366,82 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       Gb[q] = g;
     }
   };
-  const int y_hi = L.ybytes - (int)sizeof(cplx);
+  const int y_hi = L.ybytes - C;
   auto yaddr = [&](int a) -> int { return GUARD ? a : min(max(a, 0), y_hi); };
+  const bool lreal = sp.lreal != 0;
 
+  // kout = W ys - i (G' Y - Y G'^dag) + collapse terms, G' = G minus its static main diagonal
   auto compute_K = [&](const unsigned char* __restrict__ Yb, const unsigned char* __restrict__ Gb, int st) {
-    cplx D[EPT];
-    if (sp.g0_tab >= 0) {
+#pragma unroll
+    for (int e = 0; e < EPT; e++) kout[e] = cmul(W[e], ys[e]);
+    if (sp.g0_tab >= 0) {      // time-dependent main diagonal
       const unsigned char* gv = Gb + sp.g0_tab;
+      const cplx vi = *(const cplx*)(gv + oi);
 #pragma unroll
       for (int e = 0; e < EPT; e++) {
-        const cplx vi = *(const cplx*)(gv + oi[e]);
-        const cplx vj = *(const cplx*)(gv + oj[e]);
-        const cplx dd = cmake(vi.x - vj.x, vi.y + vj.y);   // v_0[i] - conj(v_0[j])
-        D[e] = cmul(dd, ys[e]);
+        const cplx vj = *(const cplx*)(gv - rowb + oy[e]);
+        const cplx dd = cmake(vi.y + vj.y, -(vi.x - vj.x));   // -i (v_0[i] - conj(v_0[j]))
+        cfma(kout[e], dd, ys[e]);
       }
-    } else {
-#pragma unroll
-      for (int e = 0; e < EPT; e++) D[e] = cmake(0, 0);
     }
 #pragma unroll 1
     for (int t = 0; t < sp.nGo; t++) {
       const unsigned char* gv = Gb + sp.go_tab[t];
-      const unsigned char* YL = Yb + sp.go_offL[t];
-      const unsigned char* YR = Yb + sp.go_offR[t];
+      const int offL = sp.go_offL[t], offR = sp.go_offR[t];
+      const cplx vi = *(const cplx*)(gv + oi);
+      const cplx mvi = cmake(vi.y, -vi.x);            // -i v_d[i]
+      const unsigned char* gvj = gv - rowb;
 #pragma unroll
       for (int e = 0; e < EPT; e++) {
-        const cplx vi = *(const cplx*)(gv + oi[e]);
-        const cplx ya = GUARD ? *(const cplx*)(YL + oy[e]) : *(const cplx*)(Yb + yaddr(oy[e] + sp.go_offL[t]));
-        cfma(D[e], vi, ya);
-        const cplx vj = *(const cplx*)(gv + oj[e]);
-        const cplx yv = GUARD ? *(const cplx*)(YR + oy[e]) : *(const cplx*)(Yb + yaddr(oy[e] + sp.go_offR[t]));
-        // D -= conj(vj) * yv
-        D[e].x = fma(-vj.x, yv.x, D[e].x); D[e].x = fma(-vj.y, yv.y, D[e].x);
-        D[e].y = fma(-vj.x, yv.y, D[e].y); D[e].y = fma(vj.y, yv.x, D[e].y);
+        const cplx ya = *(const cplx*)(Yb + yaddr(oy[e] + offL));
+        cfma(kout[e], mvi, ya);
+        const cplx vj = *(const cplx*)(gvj + oy[e]);
+        const cplx yv = *(const cplx*)(Yb + yaddr(oy[e] + offR));
+        // + i conj(vj) yv = (vj.y + i vj.x) (yv.x + i yv.y)
+        kout[e].x = fma(vj.y, yv.x, kout[e].x); kout[e].x = fma(-vj.x, yv.y, kout[e].x);
+        kout[e].y = fma(vj.y, yv.y, kout[e].y); kout[e].y = fma(vj.x, yv.x, kout[e].y);
       }
     }
-#pragma unroll
-    for (int e = 0; e < EPT; e++) kout[e] = cmake(D[e].y, -D[e].x);
     const unsigned char* lam = smem_diag + L.off_lam;
-    // collapse terms on the own element (dephasing-like: both diagonals are the main diagonal)
+    // collapse terms on the own element with a time-dependent rate
 #pragma unroll 1
     for (int t = 0; t < sp.nLo; t++) {
       const unsigned char* la = lam + sp.lo_a[t];
-      const unsigned char* lb = lam + sp.lo_b[t];
-      const int ri = sp.lo_r[t];
-      const double r = ri < 0 ? 1.0 : cv[st * n_g + ri];
+      const unsigned char* lbj = lam + sp.lo_b[t] - rowb;
+      const double r = cv[st * n_g + sp.lo_r[t]];
+      const cplx a = seq::cscale(r, *(const cplx*)(la + oi));
 #pragma unroll
       for (int e = 0; e < EPT; e++) {
-        if (LREAL) {
-          const double w = r * (*(const double*)(la + oi[e])) * (*(const double*)(lb + oj[e]));
-          kout[e].x = fma(w, ys[e].x, kout[e].x);
-          kout[e].y = fma(w, ys[e].y, kout[e].y);
-        } else {
-          const cplx a = *(const cplx*)(la + oi[e]), c = *(const cplx*)(lb + oj[e]);
-          const double wx = r * (a.x * c.x + a.y * c.y), wy = r * (a.y * c.x - a.x * c.y);
-          kout[e].x = fma(wx, ys[e].x, kout[e].x); kout[e].x = fma(-wy, ys[e].y, kout[e].x);
-          kout[e].y = fma(wx, ys[e].y, kout[e].y); kout[e].y = fma(wy, ys[e].x, kout[e].y);
-        }
+        const cplx c = *(const cplx*)(lbj + oy[e]);
+        const double wx = a.x * c.x + a.y * c.y, wy = a.y * c.x - a.x * c.y;
+        kout[e].x = fma(wx, ys[e].x, kout[e].x); kout[e].x = fma(-wy, ys[e].y, kout[e].x);
+        kout[e].y = fma(wx, ys[e].y, kout[e].y); kout[e].y = fma(wy, ys[e].x, kout[e].y);
       }
     }
     // collapse terms that gather rho[i + o_a, j + o_b]
 #pragma unroll 1
     for (int t = 0; t < sp.nLg; t++) {
       const unsigned char* la = lam + sp.lg_a[t];
-      const unsigned char* lb = lam + sp.lg_b[t];
-      const unsigned char* YG = Yb + sp.lg_off[t];
+      const unsigned char* lbj = lam + sp.lg_b[t] - rowb;
+      const int off = sp.lg_off[t];
       const int ri = sp.lg_r[t];
       const double r = ri < 0 ? 1.0 : cv[st * n_g + ri];
+      if (lreal) {
+        const double ra = r * (*(const double*)(la + oi));
 #pragma unroll
-      for (int e = 0; e < EPT; e++) {
-        const cplx yv = GUARD ? *(const cplx*)(YG + oy[e]) : *(const cplx*)(Yb + yaddr(oy[e] + sp.lg_off[t]));
-        if (LREAL) {
-          const double w = r * (*(const double*)(la + oi[e])) * (*(const double*)(lb + oj[e]));
+        for (int e = 0; e < EPT; e++) {
+          const cplx yv = *(const cplx*)(Yb + yaddr(oy[e] + off));
+          const double w = ra * (*(const double*)(lbj + oy[e]));
           kout[e].x = fma(w, yv.x, kout[e].x);
           kout[e].y = fma(w, yv.y, kout[e].y);
-        } else {
-          const cplx a = *(const cplx*)(la + oi[e]), c = *(const cplx*)(lb + oj[e]);
-          const double wx = r * (a.x * c.x + a.y * c.y), wy = r * (a.y * c.x - a.x * c.y);
+        }
+      } else {
+        const cplx a = seq::cscale(r, *(const cplx*)(la + oi));
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+          const cplx yv = *(const cplx*)(Yb + yaddr(oy[e] + off));
+          const cplx c = *(const cplx*)(lbj + oy[e]);
+          const double wx = a.x * c.x + a.y * c.y, wy = a.y * c.x - a.x * c.y;
           kout[e].x = fma(wx, yv.x, kout[e].x); kout[e].x = fma(-wy, yv.y, kout[e].x);
           kout[e].y = fma(wx, yv.y, kout[e].y); kout[e].y = fma(wy, yv.x, kout[e].y);
         }
@@ -397,25 +449,29 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
     }
   };
   auto emit = [&](const unsigned char* __restrict__ Yb, int o) {
-    const int nw = (nth + 31) >> 5;
-    for (int e = warp; e < p.n_e; e += nw) {
-      cplx acc = cmake(0, 0);
-      const int q1 = sp.e_off[e + 1];
-      for (int q = sp.e_off[e] + lane; q < q1; q += 32) {
-        const unsigned code = eij[q];
-        cfma(acc, eval_[q], ((const cplx*)Yb)[(code >> 16) * ld + (code & 0xffffu)]);   // E_ij rho_ji
-      }
-      acc.x = warp_sum(acc.x);
-      acc.y = warp_sum(acc.y);
-      if (lane == 0) {
-        const long long off = ((long long)b * p.n_e + e) * p.n_out + o;
-        if (p.flags & SEQ_FLAG_EXPECT_COMPLEX) ((cplx*)p.expect)[off] = acc;
-        else ((double*)p.expect)[off] = acc.x;
+    // one warp per operator, starting from the LAST warp (warp 0 carries the step controller); cluster: CTA 0
+    if (rank == 0) {
+      for (int e = nw - 1 - warp; e < p.n_e; e += nw) {
+        cplx acc = cmake(0, 0);
+        const int q0 = sp.e_off[e], q1 = sp.e_off[e + 1];
+        for (int q = q0 + lane; q < q1; q += 32) {
+          const unsigned code = eij[q];
+          cfma(acc, eval_[q], ((const cplx*)Yb)[(code >> 16) * ld + (code & 0xffffu)]);   // E_ij rho_ji
+        }
+        if (q1 - q0 > 1) {          // projectors (the sweeps' e_ops) have a single entry: nothing to reduce
+          acc.x = warp_sum(acc.x);
+          acc.y = warp_sum(acc.y);
+        }
+        if (lane == 0) {
+          const long long off = ((long long)b * p.n_e + e) * p.n_out + o;
+          if (p.flags & SEQ_FLAG_EXPECT_COMPLEX) ((cplx*)p.expect)[off] = acc;
+          else ((double*)p.expect)[off] = acc.x;
+        }
       }
     }
     if (p.flags & SEQ_FLAG_STORE_STATES) {
       cplx* dst = p.states + ((long long)b * p.n_out + o) * N * N;
-      for (int q = tid; q < N * N; q += nth) { const int i = q / N, j = q - i * N; dst[q] = ((const cplx*)Yb)[i * ld + j]; }
+      for (int q = tid + rank * nth; q < N * N; q += nth * CL) { const int i = q / N, j = q - i * N; dst[q] = ((const cplx*)Yb)[i * ld + j]; }
     }
   };
 
@@ -424,13 +480,13 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
     StepCtl c0;
     ctl_init(c0, p);
     cst->ctl = c0;
-    cst->htry = 0.0; cst->target = 0.0; cst->o = 0; cst->nst = 0; cst->landing = 0; cst->capped = 0;
+    cst->htry = 0.0; cst->target = 0.0; cst->o = 0; cst->nst = 0; cst->landing = 0; cst->capped = 0; cst->dbg = 0;
   }
   __syncwarp();
 
-  write_Y(smem_diag + L.off_Y, y);
+  write_Y(L.off_Y, y);
   if (warp == 0) diag_controller(p, cst, ctrl, cv, tabc, tabr, cscale, 0, 0, 0.0);
-  __syncthreads();
+  sync_all();
 
   // One embedded-RK step with the stage loop unrolled at compile time: static register indices for the stage
   // derivatives, tableau coefficients as immediates (zero entries vanish).  Returns this thread's share of
@@ -448,29 +504,31 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
         for (int j = 0; j < 6; j++) {
           const double aj = rk_a_c(PAIR, st, j);
           if (j < st && aj != 0.0) {
-            const cplx kv = KREG ? k[KREG ? j : 0][e] : kst[((long long)j * EPT + e) * nth + tid];
-            ax = fma(aj, kv.x, ax);
-            ay = fma(aj, kv.y, ay);
+            ax = fma(aj, k[j][e].x, ax);
+            ay = fma(aj, k[j][e].y, ay);
           }
         }
         ys[e] = (st == 0) ? y[e] : cmake(fma(htry, ax, y[e].x), fma(htry, ay, y[e].y));
       }
       if (sp.ybufs == 2) yb ^= 1;
       gb ^= 1;
-      unsigned char* Yb = smem_diag + L.off_Y + yb * L.ystride;
+      const int boff = L.off_Y + yb * L.ystride;
       unsigned char* Gb = smem_diag + L.off_Gt + gb * L.gtbytes;
-      write_Y(Yb, ys);
+      if (CL > 1 && sp.ybufs == 1) cg::this_cluster().barrier_wait();   // every gather of the previous stage is done
+      write_Y(boff, ys);
       build_Gt((cplx*)Gb, st);
-      __syncthreads();
-      compute_K(Yb, Gb, st);
+      PROF(1);
+      sync_all();
+      PROF(2);
+      compute_K(smem_diag + boff, Gb, st);
+      if (sp.ybufs == 1) {                      // all gathers done before the next stage overwrites Y
+        if (CL > 1) cg::this_cluster().barrier_arrive(); else __syncthreads();
+      }
       if (st < S - 1) {
 #pragma unroll
-        for (int e = 0; e < EPT; e++) {
-          if (KREG) k[KREG ? st : 0][e] = kout[e];
-          else kst[((long long)st * EPT + e) * nth + tid] = kout[e];
-        }
+        for (int e = 0; e < EPT; e++) k[st][e] = kout[e];
       }
-      if (sp.ybufs == 1) __syncthreads();       // all gathers done before the next stage overwrites Y
+      PROF(3);
     }
     // error estimate: h (sum_{j<S-1} e_j k_j + e_{S-1} k_S), weighted RMS over all N^2 elements
     double es = 0.0;
@@ -481,14 +539,13 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       for (int j = 0; j < S - 1; j++) {
         const double cj = rk_e_c(PAIR, j);
         if (cj != 0.0) {
-          const cplx kv = KREG ? k[KREG ? j : 0][e] : kst[((long long)j * EPT + e) * nth + tid];
-          ex = fma(cj, kv.x, ex);
-          ey = fma(cj, kv.y, ey);
+          ex = fma(cj, k[j][e].x, ex);
+          ey = fma(cj, k[j][e].y, ey);
         }
       }
       ex *= htry; ey *= htry;
       const double sc = p.atol + p.rtol * sqrt(fmax(cabs2(y[e]), cabs2(ys[e])));
-      const double wgt = (vmask & (1u << e)) ? ((oi[e] == oj[e]) ? 1.0 : 2.0) : 0.0;
+      const double wgt = (vmask & (1u << e)) ? ((dmask & (1u << e)) ? 1.0 : 2.0) : 0.0;
       es += wgt * (ex * ex + ey * ey) / (sc * sc);
     }
     return es;
@@ -500,38 +557,59 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
 #pragma unroll
       for (int e = 0; e < EPT; e++) {
         y[e] = ys[e];
-        if (KREG) k[0][e] = kout[e];
-        else kst[((long long)e) * nth + tid] = kout[e];
+        k[0][e] = kout[e];
       }
       ycur = yb;
     }
     for (int o = c.emit_lo; o < c.emit_hi; o++) emit(smem_diag + L.off_Y + ycur * L.ystride, o);
+    PROF(0);
     if (c.cmd) break;
-    if (sp.ybufs == 1 && c.emit_hi > c.emit_lo) __syncthreads();   // emit reads the buffer the next stage overwrites
+    if (sp.ybufs == 1) {
+      // the next stage overwrites the buffer emit() read.  Cluster: every stage starts by closing a split barrier
+      // whose arrive marks "my gathers from Y are done" - open the one for the first stage of this step here
+      if (CL > 1) cg::this_cluster().barrier_arrive();
+      else if (c.emit_hi > c.emit_lo) __syncthreads();
+    }
     double es;
     if (c.pair) es = run_step(IntTag<1>(), c.st0, c.htry);
     else es = run_step(IntTag<0>(), c.st0, c.htry);
-    es = diag_block_sum(es, red, tog);
+    PROF(4);
+    // block (cluster) sum of the error: every warp leaves its partial sum in every CTA, fixed summation order
+    es = warp_sum(es);
+    if (lane == 0) {
+      red[tog * 64 + rank * 32 + warp] = es;
+      if (CL > 1) ((double*)(peer + L.off_red))[tog * 64 + rank * 32 + warp] = es;
+    }
+    if (CL > 1 && sp.ybufs == 1) cg::this_cluster().barrier_wait();      // close the split barrier of the last stage
+    sync_all();
+    es = 0.0;
+    for (int r = 0; r < CL; r++)
+      for (int q = 0; q < nw; q++) es += red[tog * 64 + r * 32 + q];
+    tog ^= 1;
+    PROF(5);
     if (warp == 0) diag_controller(p, cst, ctrl, cv, tabc, tabr, cscale, 1, (c.pair ? 5 : 7) - c.st0, es);
+    PROF(6);
     __syncthreads();
+    PROF(7);
   }
 
   cplx* fin = p.final_state + (long long)b * N * N;
 #pragma unroll
   for (int e = 0; e < EPT; e++) {
     if (vmask & (1u << e)) {
-      const int i = oi[e] / (int)sizeof(cplx), j = oj[e] / (int)sizeof(cplx);
+      const int i = oi / C, j = (oy[e] - rowb) / C;
       fin[i * N + j] = y[e];
       if (i != j) fin[j * N + i] = cconj(y[e]);
     }
   }
-  if (tid == 0) {
+  if (tid == 0 && rank == 0) {
     p.status[b] = cst->ctl.status;
     p.stats[b * 4 + 0] = cst->ctl.nacc;
     p.stats[b * 4 + 1] = cst->ctl.nrej;
     p.stats[b * 4 + 2] = cst->ctl.nrhs;
-    p.stats[b * 4 + 3] = 0;
+    p.stats[b * 4 + 3] = cst->dbg;
   }
+  if (CL > 1) cg::this_cluster().sync();     // no CTA exits while its shared memory may still be written remotely
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -541,7 +619,7 @@ struct DiagPlan {
   DiagOps ops;          // offsets / term lists filled in; pointers set at launch
   DiagFill fill;
   int maxoff;
-  int ept, threads;
+  int ept, cl, threads;
   bool kreg, guard;
   size_t smem;
   long long macs;       // complex multiply-adds per element (cost model)
@@ -550,7 +628,7 @@ struct DiagPlan {
 // flags: host copy of diag_flags_kernel's output, [1 + n_l][2N - 1].  Returns false if the operators are not
 // diagonal-structured enough (too many diagonals) or no launch shape fits.
 static inline bool diag_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, int n_t, int nnzE, const int* flags, int max_smem,
-                             int ept_override, DiagPlan* pl) {
+                             int cl_override, DiagPlan* pl) {
   const int n_l = n_c + n_ctd, W = 2 * N - 1, c = (int)sizeof(cplx);
   if (N < 2 || N > 0x7fff) return false;
   DiagOps& o = pl->ops;
@@ -566,6 +644,7 @@ static inline bool diag_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, int n
     const int off = q - (N - 1);
     f.goff[o.nD] = off;
     if (off == 0) {
+      if (!flags[(long long)(1 + n_l) * W + q]) continue;     // static main diagonal only: folded into the own weight
       o.g0_tab = o.nD * N * c;
     } else {
       o.go_tab[o.nGo] = o.nD * N * c;
@@ -576,10 +655,10 @@ static inline bool diag_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, int n
     o.nD++;
     maxoff = abs(off) > maxoff ? abs(off) : maxoff;
   }
-  if (o.nD == 0) { f.goff[0] = 0; o.g0_tab = 0; o.nD = 1; }   // G == 0: keep one (zero) diagonal
+  if (o.nD == 0) { f.goff[0] = 0; o.nD = 1; }   // nothing but a static main diagonal: keep one (unused) table
   f.nD = o.nD;
   int nT = 0;
-  o.nLo = o.nLg = 0;
+  o.nLs = o.nLo = o.nLg = 0;
   for (int l = 0; l < n_l; l++) {
     const int first = nT;
     for (int q = 0; q < W; q++) {
@@ -594,8 +673,9 @@ static inline bool diag_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, int n
     for (int a = first; a < nT; a++)
       for (int b2 = first; b2 < nT; b2++) {
         if (f.t_off[a] == 0 && f.t_off[b2] == 0) {
-          if (o.nLo >= DIAG_MAX_LT) return false;
-          o.lo_a[o.nLo] = a * N * c; o.lo_b[o.nLo] = b2 * N * c; o.lo_r[o.nLo] = rate; o.nLo++;
+          if (o.nLo >= DIAG_MAX_LT || o.nLs >= DIAG_MAX_LT) return false;
+          if (rate < 0) { o.ls_a[o.nLs] = a * N * c; o.ls_b[o.nLs] = b2 * N * c; o.nLs++; }
+          else { o.lo_a[o.nLo] = a * N * c; o.lo_b[o.nLo] = b2 * N * c; o.lo_r[o.nLo] = rate; o.nLo++; }
         } else {
           if (o.nLg >= DIAG_MAX_LT) return false;
           o.lg_a[o.nLg] = a * N * c; o.lg_b[o.nLg] = b2 * N * c; o.lg_r[o.nLg] = rate;
@@ -607,35 +687,23 @@ static inline bool diag_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, int n
   o.nT = nT; f.nT = nT;
   o.nnzE = nnzE;
   pl->maxoff = maxoff;
-  pl->macs = 2LL * o.nD + o.nLo + o.nLg;
+  pl->macs = 2LL * o.nD + o.nLs + o.nLo + o.nLg;
   o.n_el = N * (N + 1) / 2;
-  // launch shape: registers hold k1..k6 for up to 4 elements per thread; beyond that the stage vectors
-  // stream through a thread-private L2 buffer
-  pl->ept = 0;
-  const int kreg_epts[4] = {1, 2, 3, 4};
-  for (int q = 0; q < 4 && !pl->ept; q++) {
-    const int e = kreg_epts[q];
-    if (ept_override > 0 && e != ept_override) continue;
-    const long long th = (((long long)o.n_el + e - 1) / e + 31) / 32 * 32;
-    const int cap = (e == 1) ? 128 : DIAG_MAXT(e, true);
-    if (th <= cap || (ept_override > 0 && th <= DIAG_MAXT(e, true))) { pl->ept = e; pl->threads = (int)th; pl->kreg = true; }
-  }
-  if (!pl->ept) {
-    const int st_epts[3] = {8, 6, 4};
-    for (int q = 0; q < 3 && !pl->ept; q++) {
-      const int e = st_epts[q];
-      if (ept_override > 0 && e != ept_override) continue;
-      const long long th = (((long long)o.n_el + e - 1) / e + 31) / 32 * 32;
-      if (th <= DIAG_MAXT(e, false)) { pl->ept = e; pl->threads = (int)th; pl->kreg = false; }
-    }
-  }
-  if (!pl->ept) return false;
+  // launch shape: one quarter-warp per row of the band; N <= 48 one CTA, N <= 94 a cluster of two CTAs
+  const int Lb = N / 2 + 1;
+  pl->ept = (Lb + 7) / 8;
+  pl->cl = (8 * N <= DIAG_MAXT) ? 1 : 2;
+  pl->threads = (8 * ((N + pl->cl - 1) / pl->cl) + 31) / 32 * 32;
+  if (pl->ept > DIAG_MAX_EPT || pl->threads > DIAG_MAXT) return false;
+  if (cl_override == 2 && pl->cl == 1 && N >= 16) { pl->cl = 2; pl->threads = (8 * ((N + 1) / 2) + 31) / 32 * 32; }
+  pl->kreg = true;
   // shared memory, in order of value: Y (guard bands + double buffering, then clamped addresses, then a single
   // buffer), then the G diagonals, the spline tables and the expectation operators as far as they fit
   const int guard_el = maxoff * o.ld + maxoff + 1;
   const int tries[3][2] = {{2, 1}, {2, 0}, {1, 0}};
   bool ok = false;
   for (int q = 0; q < 3 && !ok; q++) {
+    if (tries[q][1] && pl->cl > 1) continue;        // clusters always clamp (one kernel variant)
     o.ybufs = tries[q][0];
     pl->guard = tries[q][1] != 0;
     o.guard = pl->guard ? guard_el : 0;
@@ -653,49 +721,65 @@ static inline bool diag_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, int n
   return true;
 }
 
-static inline size_t diag_ws_elems(const DiagPlan& pl) { return pl.kreg ? 0 : (size_t)6 * pl.ept * pl.threads; }
+static inline size_t diag_ws_elems(const DiagPlan&) { return 0; }
 
-struct DiagPack { size_t o_g0, o_gk, o_lam, o_flag, bytes; };
+struct DiagPack { size_t o_g0, o_gk, o_lam, o_gdiag, o_flag, bytes; };
 static inline DiagPack diag_pack_layout(int N, int n_g, const DiagPlan& pl) {
   auto up = [](size_t x) { return (x + 15) / 16 * 16; };
   DiagPack k;
   size_t o = 0;
-  // g0 and gk contiguous: the kernel stages them with one layout
   k.o_g0 = o; o += (size_t)pl.ops.nD * N * sizeof(cplx);
   k.o_gk = o; o += up((size_t)(n_g > 0 ? n_g : 1) * pl.ops.nD * N * sizeof(cplx));
   k.o_lam = o; o += up((size_t)(pl.ops.nT > 0 ? pl.ops.nT : 1) * N * sizeof(cplx));
+  k.o_gdiag = o; o += up((size_t)N * sizeof(cplx));
   k.o_flag = o; o += 16;
   k.bytes = o + 64;
   return k;
 }
 
-template <int EPT, bool KREG>
-static int launch_diag_t(const SolveParams& p, const DiagOps& sp, const DiagPlan& pl, bool lreal, cudaStream_t st) {
-#define DIAG_LAUNCH(G, R)                                                                                                         \
-  do {                                                                                                                            \
-    if (cudaFuncSetAttribute(solve_diag_kernel<EPT, KREG, G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) \
-      return SEQ_ERR_CUDA;                                                                                                        \
-    solve_diag_kernel<EPT, KREG, G, R><<<p.B, pl.threads, pl.smem, st>>>(p, sp);                                                  \
-  } while (0)
-  if (pl.guard) { if (lreal) DIAG_LAUNCH(true, true); else DIAG_LAUNCH(true, false); }
-  else { if (lreal) DIAG_LAUNCH(false, true); else DIAG_LAUNCH(false, false); }
-#undef DIAG_LAUNCH
-  return SEQ_OK;
+template <int EPT, int CL, bool GUARD>
+static int launch_diag_t(const SolveParams& p, const DiagOps& sp, const DiagPlan& pl, cudaStream_t st) {
+  auto kern = solve_diag_kernel<EPT, CL, GUARD>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) return SEQ_ERR_CUDA;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)p.B * CL, 1, 1);
+  cfg.blockDim = dim3((unsigned)pl.threads, 1, 1);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p, sp) == cudaSuccess ? SEQ_OK : SEQ_ERR_CUDA;
 }
 
-static inline int launch_diag_kernel(const SolveParams& p, const DiagOps& sp, const DiagPlan& pl, bool lreal, cudaStream_t st) {
-  if (pl.kreg) {
-    switch (pl.ept) {
-      case 1: return launch_diag_t<1, true>(p, sp, pl, lreal, st);
-      case 2: return launch_diag_t<2, true>(p, sp, pl, lreal, st);
-      case 3: return launch_diag_t<3, true>(p, sp, pl, lreal, st);
-      case 4: return launch_diag_t<4, true>(p, sp, pl, lreal, st);
+static inline int launch_diag_kernel(const SolveParams& p, const DiagOps& sp, const DiagPlan& pl, cudaStream_t st) {
+  if (pl.cl == 1) {
+    if (pl.guard) {
+      switch (pl.ept) {
+        case 1: return launch_diag_t<1, 1, true>(p, sp, pl, st);
+        case 2: return launch_diag_t<2, 1, true>(p, sp, pl, st);
+        case 3: return launch_diag_t<3, 1, true>(p, sp, pl, st);
+        case 4: return launch_diag_t<4, 1, true>(p, sp, pl, st);
+      }
+    } else {
+      switch (pl.ept) {
+        case 1: return launch_diag_t<1, 1, false>(p, sp, pl, st);
+        case 2: return launch_diag_t<2, 1, false>(p, sp, pl, st);
+        case 3: return launch_diag_t<3, 1, false>(p, sp, pl, st);
+        case 4: return launch_diag_t<4, 1, false>(p, sp, pl, st);
+      }
     }
   } else {
     switch (pl.ept) {
-      case 4: return launch_diag_t<4, false>(p, sp, pl, lreal, st);
-      case 6: return launch_diag_t<6, false>(p, sp, pl, lreal, st);
-      case 8: return launch_diag_t<8, false>(p, sp, pl, lreal, st);
+      case 1: return launch_diag_t<1, 2, false>(p, sp, pl, st);
+      case 2: return launch_diag_t<2, 2, false>(p, sp, pl, st);
+      case 3: return launch_diag_t<3, 2, false>(p, sp, pl, st);
+      case 4: return launch_diag_t<4, 2, false>(p, sp, pl, st);
+      case 5: return launch_diag_t<5, 2, false>(p, sp, pl, st);
+      case 6: return launch_diag_t<6, 2, false>(p, sp, pl, st);
     }
   }
   return SEQ_ERR_UNSUPPORTED;

@@ -691,20 +691,23 @@ static int launch_sparse(seq_engine* e, const seq_solve_desc* d, SolveParams& p,
 // Diagonal structure of the operators (device flags -> host plan).  One D2H copy + synchronisation.
 static int diag_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, const cplx* Gk, const cplx* Lall, int nnzE, DiagPlan* pl, bool* usable) {
   const int N = d->N, n_g = d->n_ch + d->n_ctd, n_l = d->n_c + d->n_ctd;
-  const size_t W = 2 * (size_t)N - 1, nflag = (size_t)(1 + n_l) * W;
+  const size_t W = 2 * (size_t)N - 1, nflag = (size_t)(2 + n_l) * W;
   *usable = false;
   int rc = reserve(e, e->dflags, nflag * sizeof(int) + 64);
   if (rc) return rc;
   int* flags = (int*)e->dflags.ptr;
   CUDA_TRY(e, cudaMemsetAsync(flags, 0, nflag * sizeof(int), e->stream));
-  dim3 grid((unsigned)grid_for((long long)N * N, e->sm_count), 1 + n_l);
+  dim3 grid((unsigned)grid_for((long long)N * N, e->sm_count), 2 + n_l);
   diag_flags_kernel<<<grid, 256, 0, e->stream>>>(G0, Gk, n_g, Lall, N, flags);
   e->launches++;
   std::vector<int> h(nflag);
   CUDA_TRY(e, cudaMemcpyAsync(h.data(), flags, nflag * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-  const char* env = getenv("SEQ_DIAG_EPT");
-  *usable = diag_plan(N, n_g, d->n_c, d->n_ctd, d->n_ch, d->n_t, nnzE, h.data(), e->max_smem_optin, env ? atoi(env) : 0, pl);
+  const char* env = getenv("SEQ_DIAG_CL");
+  const char* cap = getenv("SEQ_DIAG_SMEM_CAP");
+  int max_smem = e->max_smem_optin;
+  if (cap && atoi(cap) > 0 && atoi(cap) < max_smem) max_smem = atoi(cap);
+  *usable = diag_plan(N, n_g, d->n_c, d->n_ctd, d->n_ch, d->n_t, nnzE, h.data(), max_smem, env ? atoi(env) : 0, pl);
   return SEQ_OK;
 }
 
@@ -723,8 +726,9 @@ static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, c
   char* base = (char*)e->pack.ptr;
   char* dbase = base + pk.bytes / 16 * 16;
   DiagOps& sp = pl.ops;
-  sp.ij = (unsigned*)(base + pk.o_ij); sp.e_off = (int*)(base + pk.o_eoff); sp.e_ij = (unsigned*)(base + pk.o_eij); sp.e_val = (cplx*)(base + pk.o_eval);
+  sp.e_off = (int*)(base + pk.o_eoff); sp.e_ij = (unsigned*)(base + pk.o_eij); sp.e_val = (cplx*)(base + pk.o_eval);
   sp.g0 = (cplx*)(dbase + dk.o_g0); sp.gk = (cplx*)(dbase + dk.o_gk); sp.lam = (cplx*)(dbase + dk.o_lam);
+  sp.gdiag = (cplx*)(dbase + dk.o_gdiag);
   int* any_imag = (int*)(dbase + dk.o_flag);
   const int n_ops = 1 + n_l + n_e;
   int* rowoff = info.rowcnt + (size_t)n_ops * N + 2 * (size_t)n_ops;
@@ -736,18 +740,18 @@ static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, c
                                                (unsigned*)sp.e_ij, (cplx*)sp.e_val, 1 + n_l);
     e->launches++;
   }
-  sparse_ij_kernel<<<(N * N + 255) / 256, 256, 0, e->stream>>>((unsigned*)sp.ij, N);
   CUDA_TRY(e, cudaMemsetAsync(any_imag, 0, sizeof(int), e->stream));
   dim3 gf((N + 127) / 128, pl.fill.nD + pl.fill.nT);
-  diag_fill_kernel<<<gf, 128, 0, e->stream>>>(pl.fill, G0, Gk, n_g, p.L, N, (cplx*)sp.g0, (cplx*)sp.gk, (cplx*)sp.lam, any_imag);
-  e->launches += 2;
+  diag_fill_kernel<<<gf, 128, 0, e->stream>>>(pl.fill, G0, Gk, n_g, p.L, N, (cplx*)sp.g0, (cplx*)sp.gk, (cplx*)sp.lam, (cplx*)sp.gdiag, any_imag);
+  e->launches++;
   int h_imag = 0;
   CUDA_TRY(e, cudaMemcpyAsync(&h_imag, any_imag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   p.ws = (cplx*)e->ws.ptr;
   p.ws_stride = (long long)diag_ws_elems(pl);
   CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
-  rc = launch_diag_kernel(p, sp, pl, h_imag == 0, e->stream);
+  sp.lreal = h_imag == 0 ? 1 : 0;
+  rc = launch_diag_kernel(p, sp, pl, e->stream);
   if (rc) return fail(e, rc, "diagonal kernel launch configuration failed for N=%d", N);
   e->launches++;
   return SEQ_OK;
