@@ -176,6 +176,9 @@ int seq_engine_select_method(const seq_engine* eng, const seq_solve_desc* desc);
 /* Method the last seq_engine_solve on this handle actually ran (SEQ_METHOD_*): AUTO looks at the
  * operators' sparsity on the device, which seq_engine_select_method (shape only) cannot. */
 int seq_engine_last_method(const seq_engine* eng);
+/* One-line description of the kernel variant the last solve ran (launch shape of the diagonal kernel,
+ * "large/diagonals" vs "large/zgemm", ...); empty when the method has a single variant. */
+const char* seq_engine_last_variant(const seq_engine* eng);
 
 /* Number of kernel launches issued by the last seq_engine_solve on this handle, and the
  * duration in milliseconds of its integration kernel measured with CUDA events on the

@@ -20,6 +20,7 @@
 #include "kernel_large.cuh"
 #include "kernel_sparse.cuh"
 #include "kernel_diag.cuh"
+#include "kernel_large_diag.cuh"
 
 using namespace seq;
 
@@ -42,6 +43,7 @@ struct seq_engine {
   bool timed = false;
   int launches = 0;
   int last_method = 0;
+  std::string variant;              // human-readable detail of what the last solve ran
   int sm_count = 0;
   int max_smem_optin = 0;
 };
@@ -359,6 +361,8 @@ int seq_engine_last_launch_count(const seq_engine* e) { return e ? e->launches :
 
 int seq_engine_last_method(const seq_engine* e) { return e ? e->last_method : 0; }
 
+const char* seq_engine_last_variant(const seq_engine* e) { return e ? e->variant.c_str() : ""; }
+
 float seq_engine_last_kernel_ms(seq_engine* e) {
   if (!e || !e->timed) return -1.0f;
   if (cudaEventSynchronize(e->ev1) != cudaSuccess) return -1.0f;
@@ -432,15 +436,52 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
   cudaStream_t st = e->stream;
   const int sms = e->sm_count;
 
-  size_t total = (size_t)(1 + n_g + n_l + 1) * opsz + ysz + (world > 1 ? lsz : 0) + (size_t)(2 + 7 + 1) * lsz + 64 + 2 + 2 * (size_t)(n_e + 1);
-  int rc = reserve(e, e->large, total * sizeof(double) + 256);
+  // ---- operator structure: sums of a few diagonals -> one structured RHS kernel instead of the ZGEMM chain
+  bool structured = false;
+  LargeDiagArgs la;
+  DiagFill dfill;
+  memset(&la, 0, sizeof(la));
+  int rc;
+  if (!getenv("SEQ_LARGE_DENSE")) {
+    const size_t W = 2 * (size_t)N - 1, nflag = (size_t)(2 + n_l) * W;
+    rc = reserve(e, e->dflags, nflag * sizeof(int) + 64);
+    if (rc) return rc;
+    int* flags = (int*)e->dflags.ptr;
+    CUDA_TRY(e, cudaMemsetAsync(flags, 0, nflag * sizeof(int), st));
+    dim3 fg((unsigned)grid_for((long long)N * N, sms), 2 + n_l);
+    diag_flags_kernel<<<fg, 256, 0, st>>>(G0, Gk, n_g, p.L, N, flags);
+    e->launches++;
+    std::vector<int> hflags(nflag);
+    CUDA_TRY(e, cudaMemcpyAsync(hflags.data(), flags, nflag * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(e, cudaStreamSynchronize(st));
+    structured = large_diag_terms(N, p.n_c, p.n_ctd, p.n_ch, hflags.data(), &la, &dfill);
+  }
+  e->variant = structured ? "large/diagonals" : "large/zgemm";
+  cplx *dg0 = nullptr, *dgk = nullptr, *dlam = nullptr, *dgdiag = nullptr, *dgt = nullptr;
+  if (structured) {
+    const size_t nDN = (size_t)dfill.nD * N, nTN = (size_t)(dfill.nT > 0 ? dfill.nT : 1) * N;
+    rc = reserve(e, e->pack, ((2 + (size_t)(n_g > 0 ? n_g : 1)) * nDN + nTN + N) * sizeof(cplx) + 256);
+    if (rc) return rc;
+    dg0 = (cplx*)e->pack.ptr; dgk = dg0 + nDN; dlam = dgk + (size_t)(n_g > 0 ? n_g : 1) * nDN; dgdiag = dlam + nTN; dgt = dgdiag + N;
+    rc = reserve(e, e->spinfo, 64);
+    if (rc) return rc;
+    dim3 gf((N + 127) / 128, dfill.nD + dfill.nT);
+    diag_fill_kernel<<<gf, 128, 0, st>>>(dfill, G0, Gk, n_g, p.L, N, dg0, dgk, dlam, dgdiag, (int*)e->spinfo.ptr);
+    e->launches++;
+  }
+
+  size_t total = (size_t)(structured ? 0 : (1 + n_g + n_l + 1)) * opsz + ysz + (world > 1 ? lsz : 0) + (size_t)(2 + 7 + 1) * lsz + 64 + 2 + 2 * (size_t)(n_e + 1);
+  rc = reserve(e, e->large, total * sizeof(double) + 256);
   if (rc) return rc;
   if (!e->host_err) CUDA_TRY(e, cudaMallocHost((void**)&e->host_err, 2 * sizeof(double)));
   double* base = (double*)e->large.ptr;
-  double* G0p = base; base += opsz;
-  double* Gkp = base; base += (size_t)n_g * opsz;
-  double* Lp = base; base += (size_t)n_l * opsz;
-  double* Gt = base; base += opsz;
+  double *G0p = nullptr, *Gkp = nullptr, *Lp = nullptr, *Gt = nullptr;
+  if (!structured) {
+    G0p = base; base += opsz;
+    Gkp = base; base += (size_t)n_g * opsz;
+    Lp = base; base += (size_t)n_l * opsz;
+    Gt = base; base += opsz;
+  }
   double* Yfull = base; base += ysz;
   double* Ysend = nullptr;
   if (world > 1) { Ysend = base; base += lsz; }
@@ -454,10 +495,12 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
   cplx* eacc = (cplx*)base;
 
   // operators -> planar padded
+  if (!structured) {
   large_pack_kernel<<<grid_for(oplane, sms), 256, 0, st>>>(G0, G0p, N, NP, NP);
   e->launches++;
   for (int g = 0; g < n_g; g++) { large_pack_kernel<<<grid_for(oplane, sms), 256, 0, st>>>(Gk + (size_t)g * N * N, Gkp + (size_t)g * opsz, N, NP, NP); e->launches++; }
   for (int l = 0; l < n_l; l++) { large_pack_kernel<<<grid_for(oplane, sms), 256, 0, st>>>(p.L + (size_t)l * N * N, Lp + (size_t)l * opsz, N, NP, NP); e->launches++; }
+  }
 
   // chunk schedules: per operator (0: union pattern of G0 and every Gk; 1..: L_l) one list for its use as
   // the A operand (48-row tiles of this rank's rows) and one for its use as the B^H operand (96-row tiles)
@@ -474,7 +517,7 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
   auto idxB = [&](int op) { return idxA(op) + (size_t)tilesA * kchunks; };
   auto prefA = [&](int op) { return s_int + (size_t)op * int_per_op + (tilesA + tilesB); };
   auto prefB = [&](int op) { return prefA(op) + tilesA + 1; };
-  for (int op = 0; op < nops; op++) {
+  for (int op = 0; op < (structured ? 0 : nops); op++) {
     const double* src = (op == 0) ? G0p : Lp + (size_t)(op - 1) * opsz;
     const int nsrc = (op == 0) ? 1 + n_g : 1;     // G0p and Gkp are contiguous
     int* cntA = s_int + (size_t)op * int_per_op;
@@ -502,6 +545,16 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
 
     auto rhs = [&](double t, double* kout) -> int {
       if (n_g > 0) { large_coeff_kernel<<<1, 64, 0, st>>>(p, b, t, cval); e->launches++; }
+      if (structured) {
+        const int nDN = dfill.nD * N;
+        large_diag_gt_kernel<<<(nDN + 255) / 256, 256, 0, st>>>(dg0, dgk, cval, n_g, nDN, dgt);
+        LargeDiagArgs a = la;
+        a.N = N; a.NP = NP; a.m = m; a.Mrows = Mrows; a.row0 = row0; a.y_plane = yplane; a.k_plane = mplane;
+        a.Y = Yfull; a.K = kout; a.gt = dgt; a.lam = dlam; a.gdiag = dgdiag; a.cval = cval;
+        large_diag_rhs_kernel<<<grid_for(mplane, sms), 256, 0, st>>>(a);
+        e->launches += 2;
+        return SEQ_OK;
+      }
       large_build_G_kernel<<<grid_for(opsz, sms), 256, 0, st>>>(G0p, Gkp, cval, n_g, opsz, Gt);
       e->launches++;
       CUDA_TRY(e, cudaMemsetAsync(kout, 0, lsz * sizeof(double), st));
@@ -751,6 +804,12 @@ static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, c
   p.ws_stride = (long long)diag_ws_elems(pl);
   CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
   sp.lreal = h_imag == 0 ? 1 : 0;
+  {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "diag: %d CTA%s x %d threads per trajectory, %d elements/thread, %d Y buffer%s%s, smem %zu B", pl.cl, pl.cl > 1 ? "s (cluster)" : "",
+             pl.threads, pl.ept, sp.ybufs, sp.ybufs > 1 ? "s" : "", pl.guard ? " + guard bands" : "", pl.smem);
+    e->variant = buf;
+  }
   rc = launch_diag_kernel(p, sp, pl, e->stream);
   if (rc) return fail(e, rc, "diagonal kernel launch configuration failed for N=%d", N);
   e->launches++;
@@ -857,6 +916,7 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
     }
   }
   e->last_method = method;
+  e->variant.clear();
 
   const size_t ws_per = ws_elems_per_traj(d, method);
   rc = reserve(e, e->ws, ws_per * (size_t)B * sizeof(cplx) + 256);

@@ -61,6 +61,7 @@ class BatchOutput:
     kernel_ms: float = -1.0
     launches: int = 0
     method: str = "auto"
+    variant: str = ""
 
 
 def _c128(a, shape_tail):
@@ -277,6 +278,7 @@ class Engine:
             expect=out["expect"], final_state=out["final_state"], states=out.get("states"),
             status=out["status"], stats=out["stats"], kernel_ms=self.last_kernel_ms,
             launches=self.last_launches, method=_lib.METHOD_NAMES.get(getattr(self, "_last_method", 0), "?"),
+            variant=(self.lib.seq_engine_last_variant(self.handle) or b"").decode(),
         )
 
     def kernel_ms(self) -> float:

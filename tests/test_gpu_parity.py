@@ -452,3 +452,32 @@ def test_auto_method_follows_operator_structure(gpu_engine):
         bp = random_problem(N=40, B=1, n_t=3, n_ch=1, n_c=1, n_e=1, seed=1)
         bp.method = _lib.METHOD_DIAG
         gpu_engine.solve(bp)
+
+
+def test_large_path_structured_rhs_matches_generic_and_zgemm(gpu_engine):
+    """SEQ_METHOD_LARGE with diagonal-structured operators runs ONE structured RHS kernel instead of the ZGEMM chain
+    (variant "large/diagonals"): against the FP64-FMA kernel and against the dense ZGEMM variant of the same path
+    (forced with SEQ_LARGE_DENSE=1), with constant and time-dependent collapse terms and uncapped steps."""
+    import os
+    for N, n_c, n_ctd, w_l, max_step in ((97, 2, 0, 1, 1.0), (130, 1, 1, 2, 1.0), (200, 2, 0, 1, 0.0)):
+        def mk():
+            bp = row_sparse_problem(N=N, B=2, n_t=5, w_h=5, w_l=w_l, n_ch=2, n_c=n_c, n_ctd=n_ctd, n_e=2, seed=N, hscale=0.5, store_states=True)
+            bp.max_step = max_step
+            return bp
+        a, g, z = mk(), mk(), mk()
+        a.method, g.method, z.method = _lib.METHOD_LARGE, _lib.METHOD_GENERIC, _lib.METHOD_LARGE
+        oa, og = gpu_engine.solve(a), gpu_engine.solve(g)
+        os.environ["SEQ_LARGE_DENSE"] = "1"
+        try:
+            oz = gpu_engine.solve(z)
+        finally:
+            del os.environ["SEQ_LARGE_DENSE"]
+        assert oa.method == "large" and oa.variant == "large/diagonals" and oz.variant == "large/zgemm"
+        assert np.all(oa.status == 0)
+        for other in (og, oz):
+            assert np.max(np.abs(oa.states - other.states)) < 1e-12, N
+            assert np.max(np.abs(oa.expect - other.expect)) < 1e-12, N
+            np.testing.assert_array_equal(oa.stats[:, :2], other.stats[:, :2])
+    auto = row_sparse_problem(N=120, B=1, n_t=3, w_h=3, w_l=1, n_ch=1, n_c=1, n_e=1, seed=2)
+    out = gpu_engine.solve(auto)
+    assert out.method in ("large", "sparse")       # too large for the one-CTA kernels' register budget or ELL streams
