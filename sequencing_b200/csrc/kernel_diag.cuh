@@ -183,11 +183,13 @@ __device__ __noinline__ void diag_controller(const SolveParams& p, DiagCtlState*
                                              const double2* tabc, const double2* tabr, const double* cscale,
                                              int update, int nrhs, double es) {
   const int lane = threadIdx.x & 31, n_g = p.n_g;
+  PROF_DECL
   StepCtl ctl = S->ctl;
   double c_htry = S->htry, c_target = S->target;
   int c_o = S->o, c_nst = S->nst;
   bool c_landing = S->landing != 0, c_capped = S->capped != 0;
   __syncwarp();
+  PROF(8);
   bool accepted = false;
   if (update) {
     ctl.nrhs += nrhs;
@@ -198,6 +200,7 @@ __device__ __noinline__ void diag_controller(const SolveParams& p, DiagCtlState*
 #endif
     accepted = ctl_update(ctl, p, err, c_htry, c_landing, c_capped, c_target, c_nst);
   }
+  PROF(9);
   const int emit_lo = c_o;
   int cmd = 1;
   while (ctl.status == SEQ_STATUS_OK && c_o < p.n_out) {
@@ -206,10 +209,11 @@ __device__ __noinline__ void diag_controller(const SolveParams& p, DiagCtlState*
     c_o++;           // output c_o is reached by the committed state
     c_nst = 0;
   }
+  PROF(10);
   const int emit_hi = (ctl.status == SEQ_STATUS_OK) ? c_o : emit_lo;
   const int pair = ctl.pair;
   if (cmd == 0) {
-    for (int q = lane; q < 7 * n_g; q += 32) {
+    for (int q = lane; q < RK_STAGES[pair] * n_g; q += 32) {
       const int st = q / n_g, m = q - st * n_g;
       const double ts = ctl.t + RK_C[pair][st] * c_htry;
       double v;
@@ -222,6 +226,7 @@ __device__ __noinline__ void diag_controller(const SolveParams& p, DiagCtlState*
       cv[q] = v;
     }
   }
+  PROF(11);
   if (lane == 0) {
     ctrl->htry = c_htry;
     ctrl->cmd = cmd;
@@ -235,16 +240,28 @@ __device__ __noinline__ void diag_controller(const SolveParams& p, DiagCtlState*
     S->o = c_o; S->nst = c_nst; S->landing = c_landing ? 1 : 0; S->capped = c_capped ? 1 : 0;
   }
   __syncwarp();
+  PROF(12);
 }
 
 // threads per CTA by (elements per thread, stage vectors in registers): 65536 registers / threads, allocated per 4 warps
+// Inner loops over a thread's elements run in chunks of at most 3 with a compiler barrier in between: the loads
+// of all EPT elements of one term would otherwise be hoisted together (EPT = 6: 72 registers of operands in
+// flight on top of the 130 of persistent state -> spills to local memory that miss the small L1)
+#define DIAG_CHUNK 3
+#define DIAG_FOR_CHUNKED(e)                                                                         \
+  _Pragma("unroll") for (int e##0 = 0; e##0 < EPT; e##0 += DIAG_CHUNK)                              \
+    _Pragma("unroll") for (int e = (diag_chunk_fence(e##0), e##0); e < (e##0 + DIAG_CHUNK < EPT ? e##0 + DIAG_CHUNK : EPT); e++)
+__device__ __forceinline__ void diag_chunk_fence(int e0) { if (e0 > 0) asm volatile("" ::: "memory"); }
+
 #define DIAG_MAX_EPT 6
 #define DIAG_MAXT 384       // 168 registers per thread
 
 namespace cg = cooperative_groups;
 
-template <int EPT, int CL, bool GUARD>
-__global__ void __launch_bounds__(DIAG_MAXT, 1)
+#define DIAG_MAXT_STREAM 736   // stage vectors streamed through L2: 80 registers per thread
+
+template <int EPT, int CL, bool GUARD, bool KREG>
+__global__ void __launch_bounds__(KREG ? DIAG_MAXT : DIAG_MAXT_STREAM, 1)
 solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__ DiagOps sp) {
   extern __shared__ __align__(16) unsigned char smem_diag[];
   constexpr int C = (int)sizeof(cplx);
@@ -297,8 +314,13 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
   // offset of entry j_e of a table).  Laundered through an empty asm so that they stay in registers as computed.
   int oy[EPT], oi, rowb;
   unsigned vmask = 0, dmask = 0;      // valid elements; elements on the main diagonal
-  cplx y[EPT], ys[EPT], kout[EPT], W[EPT];
-  cplx k[6][EPT];
+  // KREG: y, the static weights W and the stage derivatives k1..k6 live in registers (EPT <= 4); otherwise they are
+  // thread-private coalesced streams in global memory (L2-resident), slots 0..5: k, 6: y, 7: W
+  cplx ys[EPT], kout[EPT];
+  cplx y[KREG ? EPT : 1], W[KREG ? EPT : 1];
+  cplx k[KREG ? 6 : 1][KREG ? EPT : 1];
+  cplx* kst = KREG ? nullptr : p.ws + (long long)blockIdx.x * p.ws_stride;
+  auto st_at = [&](int slot, int e) -> cplx& { return kst[((long long)slot * EPT + e) * nth + tid]; };
   {
     const int i_raw = (tid >> 3) * CL + rank, q8 = tid & 7;
     const bool rowok = i_raw < N;
@@ -317,11 +339,16 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       if (v) vmask |= 1u << e;
       if (v && d == 0) dmask |= 1u << e;
       oy[e] = (i * ld + j) * C;
-      y[e] = v ? y0[i * N + j] : cmake(0, 0);
-      ys[e] = y[e];
+      ys[e] = v ? y0[i * N + j] : cmake(0, 0);
       kout[e] = cmake(0, 0);
+      if (KREG) {
+        y[KREG ? e : 0] = ys[e];
 #pragma unroll
-      for (int q = 0; q < 6; q++) k[q][e] = cmake(0, 0);
+        for (int q = 0; q < 6; q++) k[KREG ? q : 0][KREG ? e : 0] = cmake(0, 0);
+      } else {
+        st_at(6, e) = ys[e];
+        for (int q = 0; q < 6; q++) st_at(q, e) = cmake(0, 0);
+      }
       // static own-element weight: -i (G0_ii - conj(G0_jj)) + sum over constant-rate pairs lam_a[i] conj(lam_b[j])
       const cplx gj = sp.gdiag[j];
       cplx w = cmake(gi.y + gj.y, -(gi.x - gj.x));
@@ -330,7 +357,7 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
         w.x += a.x * c.x + a.y * c.y;
         w.y += a.y * c.x - a.x * c.y;
       }
-      W[e] = w;
+      if (KREG) W[KREG ? e : 0] = w; else st_at(7, e) = w;
       asm volatile("" : "+r"(oy[e]));
     }
     asm volatile("" : "+r"(oi), "+r"(rowb));
@@ -373,12 +400,11 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
   // kout = W ys - i (G' Y - Y G'^dag) + collapse terms, G' = G minus its static main diagonal
   auto compute_K = [&](const unsigned char* __restrict__ Yb, const unsigned char* __restrict__ Gb, int st) {
 #pragma unroll
-    for (int e = 0; e < EPT; e++) kout[e] = cmul(W[e], ys[e]);
+    for (int e = 0; e < EPT; e++) kout[e] = cmul(KREG ? W[KREG ? e : 0] : st_at(7, e), ys[e]);
     if (sp.g0_tab >= 0) {      // time-dependent main diagonal
       const unsigned char* gv = Gb + sp.g0_tab;
       const cplx vi = *(const cplx*)(gv + oi);
-#pragma unroll
-      for (int e = 0; e < EPT; e++) {
+      DIAG_FOR_CHUNKED(e) {
         const cplx vj = *(const cplx*)(gv - rowb + oy[e]);
         const cplx dd = cmake(vi.y + vj.y, -(vi.x - vj.x));   // -i (v_0[i] - conj(v_0[j]))
         cfma(kout[e], dd, ys[e]);
@@ -391,8 +417,7 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       const cplx vi = *(const cplx*)(gv + oi);
       const cplx mvi = cmake(vi.y, -vi.x);            // -i v_d[i]
       const unsigned char* gvj = gv - rowb;
-#pragma unroll
-      for (int e = 0; e < EPT; e++) {
+      DIAG_FOR_CHUNKED(e) {
         const cplx ya = *(const cplx*)(Yb + yaddr(oy[e] + offL));
         cfma(kout[e], mvi, ya);
         const cplx vj = *(const cplx*)(gvj + oy[e]);
@@ -410,8 +435,7 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       const unsigned char* lbj = lam + sp.lo_b[t] - rowb;
       const double r = cv[st * n_g + sp.lo_r[t]];
       const cplx a = seq::cscale(r, *(const cplx*)(la + oi));
-#pragma unroll
-      for (int e = 0; e < EPT; e++) {
+      DIAG_FOR_CHUNKED(e) {
         const cplx c = *(const cplx*)(lbj + oy[e]);
         const double wx = a.x * c.x + a.y * c.y, wy = a.y * c.x - a.x * c.y;
         kout[e].x = fma(wx, ys[e].x, kout[e].x); kout[e].x = fma(-wy, ys[e].y, kout[e].x);
@@ -428,8 +452,7 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       const double r = ri < 0 ? 1.0 : cv[st * n_g + ri];
       if (lreal) {
         const double ra = r * (*(const double*)(la + oi));
-#pragma unroll
-        for (int e = 0; e < EPT; e++) {
+        DIAG_FOR_CHUNKED(e) {
           const cplx yv = *(const cplx*)(Yb + yaddr(oy[e] + off));
           const double w = ra * (*(const double*)(lbj + oy[e]));
           kout[e].x = fma(w, yv.x, kout[e].x);
@@ -437,8 +460,7 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
         }
       } else {
         const cplx a = seq::cscale(r, *(const cplx*)(la + oi));
-#pragma unroll
-        for (int e = 0; e < EPT; e++) {
+        DIAG_FOR_CHUNKED(e) {
           const cplx yv = *(const cplx*)(Yb + yaddr(oy[e] + off));
           const cplx c = *(const cplx*)(lbj + oy[e]);
           const double wx = a.x * c.x + a.y * c.y, wy = a.y * c.x - a.x * c.y;
@@ -484,7 +506,7 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
   }
   __syncwarp();
 
-  write_Y(L.off_Y, y);
+  write_Y(L.off_Y, ys);
   if (warp == 0) diag_controller(p, cst, ctrl, cv, tabc, tabr, cscale, 0, 0, 0.0);
   sync_all();
 
@@ -504,11 +526,13 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
         for (int j = 0; j < 6; j++) {
           const double aj = rk_a_c(PAIR, st, j);
           if (j < st && aj != 0.0) {
-            ax = fma(aj, k[j][e].x, ax);
-            ay = fma(aj, k[j][e].y, ay);
+            const cplx kv = KREG ? k[KREG ? j : 0][KREG ? e : 0] : st_at(j, e);
+            ax = fma(aj, kv.x, ax);
+            ay = fma(aj, kv.y, ay);
           }
         }
-        ys[e] = (st == 0) ? y[e] : cmake(fma(htry, ax, y[e].x), fma(htry, ay, y[e].y));
+        const cplx yv = KREG ? y[KREG ? e : 0] : st_at(6, e);
+        ys[e] = (st == 0) ? yv : cmake(fma(htry, ax, yv.x), fma(htry, ay, yv.y));
       }
       if (sp.ybufs == 2) yb ^= 1;
       gb ^= 1;
@@ -526,7 +550,7 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       }
       if (st < S - 1) {
 #pragma unroll
-        for (int e = 0; e < EPT; e++) k[st][e] = kout[e];
+        for (int e = 0; e < EPT; e++) { if (KREG) k[KREG ? st : 0][KREG ? e : 0] = kout[e]; else st_at(st, e) = kout[e]; }
       }
       PROF(3);
     }
@@ -539,12 +563,14 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       for (int j = 0; j < S - 1; j++) {
         const double cj = rk_e_c(PAIR, j);
         if (cj != 0.0) {
-          ex = fma(cj, k[j][e].x, ex);
-          ey = fma(cj, k[j][e].y, ey);
+          const cplx kv = KREG ? k[KREG ? j : 0][KREG ? e : 0] : st_at(j, e);
+          ex = fma(cj, kv.x, ex);
+          ey = fma(cj, kv.y, ey);
         }
       }
       ex *= htry; ey *= htry;
-      const double sc = p.atol + p.rtol * sqrt(fmax(cabs2(y[e]), cabs2(ys[e])));
+      const cplx yo = KREG ? y[KREG ? e : 0] : st_at(6, e);
+      const double sc = p.atol + p.rtol * sqrt(fmax(cabs2(yo), cabs2(ys[e])));
       const double wgt = (vmask & (1u << e)) ? ((dmask & (1u << e)) ? 1.0 : 2.0) : 0.0;
       es += wgt * (ex * ex + ey * ey) / (sc * sc);
     }
@@ -556,8 +582,8 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
     if (c.accepted) {
 #pragma unroll
       for (int e = 0; e < EPT; e++) {
-        y[e] = ys[e];
-        k[0][e] = kout[e];
+        if (KREG) { y[KREG ? e : 0] = ys[e]; k[0][KREG ? e : 0] = kout[e]; }
+        else { st_at(6, e) = ys[e]; st_at(0, e) = kout[e]; }
       }
       ycur = yb;
     }
@@ -598,8 +624,9 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
   for (int e = 0; e < EPT; e++) {
     if (vmask & (1u << e)) {
       const int i = oi / C, j = (oy[e] - rowb) / C;
-      fin[i * N + j] = y[e];
-      if (i != j) fin[j * N + i] = cconj(y[e]);
+      const cplx yf = KREG ? y[KREG ? e : 0] : st_at(6, e);
+      fin[i * N + j] = yf;
+      if (i != j) fin[j * N + i] = cconj(yf);
     }
   }
   if (tid == 0 && rank == 0) {
@@ -619,7 +646,7 @@ struct DiagPlan {
   DiagOps ops;          // offsets / term lists filled in; pointers set at launch
   DiagFill fill;
   int maxoff;
-  int ept, cl, threads;
+  int ept, cl, lpr, threads;
   bool kreg, guard;
   size_t smem;
   long long macs;       // complex multiply-adds per element (cost model)
@@ -691,19 +718,30 @@ static inline bool diag_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, int n
   o.n_el = N * (N + 1) / 2;
   // launch shape: one quarter-warp per row of the band; N <= 48 one CTA, N <= 94 a cluster of two CTAs
   const int Lb = N / 2 + 1;
+  pl->lpr = 8;
   pl->ept = (Lb + 7) / 8;
-  pl->cl = (8 * N <= DIAG_MAXT) ? 1 : 2;
-  pl->threads = (8 * ((N + pl->cl - 1) / pl->cl) + 31) / 32 * 32;
-  if (pl->ept > DIAG_MAX_EPT || pl->threads > DIAG_MAXT) return false;
-  if (cl_override == 2 && pl->cl == 1 && N >= 16) { pl->cl = 2; pl->threads = (8 * ((N + 1) / 2) + 31) / 32 * 32; }
-  pl->kreg = true;
+  if (pl->ept > DIAG_MAX_EPT) return false;
+  if (8 * N <= DIAG_MAXT) {                // N <= 48: one CTA, everything in registers
+    pl->cl = 1; pl->kreg = true;
+    pl->threads = (8 * N + 31) / 32 * 32;
+    if (cl_override == 2 && N >= 16) { pl->cl = 2; pl->threads = (8 * ((N + 1) / 2) + 31) / 32 * 32; }
+  } else if (8 * N <= DIAG_MAXT_STREAM && cl_override != 2) {   // N <= 92: one CTA, stage vectors streamed through L2
+    pl->cl = 1; pl->kreg = false;
+    pl->threads = (8 * N + 31) / 32 * 32;
+  } else {                                 // (override) a cluster of two CTAs with register-resident stage vectors
+    pl->cl = 2; pl->kreg = true;
+    pl->threads = (8 * ((N + 1) / 2) + 31) / 32 * 32;
+    if (pl->threads > DIAG_MAXT) return false;
+  }
+  // (16 lanes per row - twice the warps at 80 registers - was measured slower on C2: 9.7k vs 13.0k trajectories/s;
+  // the kernel is bound by shared-memory bandwidth, not by latency)
   // shared memory, in order of value: Y (guard bands + double buffering, then clamped addresses, then a single
   // buffer), then the G diagonals, the spline tables and the expectation operators as far as they fit
   const int guard_el = maxoff * o.ld + maxoff + 1;
   const int tries[3][2] = {{2, 1}, {2, 0}, {1, 0}};
   bool ok = false;
   for (int q = 0; q < 3 && !ok; q++) {
-    if (tries[q][1] && pl->cl > 1) continue;        // clusters always clamp (one kernel variant)
+    if (tries[q][1] && (pl->cl > 1 || !pl->kreg)) continue;   // clusters and streamed variants always clamp
     o.ybufs = tries[q][0];
     pl->guard = tries[q][1] != 0;
     o.guard = pl->guard ? guard_el : 0;
@@ -721,7 +759,7 @@ static inline bool diag_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, int n
   return true;
 }
 
-static inline size_t diag_ws_elems(const DiagPlan&) { return 0; }
+static inline size_t diag_ws_elems(const DiagPlan& pl) { return pl.kreg ? 0 : (size_t)8 * pl.ept * pl.threads; }
 
 struct DiagPack { size_t o_g0, o_gk, o_lam, o_gdiag, o_flag, bytes; };
 static inline DiagPack diag_pack_layout(int N, int n_g, const DiagPlan& pl) {
@@ -737,9 +775,9 @@ static inline DiagPack diag_pack_layout(int N, int n_g, const DiagPlan& pl) {
   return k;
 }
 
-template <int EPT, int CL, bool GUARD>
+template <int EPT, int CL, bool GUARD, bool KREG>
 static int launch_diag_t(const SolveParams& p, const DiagOps& sp, const DiagPlan& pl, cudaStream_t st) {
-  auto kern = solve_diag_kernel<EPT, CL, GUARD>;
+  auto kern = solve_diag_kernel<EPT, CL, GUARD, KREG>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) return SEQ_ERR_CUDA;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -756,30 +794,36 @@ static int launch_diag_t(const SolveParams& p, const DiagOps& sp, const DiagPlan
 }
 
 static inline int launch_diag_kernel(const SolveParams& p, const DiagOps& sp, const DiagPlan& pl, cudaStream_t st) {
-  if (pl.cl == 1) {
+  if (!pl.kreg) {
+    switch (pl.ept) {
+      case 4: return launch_diag_t<4, 1, false, false>(p, sp, pl, st);
+      case 5: return launch_diag_t<5, 1, false, false>(p, sp, pl, st);
+      case 6: return launch_diag_t<6, 1, false, false>(p, sp, pl, st);
+    }
+  } else if (pl.cl == 1) {
     if (pl.guard) {
       switch (pl.ept) {
-        case 1: return launch_diag_t<1, 1, true>(p, sp, pl, st);
-        case 2: return launch_diag_t<2, 1, true>(p, sp, pl, st);
-        case 3: return launch_diag_t<3, 1, true>(p, sp, pl, st);
-        case 4: return launch_diag_t<4, 1, true>(p, sp, pl, st);
+        case 1: return launch_diag_t<1, 1, true, true>(p, sp, pl, st);
+        case 2: return launch_diag_t<2, 1, true, true>(p, sp, pl, st);
+        case 3: return launch_diag_t<3, 1, true, true>(p, sp, pl, st);
+        case 4: return launch_diag_t<4, 1, true, true>(p, sp, pl, st);
       }
     } else {
       switch (pl.ept) {
-        case 1: return launch_diag_t<1, 1, false>(p, sp, pl, st);
-        case 2: return launch_diag_t<2, 1, false>(p, sp, pl, st);
-        case 3: return launch_diag_t<3, 1, false>(p, sp, pl, st);
-        case 4: return launch_diag_t<4, 1, false>(p, sp, pl, st);
+        case 1: return launch_diag_t<1, 1, false, true>(p, sp, pl, st);
+        case 2: return launch_diag_t<2, 1, false, true>(p, sp, pl, st);
+        case 3: return launch_diag_t<3, 1, false, true>(p, sp, pl, st);
+        case 4: return launch_diag_t<4, 1, false, true>(p, sp, pl, st);
       }
     }
   } else {
     switch (pl.ept) {
-      case 1: return launch_diag_t<1, 2, false>(p, sp, pl, st);
-      case 2: return launch_diag_t<2, 2, false>(p, sp, pl, st);
-      case 3: return launch_diag_t<3, 2, false>(p, sp, pl, st);
-      case 4: return launch_diag_t<4, 2, false>(p, sp, pl, st);
-      case 5: return launch_diag_t<5, 2, false>(p, sp, pl, st);
-      case 6: return launch_diag_t<6, 2, false>(p, sp, pl, st);
+      case 1: return launch_diag_t<1, 2, false, true>(p, sp, pl, st);
+      case 2: return launch_diag_t<2, 2, false, true>(p, sp, pl, st);
+      case 3: return launch_diag_t<3, 2, false, true>(p, sp, pl, st);
+      case 4: return launch_diag_t<4, 2, false, true>(p, sp, pl, st);
+      case 5: return launch_diag_t<5, 2, false, true>(p, sp, pl, st);
+      case 6: return launch_diag_t<6, 2, false, true>(p, sp, pl, st);
     }
   }
   return SEQ_ERR_UNSUPPORTED;

@@ -806,8 +806,8 @@ static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, c
   sp.lreal = h_imag == 0 ? 1 : 0;
   {
     char buf[160];
-    snprintf(buf, sizeof(buf), "diag: %d CTA%s x %d threads per trajectory, %d elements/thread, %d Y buffer%s%s, smem %zu B", pl.cl, pl.cl > 1 ? "s (cluster)" : "",
-             pl.threads, pl.ept, sp.ybufs, sp.ybufs > 1 ? "s" : "", pl.guard ? " + guard bands" : "", pl.smem);
+    snprintf(buf, sizeof(buf), "diag: %d CTA%s x %d threads per trajectory, %d elements/thread, stage vectors in %s, %d Y buffer%s%s, smem %zu B", pl.cl, pl.cl > 1 ? "s (cluster)" : "",
+             pl.threads, pl.ept, pl.kreg ? "registers" : "L2 streams", sp.ybufs, sp.ybufs > 1 ? "s" : "", pl.guard ? " + guard bands" : "", pl.smem);
     e->variant = buf;
   }
   rc = launch_diag_kernel(p, sp, pl, e->stream);

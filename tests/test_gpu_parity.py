@@ -481,3 +481,18 @@ def test_large_path_structured_rhs_matches_generic_and_zgemm(gpu_engine):
     auto = row_sparse_problem(N=120, B=1, n_t=3, w_h=3, w_l=1, n_ch=1, n_c=1, n_e=1, seed=2)
     out = gpu_engine.solve(auto)
     assert out.method in ("large", "sparse")       # too large for the one-CTA kernels' register budget or ELL streams
+
+
+def test_diag_kernel_two_cta_cluster_variant(gpu_engine):
+    """The diagonal kernel's cluster variant (SEQ_DIAG_CL=2: one trajectory on two CTAs, the stage matrix written into
+    both CTAs' shared memory through DSMEM stores, cluster barriers per RHS) against the FP64-FMA kernel, with one and
+    two Y buffers and an odd / even number of rows per CTA."""
+    import os
+    os.environ["SEQ_DIAG_CL"] = "2"
+    try:
+        for N, w_h, w_l, n_c, n_ctd in ((17, 3, 1, 2, 0), (45, 3, 1, 4, 0), (64, 3, 1, 2, 1), (90, 5, 1, 3, 0)):
+            mk = lambda: row_sparse_problem(N=N, B=3, n_t=8, w_h=w_h, w_l=w_l, n_ch=2, n_c=n_c, n_ctd=n_ctd, n_e=2, seed=N, hscale=0.3, store_states=True)
+            _match_generic(gpu_engine, mk, _lib.METHOD_DIAG, "diag")
+            assert "2 CTAs (cluster)" in gpu_engine.solve(mk()).variant or N > 94
+    finally:
+        del os.environ["SEQ_DIAG_CL"]

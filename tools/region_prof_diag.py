@@ -33,10 +33,11 @@ eng.lib.seq_engine_debug_regions(buf, 0)
 cyc = np.array(list(buf), dtype=float)
 rhs, steps = float(out.stats[0, 2]), float(out.stats[0, 0] + out.stats[0, 1])
 names = {0: "commit + outputs (Tr(E rho), stores)", 1: "stage combine + Y write + G(t) build", 2: "RHS barrier", 3: "RHS terms (compute_K) + k store",
-         4: "error estimate", 5: "error block sum (barrier)", 6: "controller (warp 0: step control, spline values)", 7: "step barrier"}
+         4: "error estimate", 5: "error block sum (barrier)", 6: "controller (warp 0: step control, spline values) - call overhead", 7: "step barrier",
+         8: "  controller: state load", 9: "  controller: ctl_update (pow)", 10: "  controller: output bookkeeping + ctl_next", 11: "  controller: spline values", 12: "  controller: state store"}
 tot = cyc.sum()
 d = out.stats[:, 3]
 print("steps with err <= 2.9e-6:", float((d & 0xffff).mean()), " err <= 2.9e-7:", float((d >> 16).mean()), "of", steps)
 print(f"{which}: method {out.method} kernel_ms {out.kernel_ms:.2f}  steps {steps:.0f} RHS {rhs:.0f}  cycles/step {tot / steps:.0f}  cycles/RHS {tot / rhs:.0f}")
-for r in range(8):
+for r in range(13):
     print(f"  {cyc[r] / steps:8.0f} cyc/step  {cyc[r] / rhs:8.0f} cyc/RHS  {cyc[r] / tot * 100:5.1f}%  {names[r]}")
