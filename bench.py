@@ -408,7 +408,8 @@ def ours(args):
         k_ms = float(np.mean(kernel_ms))
         achieved = flops / (k_ms * 1e-3) / 1e12
         s = shape_of(bp)
-        kname = "zgemm_dmma_kernel" if out_h.method == "large" else f"solve_{out_h.method}_kernel"
+        structured_large = out_h.method == "large" and out_h.variant == "large/diagonals"
+        kname = ("large_diag_rhs_kernel" if structured_large else "zgemm_dmma_kernel") if out_h.method == "large" else f"solve_{out_h.method}_kernel"
         peak_scale = world if rows_mode else 1     # rows mode: the algorithmic flops of the ONE system are spread over all GPUs
         if out_h.method == "small":
             # N <= 6: below one DMMA tile -> the HBM roofline, FP64-FMA ceiling noted
@@ -433,7 +434,14 @@ def ours(args):
                 roof["tile_sparsity"] = sp
                 roof["executed_dmma_TFLOPs"] = achieved * sp["executed_over_algorithmic_flops"]
                 roof["executed_dmma_frac_of_peak"] = roof["executed_dmma_TFLOPs"] / FP64_DMMA_PEAK_TFLOPS
-            sw = structured_work(bp, out_h.method)
+            sw = structured_work(bp, "diag" if structured_large else out_h.method)
+            if structured_large:
+                # the structured RHS of the large path is HBM-bound: 16 N^2 bytes of state read + 16 N^2 written per RHS
+                peak_h, src_h = hbm_peak()
+                gb = 32.0 * s["N"] ** 2 * float(np.sum(stats[:, 2])) / (k_ms * 1e-3) / 1e9
+                roof["hbm"] = {"bound": "hbm", "achieved": gb, "peak": peak_h * peak_scale, "unit": "GB/s", "frac": gb / (peak_h * peak_scale),
+                               "bytes_per_rhs": 32.0 * s["N"] ** 2, "peak_source": src_h,
+                               "note": "whole stepper time (RHS + stage combinations + error norm + outputs) against the RHS kernel's compulsory bytes"}
             if sw:
                 ex = sw["executed_flops_per_rhs"] * float(np.sum(stats[:, 2])) / (k_ms * 1e-3) / 1e12
                 roof["structured"] = sw
@@ -481,7 +489,7 @@ def ours(args):
             "dtype": "c128 (f64)", "data": "synthetic",
             "config": {"workload": desc, **s, "B_per_gpu": bp.B, "atol": bp.atol, "rtol": bp.rtol, "max_step": bp.max_step,
                        "parallelism": (f"rho row-sharded x{world}, all-gather of the stage state per RHS" if rows_mode else f"batch-sharded x{world}"), "l2": "256 MiB L2 flush between timed steps; per-step scratch 300 MB > L2",
-                       "method": out_h.method, "steps_accepted_mean": float(stats[:, 0].mean()), "steps_rejected_mean": float(stats[:, 1].mean())},
+                       "method": out_h.method, "variant": out_h.variant, "steps_accepted_mean": float(stats[:, 0].mean()), "steps_rejected_mean": float(stats[:, 1].mean())},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "roofline": roof,

@@ -106,7 +106,7 @@ def solve_sharded(bp: BatchProblem, engine=None, group=None, gather: bool = True
     return BatchOutput(
         expect=g(out.expect), final_state=g(out.final_state),
         states=g(out.states) if out.states is not None else None,
-        status=g(out.status), stats=g(out.stats), kernel_ms=out.kernel_ms, launches=out.launches, method=out.method,
+        status=g(out.status), stats=g(out.stats), kernel_ms=out.kernel_ms, launches=out.launches, method=out.method, variant=getattr(out, "variant", ""),
     )
 
 

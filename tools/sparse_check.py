@@ -71,3 +71,11 @@ if "time" in which:
         out = eng.solve(bp)
         print(f"[time c4] B={bp.B} method={out.method}: kernel {out.kernel_ms:.1f} ms -> {bp.B / out.kernel_ms * 1e3:.0f} traj/s (steps {out.stats[:, 0].mean():.0f}, rhs {out.stats[:, 2].mean():.0f})", flush=True)
 print("SPARSE_CHECK", "FAILED" if bad else "OK", bad)
+if "fast" in which:
+    # C2-shaped systems of several sizes (FAST variant of the diagonal kernel: rank-1 drive diagonals) vs the generic kernel
+    for lv in (4, 7, 10, 15, 16):
+        mk = lambda: w.c2_selective(2, 2, sigma=10, cavity_levels=lv)
+        bp = mk()
+        out = eng.solve(bp)
+        print("[fast] levels", lv, "N", bp.N, "->", out.method, "|", out.variant)
+        cmp(f"c2 levels={lv}", mk, methods=(DG,))
