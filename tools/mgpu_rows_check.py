@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from helpers import random_problem  # noqa: E402
+from helpers import random_problem, row_sparse_problem  # noqa: E402
 from sequencing_b200.distributed import solve_rows_sharded  # noqa: E402
 from sequencing_b200.solver import Engine, _lib  # noqa: E402
 
@@ -27,8 +27,12 @@ def main():
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 150
     n_t = int(sys.argv[2]) if len(sys.argv) > 2 else 5
     ok = True
-    for n_c, n_ctd in ((2, 1), (0, 0)):
-        mk = lambda: random_problem(N=N, B=1, n_t=n_t, n_ch=2, n_c=n_c, n_ctd=n_ctd, n_e=2, seed=N + n_c, hscale=0.3, store_states=True)
+    # dense operators -> ZGEMM chain; diagonal-structured operators -> the structured RHS kernel on every rank's row block
+    for n_c, n_ctd, structured in ((2, 1, False), (0, 0, False), (2, 1, True)):
+        if structured:
+            mk = lambda: row_sparse_problem(N=N, B=1, n_t=n_t, w_h=5, w_l=2, n_ch=2, n_c=n_c, n_ctd=n_ctd, n_e=2, seed=N + n_c, hscale=0.5, store_states=True)
+        else:
+            mk = lambda: random_problem(N=N, B=1, n_t=n_t, n_ch=2, n_c=n_c, n_ctd=n_ctd, n_e=2, seed=N + n_c, hscale=0.3, store_states=True)
         eng = Engine.get(local)
         single = mk()
         single.method = _lib.METHOD_LARGE
@@ -37,8 +41,9 @@ def main():
         d_states = float(np.max(np.abs(out.states - ref.states)))
         d_exp = float(np.max(np.abs(out.expect - ref.expect)))
         same_steps = bool(np.array_equal(out.stats[:, :2], ref.stats[:, :2]))
-        good = bool(np.all(out.status == 0)) and d_states < 1e-12 and d_exp < 1e-12 and same_steps and out.method == "large"
-        print(f"[rank {rank}/{world}] N={N} n_c={n_c} n_ctd={n_ctd}: states {d_states:.2e} expect {d_exp:.2e} steps_equal={same_steps} "
+        good = (bool(np.all(out.status == 0)) and d_states < 1e-12 and d_exp < 1e-12 and same_steps and out.method == "large"
+                and ref.variant == ("large/diagonals" if structured else "large/zgemm"))
+        print(f"[rank {rank}/{world}] N={N} n_c={n_c} n_ctd={n_ctd} {ref.variant}: states {d_states:.2e} expect {d_exp:.2e} steps_equal={same_steps} "
               f"collectives={getattr(out, 'comm_stats', None)} ok={good}", flush=True)
         ok = ok and good
     flag = torch.tensor([1 if ok else 0], device="cuda")
