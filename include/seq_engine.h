@@ -190,6 +190,29 @@ float seq_engine_last_kernel_ms(seq_engine* eng);
  * grid (device pointers).  Replaces qutip's _prep_cubic_spline (QobjEvo array coefficients). */
 int seq_engine_spline_prep(seq_engine* eng, const double* y, double* M, int64_t n_series, int32_t n_t, double dt);
 
+/*
+ * On-device waveform synthesis: the coefficient tables of a sweep are generated on
+ * the GPU from per-trajectory pulse parameters instead of being built sample by sample in Python and copied over.
+ * One descriptor = one chopped Gaussian(-DRAG) pulse of one trajectory:
+ *     c(t_k) = amp (I_k + i Q_k) exp(-2 pi i detune tau_k) exp(i phase),          k = 0 .. n-1, n = int(chop sigma / dt)
+ *     I_k = (g_k - g_0) / (1 - g_0),  g_k = exp(-t_k^2 / 2 sigma^2),  t_k = linspace(-chop sigma / 2, chop sigma / 2, n)[k]
+ *     Q_k = drag t_k g_k / (4 sigma^2 (1 - g_0)),                      tau_k = linspace(0, n dt, n)[k]
+ * and sign_re Re c / sign_im Im c are ADDED to coeff[traj, ch_re / ch_im, start + k] (channel -1: skipped).
+ * Replaces: pulses.py:31-117 (array_pulse, gaussian_wave, gaussian_deriv_wave), pulses.py:262-293
+ * (Pulse.__call__) and the quadrature split of modes.py:719-753 (Qubit.rotate: x <- Re, y <- Im) and
+ * modes.py:864-897 (Cavity.displace: x <- -Im, y <- Re) for sweeps over amp / drag / detune / phase.
+ * `descs` is a HOST array; `coeff` a DEVICE buffer f64 [B, n_ch, n_t] which the call zeroes first unless
+ * `accumulate` is non-zero.
+ */
+typedef struct seq_pulse_desc {
+  int32_t traj, ch_re, ch_im, start;
+  double sign_re, sign_im;
+  double sigma, chop, dt;
+  double amp, drag, detune, phase;
+} seq_pulse_desc;
+int seq_engine_synth_gaussian(seq_engine* eng, const seq_pulse_desc* descs, int64_t n_desc, double* coeff, int32_t B,
+                              int32_t n_ch, int32_t n_t, int accumulate);
+
 /* states[b] <- U states[b] U^dag (density matrices) or U states[b] (kets); U is c128 [N,N]
  * shared by the batch (device pointers).  Replaces main.py:316-322. */
 int seq_engine_apply_unitary(seq_engine* eng, const void* U, void* states, int32_t N, int32_t B, int is_ket);

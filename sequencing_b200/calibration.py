@@ -18,7 +18,7 @@ import numpy as np
 from scipy.optimize import curve_fit
 
 from .sequencing import get_sequence, ket2dm, ops2dms, sync, tqdm
-from .solver import deferred_solves
+from .solver import deferred_solves, synth
 
 
 class _Fit:
@@ -120,19 +120,34 @@ def _setup(system, init_state, e_ops, mode_name, pulse_name):
 
 
 def tune_rabi(system, init_state, e_ops=None, mode_name="qubit", pulse_name=None, amp_range=(-2, 2, 51),
-              progbar=True, plot=True, ax=None, ylabel=None, update=True, verify=True):
-    """Amplitude-Rabi calibration of a qubit pulse; returns ``((fig, ax), old_amp, new_amp)``."""
+              progbar=True, plot=True, ax=None, ylabel=None, update=True, verify=True, device_synthesis=False):
+    """Amplitude-Rabi calibration of a qubit pulse; returns ``((fig, ax), old_amp, new_amp)``.
+
+    ``device_synthesis=True`` (an addition to the reference's signature): ONE template sequence is lowered and the
+    coefficient tables of all sweep points are generated on the GPU (``solver/synth.py``)
+    instead of compiling one sequence per point in Python."""
     init_state, qubit, pulse_name, pulse, e_ops = _setup(system, init_state, e_ops, mode_name, pulse_name)
     amps = np.linspace(*amp_range)
     prog = tqdm if progbar else (lambda x, **kw: x)
-    results = []
-    with deferred_solves():
-        for amp in prog(amps):
-            seq = get_sequence(system)
-            with qubit.pulse_scale(amp, pulse_name=pulse_name):
+    if device_synthesis and synth.supported(pulse):
+        def template():
+            with deferred_solves(execute=False) as d:
+                seq = get_sequence(system)
                 qubit.rotate_x(np.pi, pulse_name=pulse_name)
-            results.append(seq.run(init_state, e_ops=e_ops, only_final_state=False))
-    e_pop = [r.expect[0][-1] for r in results]
+                seq.run(init_state, e_ops=e_ops, only_final_state=False)
+            return d
+        out = synth.qubit_rotation_sweep(system, qubit, pulse_name, [[(np.pi, 0.0, amp, pulse.drag)] for amp in amps],
+                                         init_state, e_ops, template)
+        e_pop = [float(v) for v in np.real(out.expect[:, 0, -1])]
+    else:
+        results = []
+        with deferred_solves():
+            for amp in prog(amps):
+                seq = get_sequence(system)
+                with qubit.pulse_scale(amp, pulse_name=pulse_name):
+                    qubit.rotate_x(np.pi, pulse_name=pulse_name)
+                results.append(seq.run(init_state, e_ops=e_ops, only_final_state=False))
+        e_pop = [r.expect[0][-1] for r in results]
 
     fit = fit_sine(amps, e_pop)
     old_amp = pulse.amp
@@ -152,7 +167,8 @@ def tune_rabi(system, init_state, e_ops=None, mode_name="qubit", pulse_name=None
         print(f"Updating {qubit.name} unit amp from {old_amp:.2e} to {new_amp:.2e}.", flush=True)
     if verify:
         tune_rabi(system, init_state, e_ops=e_ops, mode_name=mode_name, pulse_name=pulse_name,
-                  amp_range=amp_range, progbar=progbar, plot=plot, ax=ax, update=False, verify=False)
+                  amp_range=amp_range, progbar=progbar, plot=plot, ax=ax, update=False, verify=False,
+                  device_synthesis=device_synthesis)
     return (fig, ax), old_amp, new_amp
 
 
@@ -219,30 +235,47 @@ def tune_repeated_pio2_pulses(system, init_state, e_ops=None, mode_name="qubit",
 
 
 def tune_drag(system, init_state, e_ops=None, mode_name="qubit", pulse_name=None, drag_range=(-5, 5, 21),
-              progbar=True, plot=True, ax=None, ylabel=None, update=True):
+              progbar=True, plot=True, ax=None, ylabel=None, update=True, device_synthesis=False):
     """DRAG calibration: ``Rx(pi);Ry(pi/2)`` vs ``Ry(pi);Rx(pi/2)`` over a DRAG sweep; the crossing
-    of the two fitted lines is the optimum.  Returns ``((fig, ax), old_drag, new_drag)``."""
+    of the two fitted lines is the optimum.  Returns ``((fig, ax), old_drag, new_drag)``.
+    ``device_synthesis``: see ``tune_rabi``."""
     init_state, qubit, pulse_name, pulse, e_ops = _setup(system, init_state, e_ops, mode_name, pulse_name)
     old_drag = pulse.drag
     drags = np.linspace(*drag_range)
     prog = tqdm if progbar else (lambda x, **kw: x)
-    res_xy, res_yx = [], []
-    with deferred_solves():
-        for drag in prog(drags):
-            pulse.drag = drag
-            seq = get_sequence(system)
-            qubit.rotate_x(np.pi, pulse_name=pulse_name)
-            sync()
-            qubit.rotate_y(np.pi / 2, pulse_name=pulse_name)
-            res_xy.append(seq.run(init_state, e_ops=e_ops, only_final_state=False))
+    if device_synthesis and synth.supported(pulse):
+        def template():
+            with deferred_solves(execute=False) as d:
+                seq = get_sequence(system)
+                qubit.rotate_x(np.pi, pulse_name=pulse_name)
+                sync()
+                qubit.rotate_y(np.pi / 2, pulse_name=pulse_name)
+                seq.run(init_state, e_ops=e_ops, only_final_state=False)
+            return d
+        hp = np.pi / 2
+        trajs = [[(np.pi, 0.0, 1.0, drag), (hp, hp, 1.0, drag)] for drag in drags] + \
+                [[(np.pi, hp, 1.0, drag), (hp, 0.0, 1.0, drag)] for drag in drags]
+        out = synth.qubit_rotation_sweep(system, qubit, pulse_name, trajs, init_state, e_ops, template)
+        pops = np.real(out.expect[:, 0, -1])
+        XpY9, YpX9 = [float(v) for v in pops[:len(drags)]], [float(v) for v in pops[len(drags):]]
+    else:
+        res_xy, res_yx = [], []
+        with deferred_solves():
+            for drag in prog(drags):
+                pulse.drag = drag
+                seq = get_sequence(system)
+                qubit.rotate_x(np.pi, pulse_name=pulse_name)
+                sync()
+                qubit.rotate_y(np.pi / 2, pulse_name=pulse_name)
+                res_xy.append(seq.run(init_state, e_ops=e_ops, only_final_state=False))
 
-            seq = get_sequence(system)
-            qubit.rotate_y(np.pi, pulse_name=pulse_name)
-            sync()
-            qubit.rotate_x(np.pi / 2, pulse_name=pulse_name)
-            res_yx.append(seq.run(init_state, e_ops=e_ops, only_final_state=False))
-    XpY9 = [r.expect[0][-1] for r in res_xy]
-    YpX9 = [r.expect[0][-1] for r in res_yx]
+                seq = get_sequence(system)
+                qubit.rotate_y(np.pi, pulse_name=pulse_name)
+                sync()
+                qubit.rotate_x(np.pi / 2, pulse_name=pulse_name)
+                res_yx.append(seq.run(init_state, e_ops=e_ops, only_final_state=False))
+        XpY9 = [r.expect[0][-1] for r in res_xy]
+        YpX9 = [r.expect[0][-1] for r in res_yx]
 
     r0, r1 = fit_line(drags, XpY9), fit_line(drags, YpX9)
     b0, b1 = r0.params["intercept"].value, r1.params["intercept"].value

@@ -186,6 +186,41 @@ __global__ void spline_unpack_kernel(const double2* __restrict__ packed, double*
   if (i < n) M[i] = packed[i].y * scale;
 }
 
+// One CTA per pulse descriptor: chopped Gaussian(-DRAG) waveform, modulated and added to the coefficient tables
+// (include/seq_engine.h: seq_engine_synth_gaussian).  linspace() is evaluated as numpy does (start + k step, last
+// sample exactly the stop value) so that the samples agree with pulses.py to the last bits of exp / sincos.
+__global__ void synth_gaussian_kernel(const seq_pulse_desc* __restrict__ descs, double* __restrict__ coeff, int B, int n_ch, int n_t) {
+  const seq_pulse_desc d = descs[blockIdx.x];
+  const double len = d.chop * d.sigma;
+  const int n = (int)(len / d.dt);
+  if (d.traj < 0 || d.traj >= B || n < 1) return;
+  const double t_lo = -len / 2, t_hi = len / 2;
+  const double t_step = n > 1 ? (t_hi - t_lo) / (double)(n - 1) : 0.0;
+  const double tau_hi = (double)n * d.dt, tau_step = n > 1 ? tau_hi / (double)(n - 1) : 0.0;
+  const double inv2s2 = 1.0 / (2.0 * d.sigma * d.sigma);
+  const double g0 = exp(-(t_lo * t_lo) * inv2s2);
+  const double cph = cos(d.phase), sph = sin(d.phase);
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const int col = d.start + k;
+    if (col < 0 || col >= n_t) continue;
+    const double t = (k == n - 1 && n > 1) ? t_hi : t_lo + (double)k * t_step;
+    const double g = exp(-(t * t) * inv2s2);
+    double wr = (g - g0) / (1.0 - g0);
+    double wi = d.drag * ((0.25 / (d.sigma * d.sigma)) * t * g / (1.0 - g0));
+    if (d.detune != 0.0) {
+      const double tau = (k == n - 1 && n > 1) ? tau_hi : (double)k * tau_step;
+      const double ang = -2.0 * 3.141592653589793238462643383279502884 * tau * d.detune;
+      const double c = cos(ang), s_ = sin(ang);
+      const double r = wr * c - wi * s_, i = wr * s_ + wi * c;
+      wr = r; wi = i;
+    }
+    wr *= d.amp; wi *= d.amp;
+    const double re = wr * cph - wi * sph, im = wr * sph + wi * cph;
+    if (d.ch_re >= 0 && d.ch_re < n_ch) atomicAdd(&coeff[((long long)d.traj * n_ch + d.ch_re) * n_t + col], d.sign_re * re);
+    if (d.ch_im >= 0 && d.ch_im < n_ch) atomicAdd(&coeff[((long long)d.traj * n_ch + d.ch_im) * n_t + col], d.sign_im * im);
+  }
+}
+
 // states[b] <- U states[b] U^dag  /  U psi_b   (one CTA per trajectory; scratch T in global)
 __global__ void apply_unitary_kernel(const cplx* __restrict__ U, cplx* __restrict__ states, cplx* __restrict__ scratch,
                                      int N, int is_ket) {
@@ -1100,6 +1135,28 @@ int seq_engine_debug_regions(unsigned long long* out16, int reset) {
   return SEQ_OK;
 }
 #endif
+
+int seq_engine_synth_gaussian(seq_engine* e, const seq_pulse_desc* descs, int64_t n_desc, double* coeff, int32_t B, int32_t n_ch,
+                              int32_t n_t, int accumulate) {
+  if (!e) return SEQ_ERR_INVALID;
+  if (n_desc < 0 || (n_desc > 0 && !descs) || !coeff || B < 0 || n_ch < 1 || n_t < 1) return fail(e, SEQ_ERR_INVALID, "bad synth_gaussian arguments");
+  for (int64_t q = 0; q < n_desc; q++)
+    if (!(descs[q].sigma > 0) || !(descs[q].dt > 0) || !(descs[q].chop > 0))
+      return fail(e, SEQ_ERR_INVALID, "pulse descriptor %lld: sigma, chop and dt must be positive", (long long)q);
+  e->launches = 0;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  const size_t bytes = (size_t)B * n_ch * n_t * sizeof(double);
+  if (!accumulate && bytes) CUDA_TRY(e, cudaMemsetAsync(coeff, 0, bytes, e->stream));
+  if (n_desc == 0 || B == 0) return SEQ_OK;
+  int rc = reserve(e, e->stage_in, (size_t)n_desc * sizeof(seq_pulse_desc) + 256);
+  if (rc) return rc;
+  CUDA_TRY(e, cudaMemcpyAsync(e->stage_in.ptr, descs, (size_t)n_desc * sizeof(seq_pulse_desc), cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));    // `descs` is caller memory (possibly pageable)
+  synth_gaussian_kernel<<<(unsigned)n_desc, 128, 0, e->stream>>>((const seq_pulse_desc*)e->stage_in.ptr, coeff, B, n_ch, n_t);
+  e->launches++;
+  CUDA_TRY(e, cudaGetLastError());
+  return SEQ_OK;
+}
 
 int seq_engine_apply_unitary(seq_engine* e, const void* U, void* states, int32_t N, int32_t B, int is_ket) {
   if (!e) return SEQ_ERR_INVALID;

@@ -23,7 +23,7 @@ EXPORTS = (
     "seq_engine_last_error", "seq_engine_workspace_bytes", "seq_engine_solve",
     "seq_engine_select_method", "seq_engine_last_launch_count", "seq_engine_last_kernel_ms",
     "seq_engine_spline_prep", "seq_engine_apply_unitary", "seq_engine_expect", "seq_engine_solve_sharded",
-    "seq_engine_last_method", "seq_engine_last_variant",
+    "seq_engine_last_method", "seq_engine_last_variant", "seq_engine_synth_gaussian",
 )
 
 
@@ -50,6 +50,15 @@ class SolveDesc(C.Structure):
         ("expect", C.c_void_p), ("final_state", C.c_void_p), ("states", C.c_void_p),
         ("status", C.c_void_p), ("stats", C.c_void_p),
     ]
+
+
+class PulseDesc(C.Structure):
+    """``struct seq_pulse_desc`` - one chopped Gaussian(-DRAG) pulse of one trajectory (on-device synthesis)."""
+
+    _fields_ = [("traj", C.c_int32), ("ch_re", C.c_int32), ("ch_im", C.c_int32), ("start", C.c_int32),
+                ("sign_re", C.c_double), ("sign_im", C.c_double),
+                ("sigma", C.c_double), ("chop", C.c_double), ("dt", C.c_double),
+                ("amp", C.c_double), ("drag", C.c_double), ("detune", C.c_double), ("phase", C.c_double)]
 
 
 ALL_GATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
@@ -100,6 +109,7 @@ def load():
     lib.seq_engine_last_kernel_ms.restype = C.c_float
     lib.seq_engine_spline_prep.argtypes = [vp, vp, vp, i64, i32, C.c_double]
     lib.seq_engine_apply_unitary.argtypes = [vp, vp, vp, i32, i32, C.c_int]
+    lib.seq_engine_synth_gaussian.argtypes = [vp, C.POINTER(PulseDesc), i64, vp, i32, i32, i32, C.c_int]
     lib.seq_engine_expect.argtypes = [vp, vp, vp, vp, i32, i32, i32, C.c_int]
     if lib.seq_engine_abi_version() != ABI_VERSION:
         raise EngineUnavailable("seq_engine ABI version mismatch")

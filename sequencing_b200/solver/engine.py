@@ -64,6 +64,16 @@ class BatchOutput:
     variant: str = ""
 
 
+def _with_batched_coeff(bp):
+    """A shallow copy of ``bp`` whose (host) coefficient array has the per-trajectory shape - only the shape is
+    used once the tables themselves come from a device tensor."""
+    import copy
+
+    out = copy.copy(bp)
+    out.coeff = np.broadcast_to(bp.coeff[:1], (bp.B,) + bp.coeff.shape[1:])
+    return out
+
+
 def _c128(a, shape_tail):
     a = np.ascontiguousarray(a, dtype=np.complex128)
     return a.reshape((-1,) + tuple(shape_tail)) if a.size else a.reshape((0,) + tuple(shape_tail))
@@ -202,9 +212,16 @@ class Engine:
         return shapes
 
     # -- solves ----------------------------------------------------------------------------
-    def solve(self, bp: BatchProblem) -> BatchOutput:
-        """Public host-buffer solve: numpy in, numpy out; H2D/D2H staging via pinned memory."""
-        dev = self.solve_device(self.to_device(bp), bp)
+    def solve(self, bp: BatchProblem, coeff_device=None) -> BatchOutput:
+        """Public host-buffer solve: numpy in, numpy out; H2D/D2H staging via pinned memory.
+        ``coeff_device``: a device tensor f64 [B, n_ch, n_t] (e.g. from ``synth_gaussian``) used instead of
+        ``bp.coeff`` - the tables then never exist on the host."""
+        tens = self.to_device(bp)
+        if coeff_device is not None:
+            assert tuple(coeff_device.shape) == (bp.B, bp.Hk.shape[0], bp.coeff.shape[-1]), coeff_device.shape
+            tens["coeff"] = coeff_device
+            bp = _with_batched_coeff(bp)
+        dev = self.solve_device(tens, bp)
         out = {k: v.cpu().numpy() for k, v in dev["out"].items()}
         return self._finish(bp, out)
 
@@ -283,6 +300,24 @@ class Engine:
 
     def kernel_ms(self) -> float:
         return float(self.lib.seq_engine_last_kernel_ms(self.handle))
+
+    # -- on-device waveform synthesis ------------------------------------
+    def synth_gaussian(self, descs, B: int, n_ch: int, n_t: int, out=None):
+        """Coefficient tables f64 [B, n_ch, n_t] generated on the device from pulse descriptors: ``descs`` is a
+        list of dicts / tuples with the fields of ``_lib.PulseDesc`` (traj, ch_re, ch_im, start, sign_re, sign_im,
+        sigma, chop, dt, amp, drag, detune, phase).  ``out``: accumulate into an existing device tensor."""
+        torch = self.torch
+        arr = (_lib.PulseDesc * max(len(descs), 1))()
+        names = [f[0] for f in _lib.PulseDesc._fields_]
+        for q, d in enumerate(descs):
+            vals = d if isinstance(d, dict) else dict(zip(names, d))
+            for k in names:
+                setattr(arr[q], k, vals[k])
+        with torch.cuda.device(self.device):
+            coeff = out if out is not None else torch.empty((B, n_ch, n_t), dtype=torch.float64, device=self.device)
+            self._check(self.lib.seq_engine_synth_gaussian(self.handle, arr, len(descs), coeff.data_ptr(), B, n_ch, n_t, 0 if out is None else 1))
+            self.total_launches += self.lib.seq_engine_last_launch_count(self.handle)
+        return coeff
 
     # -- auxiliary entry points --------------------------------------------------------------
     def spline_prep(self, y: np.ndarray, dt: float) -> np.ndarray:

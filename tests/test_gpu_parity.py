@@ -496,3 +496,52 @@ def test_diag_kernel_two_cta_cluster_variant(gpu_engine):
             assert "2 CTAs (cluster)" in gpu_engine.solve(mk()).variant or N > 94
     finally:
         del os.environ["SEQ_DIAG_CL"]
+
+
+def test_device_waveform_synthesis_matches_host_pulses(gpu_engine):
+    """seq_engine_synth_gaussian against the host waveform code (pulses.py: gaussian_wave,
+    gaussian_deriv_wave, array_pulse): amplitudes, DRAG, detuning, phase, several pulses per trajectory, offsets,
+    the cavity quadrature convention (x <- -Im, y <- Re) and accumulation into the same channel."""
+    from sequencing_b200.pulses import GaussianPulse
+    rng = np.random.default_rng(7)
+    B, n_ch, n_t = 6, 4, 140
+    descs, ref = [], np.zeros((B, n_ch, n_t))
+    for b in range(B):
+        for q in range(3):
+            sigma, chop, dt = [(10, 4, 1), (7, 6, 1), (12, 4, 1)][q]
+            amp, drag, phase = rng.uniform(-2, 2), rng.uniform(-3, 3), rng.uniform(-np.pi, np.pi)
+            detune = [0.0, 0.013, -0.004][(b + q) % 3]
+            p = GaussianPulse(name="g", sigma=sigma, chop=chop, drag=drag, detune=detune, dt=dt)
+            wave = p(amp=amp, phase=phase)
+            start = [0, 41, 85][q]
+            cavity = (b % 2 == 1)
+            ch_re, ch_im = (1, 0) if cavity else (2, 3)
+            s_re, s_im = (1.0, -1.0) if cavity else (1.0, 1.0)       # cavity: y <- Re (channel 1), x <- -Im (channel 0)
+            ref[b, ch_re, start:start + len(wave)] += s_re * wave.real
+            ref[b, ch_im, start:start + len(wave)] += s_im * wave.imag
+            descs.append(dict(traj=b, ch_re=ch_re, ch_im=ch_im, start=start, sign_re=s_re, sign_im=s_im, sigma=sigma, chop=chop,
+                              dt=dt, amp=amp, drag=drag, detune=detune, phase=phase))
+    got = gpu_engine.synth_gaussian(descs, B, n_ch, n_t).cpu().numpy()
+    assert np.max(np.abs(got - ref)) < 5e-15 * max(1.0, np.max(np.abs(ref)))
+    assert np.max(np.abs(ref)) > 0.5
+
+
+def test_calibration_sweeps_with_device_synthesis_match_host_path(gpu_engine):
+    """tune_rabi / tune_drag with device_synthesis=True (one template sequence + descriptors, tables generated on the
+    GPU) give the same populations-derived calibration values as the per-point host compilation."""
+    from sequencing_b200 import System, Transmon
+    from sequencing_b200.calibration import tune_drag, tune_rabi
+
+    def make():
+        q = Transmon("qubit", levels=3, kerr=-0.2, t1=20e3, t2=15e3)
+        return System("system", modes=[q]), q
+    vals = {}
+    for dev in (False, True):
+        system, q = make()
+        _, old, new = tune_rabi(system, q.fock(0), amp_range=(-2, 2, 21), progbar=False, plot=False, update=False, verify=False,
+                                device_synthesis=dev)
+        _, old_d, new_d = tune_drag(system, q.fock(0), e_ops=[q.fock(1)], drag_range=(-3, 3, 9), progbar=False, plot=False,
+                                    update=False, device_synthesis=dev)
+        vals[dev] = (new, new_d)
+    assert abs(vals[True][0] - vals[False][0]) < 1e-9 * abs(vals[False][0])
+    assert abs(vals[True][1] - vals[False][1]) < 1e-7 * max(1.0, abs(vals[False][1]))
