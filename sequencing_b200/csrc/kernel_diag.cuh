@@ -320,7 +320,12 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
   cplx y[KREG ? EPT : 1], W[KREG ? EPT : 1];
   cplx k[KREG ? 6 : 1][KREG ? EPT : 1];
   cplx* kst = KREG ? nullptr : p.ws + (long long)blockIdx.x * p.ws_stride;
-  auto st_at = [&](int slot, int e) -> cplx& { return kst[((long long)slot * EPT + e) * nth + tid]; };
+  // the static weights are the same for every trajectory: ONE table behind the per-trajectory streams, written by
+  // every CTA with identical values (keeps 1/8 of the stream footprint out of L2 / HBM)
+  cplx* wtab = KREG ? nullptr : p.ws + (long long)gridDim.x * p.ws_stride;
+  auto st_at = [&](int slot, int e) -> cplx& {
+    return slot == 7 ? wtab[(long long)e * nth + tid] : kst[((long long)slot * EPT + e) * nth + tid];
+  };
   {
     const int i_raw = (tid >> 3) * CL + rank, q8 = tid & 7;
     const bool rowok = i_raw < N;
@@ -759,7 +764,8 @@ static inline bool diag_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, int n
   return true;
 }
 
-static inline size_t diag_ws_elems(const DiagPlan& pl) { return pl.kreg ? 0 : (size_t)8 * pl.ept * pl.threads; }
+static inline size_t diag_ws_elems(const DiagPlan& pl) { return pl.kreg ? 0 : (size_t)7 * pl.ept * pl.threads; }   // k1..k6, y
+static inline size_t diag_ws_shared_elems(const DiagPlan& pl) { return pl.kreg ? 0 : (size_t)pl.ept * pl.threads; }  // W
 
 struct DiagPack { size_t o_g0, o_gk, o_lam, o_gdiag, o_flag, bytes; };
 static inline DiagPack diag_pack_layout(int N, int n_g, const DiagPlan& pl) {

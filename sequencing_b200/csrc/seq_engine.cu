@@ -809,7 +809,7 @@ static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, c
   DiagPack dk = diag_pack_layout(N, n_g, pl);
   int rc = reserve(e, e->pack, pk.bytes + dk.bytes);
   if (rc) return rc;
-  rc = reserve(e, e->ws, diag_ws_elems(pl) * (size_t)d->B * sizeof(cplx) + 256);
+  rc = reserve(e, e->ws, (diag_ws_elems(pl) * (size_t)d->B + diag_ws_shared_elems(pl)) * sizeof(cplx) + 256);
   if (rc) return rc;
   char* base = (char*)e->pack.ptr;
   char* dbase = base + pk.bytes / 16 * 16;
