@@ -545,3 +545,43 @@ def test_calibration_sweeps_with_device_synthesis_match_host_path(gpu_engine):
         vals[dev] = (new, new_d)
     assert abs(vals[True][0] - vals[False][0]) < 1e-9 * abs(vals[False][0])
     assert abs(vals[True][1] - vals[False][1]) < 1e-7 * max(1.0, abs(vals[False][1]))
+
+
+def test_sequence_run_batch_keeps_states_on_device(gpu_engine):
+    """Sequence.run_batch (pulsed segments chained on the GPU, instantaneous unitaries by
+    seq_engine_apply_unitary, boundary expectation values by seq_engine_expect) against the per-state
+    Sequence.run(full_evolution=False) loop, for kets without collapse operators and for density matrices with."""
+    from sequencing_b200 import Cavity, System, Transmon
+    from sequencing_b200.sequencing import Sequence
+
+    for lossy in (False, True):
+        q = Transmon("qubit", levels=3, kerr=-0.2, **({"t1": 5e3, "t2": 4e3} if lossy else {}))
+        c = Cavity("cavity", levels=5, kerr=-1e-4, **({"t1": 8e3} if lossy else {}))
+        system = System("system", modes=[q, c])
+        system.set_cross_kerr(q, c, -2e-3)
+
+        def build():
+            seq = Sequence(system)
+            q.rotate_x(np.pi / 2)
+            seq.capture()
+            seq.append(q.Ry(np.pi / 3))
+            c.displace(0.7)
+            seq.capture()
+            seq.append(q.Rx(np.pi))
+            q.rotate_y(np.pi)
+            seq.capture()
+            return seq
+
+        inits = [system.fock(qubit=0, cavity=0), system.fock(qubit=1, cavity=0), (system.fock(qubit=0, cavity=1) + 1j * system.fock(qubit=1, cavity=2)).unit()]
+        e_ops = [q.n, c.n, system.fock_dm(qubit=1, cavity=0)]
+        batch = build().run_batch(inits, e_ops=e_ops)
+        assert len(batch) == 3
+        for st, got in zip(inits, batch):
+            ref = build().run(st, e_ops=e_ops, full_evolution=False)
+            np.testing.assert_allclose(got.times, ref.times, atol=0)
+            assert len(got.states) == len(ref.states) == 6
+            for a, b in zip(got.states, ref.states):
+                assert a.isket == b.isket
+                assert np.max(np.abs(a.full() - b.full())) < 1e-12
+            for a, b in zip(got.expect, ref.expect):
+                np.testing.assert_allclose(a, b, atol=1e-12)
