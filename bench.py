@@ -385,7 +385,7 @@ def ours(args):
     def solve_host():
         if rows_mode:                      # public API of the sharded mode: host arrays in, host arrays out
             return eng.solve_rows_sharded(bp_h, comm)
-        return eng.solve_host_abi(bp_h)    # returns after D2H + stream sync
+        return eng.solve_host_abi(bp_h, pinned_out=True)    # returns after D2H (into pinned buffers) + stream sync
 
     solve_host()  # warm the staging buffers
     barrier()

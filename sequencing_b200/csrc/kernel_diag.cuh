@@ -58,6 +58,8 @@ struct DiagOps {
   int n_el, ld, ybufs, guard; // owned elements, leading dimension, Y buffers, guard band (elements)
   int stage_g, stage_e, stage_tab, nnzE;   // what is staged in shared memory
   int lreal;                  // every collapse diagonal is real
+  int nct;                    // compute threads (controller-warp variant: blockDim has the controller's warp group on top)
+  int wsm;                    // bytes of k4 .. k6 kept in shared memory (registers + controller warp)
   const cplx* g0;             // [nD][N]
   const cplx* gk;             // [n_g][nD][N]
   const cplx* lam;            // [nT][N]
@@ -132,6 +134,9 @@ struct DiagCtrl {
   int pair, st0;      // embedded pair and first stage to evaluate (1: k1 is known)
   int accepted;       // commit the step that was just evaluated
   int emit_lo, emit_hi;   // outputs [emit_lo, emit_hi) are produced from the committed state
+  int cvbuf;          // which buffer of spline values belongs to this step (controller-warp variant)
+  int valid;          // prediction slot: a prediction was made
+  int verdict;        // actual slot: the prediction published before was confirmed - use it instead of this block
 };
 
 // controller state, kept in shared memory between calls (warp 0 only)
@@ -139,10 +144,11 @@ struct DiagCtlState {
   StepCtl ctl;
   double htry, target;
   int o, nst, landing, capped, dbg;
+  int nstA;           // nst right after the accept/reject decision (before the output loop resets it)
 };
 
 struct DiagLayout {
-  int off_Y, ystride, ybytes, off_Gt, gtbytes, off_lam, off_g, off_e, off_tab, off_cv, off_red, off_ctrl, total;
+  int off_Y, ystride, ybytes, off_Gt, gtbytes, off_lam, off_g, off_e, off_tab, off_cv, cvstride, off_red, off_ctrl, off_w, total;
 };
 __host__ __device__ inline DiagLayout diag_layout(int N, int n_g, int n_t, const DiagOps& o) {
   DiagLayout L;
@@ -158,9 +164,11 @@ __host__ __device__ inline DiagLayout diag_layout(int N, int n_g, int n_t, const
   L.off_e = L.off_g + (o.stage_g ? (1 + n_g) * L.gtbytes : 0);
   L.off_tab = L.off_e + (o.stage_e ? (o.nnzE > 0 ? o.nnzE : 1) * 32 : 0);   // 16 B value + 4 B index, padded
   L.off_cv = L.off_tab + (o.stage_tab ? n_g * n_t * (int)sizeof(double2) : 0);
-  L.off_red = L.off_cv + 7 * (n_g > 0 ? n_g : 1) * (int)sizeof(double);
+  L.cvstride = 7 * (n_g > 0 ? n_g : 1);
+  L.off_red = L.off_cv + 2 * L.cvstride * (int)sizeof(double);
   L.off_ctrl = L.off_red + 128 * (int)sizeof(double);
-  L.total = L.off_ctrl + 64 + 192;   // DiagCtrl + DiagCtlState
+  L.off_w = L.off_ctrl + 2 * 64 + 2 * 192;   // DiagCtrl[2] (actual, predicted) + DiagCtlState[2]
+  L.total = L.off_w + o.wsm;
   return L;
 }
 
@@ -181,7 +189,7 @@ __device__ __forceinline__ double diag_block_sum(double v, double* red, int& tog
 // in shared memory and must not occupy registers of the element loops.
 __device__ __noinline__ void diag_controller(const SolveParams& p, DiagCtlState* S, DiagCtrl* ctrl, double* cv,
                                              const double2* tabc, const double2* tabr, const double* cscale,
-                                             int update, int nrhs, double es) {
+                                             int update, int nrhs, double es, int cvbuf) {
   const int lane = threadIdx.x & 31, n_g = p.n_g;
   PROF_DECL
   StepCtl ctl = S->ctl;
@@ -200,6 +208,7 @@ __device__ __noinline__ void diag_controller(const SolveParams& p, DiagCtlState*
 #endif
     accepted = ctl_update(ctl, p, err, c_htry, c_landing, c_capped, c_target, c_nst);
   }
+  const int nstA = c_nst;
   PROF(9);
   const int emit_lo = c_o;
   int cmd = 1;
@@ -235,12 +244,52 @@ __device__ __noinline__ void diag_controller(const SolveParams& p, DiagCtlState*
     ctrl->accepted = accepted ? 1 : 0;
     ctrl->emit_lo = emit_lo;
     ctrl->emit_hi = emit_hi;
+    ctrl->cvbuf = cvbuf;
+    ctrl->valid = 0;
+    ctrl->verdict = 0;
+    S->nstA = nstA;
     S->ctl = ctl;
     S->htry = c_htry; S->target = c_target;
     S->o = c_o; S->nst = c_nst; S->landing = c_landing ? 1 : 0; S->capped = c_capped ? 1 : 0;
   }
   __syncwarp();
   PROF(12);
+}
+
+// Controller-warp variant: was the prediction `Sp` (the controller run on a copy of `S` with the previous step's
+// error estimate while the step was still being evaluated) the decision the real error estimate leads to?  The
+// accept/reject logic is re-run on the real estimate; every field of the controller except the step-size
+// proposal h must agree, and h must not bind in either (both proposals at or above max_step: the next trial
+// step, its landing / capped flags and therefore the spline values are then identical).  On success the
+// prediction becomes the state, with the real h.
+__device__ __noinline__ bool diag_verify(const SolveParams& p, const DiagCtlState* S, DiagCtlState* Sp, int nrhs, double es) {
+  StepCtl ct = S->ctl;
+  int nst = S->nst;
+  ct.nrhs += nrhs;
+  ct.have_k1 = true;
+  const double err = sqrt(es / ((double)p.N * (double)p.N));
+  const bool acc = ctl_update(ct, p, err, S->htry, S->landing != 0, S->capped != 0, S->target, nst);
+  const StepCtl cp = Sp->ctl;
+  const bool same = acc && p.max_step > 0 && ct.h >= p.max_step && cp.h >= p.max_step && ct.t == cp.t && ct.pair == cp.pair &&
+                    ct.status == cp.status && ct.nacc == cp.nacc && ct.nrej == cp.nrej && ct.nrhs == cp.nrhs &&
+                    ct.probe_wait == cp.probe_wait && ct.probe_backoff == cp.probe_backoff && ct.have_k1 == cp.have_k1 &&
+                    ct.prev_rejected == cp.prev_rejected && nst == Sp->nstA;
+  __syncwarp();
+  if (same && (threadIdx.x & 31) == 0) Sp->ctl.h = ct.h;
+  __syncwarp();
+  return same;
+}
+
+// named barriers of the controller-warp variant (0 is __syncthreads)
+#define DIAG_BAR_STAGE 1   // compute warps only
+#define DIAG_BAR_LAST 2    // last stage of a step: compute warps + controller (publishes the prediction)
+#define DIAG_BAR_ERR 3     // compute warps arrive with their error partial sums, the controller waits
+#define DIAG_BAR_VERDICT 4 // the controller arrives with the verdict / the actual control block, compute warps wait
+#define DIAG_BAR_ALL 5     // compute warps + controller (set-up)
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 // threads per CTA by (elements per thread, stage vectors in registers): 65536 registers / threads, allocated per 4 warps
@@ -260,14 +309,33 @@ namespace cg = cooperative_groups;
 
 #define DIAG_MAXT_STREAM 736   // stage vectors streamed through L2: 80 registers per thread
 
-template <int EPT, int CL, bool GUARD, bool KREG>
-__global__ void __launch_bounds__(KREG ? DIAG_MAXT : DIAG_MAXT_STREAM, 1)
+// CW: one extra warp (the last) carries the step controller and nothing else.  While the compute warps evaluate a
+// step it PREDICTS the next control block (assuming the error estimate of the previous step; spline values of the next stage times
+// included); once the error partial sums are in, it only re-runs the accept/reject logic (diag_verify) and
+// publishes a verdict.  The compute warps do not wait for it: after handing in their partial sums they emit the
+// outputs and stage the first RHS input of the predicted next step into the free Y / G(t) buffers (double-buffered
+// Y only), and pick up the verdict at that stage's barrier.  A wrong prediction (rejected step, order switch, a
+// binding step-size proposal) discards the staged input and takes the controller's actual block - decisions are
+// bit-identical to the variant without the controller warp.  With CW the register budget is 128 (13 warps: one scheduler holds four), so
+// k5 / k6 - used by the 5(4) pair only - and the static weights move to thread-private slots in shared memory.
+template <int EPT, int CL, bool GUARD, bool KREG, bool CW>
+__global__ void __launch_bounds__((KREG ? DIAG_MAXT : DIAG_MAXT_STREAM) + (CW ? 32 : 0), 1)
 solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__ DiagOps sp) {
+  static_assert(!CW || CL == 1, "the controller warp variant is single-CTA");
   extern __shared__ __align__(16) unsigned char smem_diag[];
+#ifdef SEQ_PROFILE_REGIONS
+  const unsigned long long prof_c0 = clock64();
+  unsigned long long prof_g0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_g0));
+#endif
   constexpr int C = (int)sizeof(cplx);
+  constexpr int KR = KREG ? (CW ? 3 : 6) : 0;      // stage derivatives kept in registers
   const int N = p.N, ld = sp.ld, n_g = p.n_g;
-  const int tid = threadIdx.x, nth = blockDim.x;
-  const int lane = tid & 31, warp = tid >> 5, nw = (nth + 31) >> 5;
+  const int nth = CW ? sp.nct : (int)blockDim.x;                 // compute threads; CW: the controller warp comes on top
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (nth + 31) >> 5;
+  const bool is_ctl = CW && warp == nw;
+  const int nall = nth + (CW ? 32 : 0);                          // threads that take part from here on
+  const int tid = threadIdx.x;
   const int rank = (CL > 1) ? (int)(blockIdx.x % CL) : 0;      // CTA inside the cluster
   const int b = blockIdx.x / CL;                                // trajectory
   const DiagLayout L = diag_layout(N, n_g, p.n_t, sp);
@@ -276,22 +344,22 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
   DiagCtrl* ctrl = (DiagCtrl*)(smem_diag + L.off_ctrl);
   unsigned char* peer = nullptr;                                // the other CTA's shared memory (same layout)
   if (CL > 1) peer = (unsigned char*)cg::this_cluster().map_shared_rank((void*)smem_diag, rank ^ 1);
-  auto sync_all = [&]() { if (CL > 1) cg::this_cluster().sync(); else __syncthreads(); };
+  auto sync_all = [&]() { if (CL > 1) cg::this_cluster().sync(); else if (CW) bar_sync(DIAG_BAR_ALL, nall); else __syncthreads(); };
 
   const double2* tabc = p.tab + (long long)b * p.tab_bstride_c;
   const double2* tabr = p.tab_rate + (long long)b * p.tab_bstride_r;
   const double* cscale = p.coeff_scale ? p.coeff_scale + (long long)b * p.n_ch : nullptr;
 
   // ---- stage shared tables: zero guard bands / Y padding, collapse diagonals, G diagonals, E, spline tables
-  for (int q = tid; q < L.off_Gt / 16; q += nth) ((cplx*)smem_diag)[q] = cmake(0, 0);
-  for (int q = tid; q < sp.nT * N; q += nth) ((cplx*)(smem_diag + L.off_lam))[q] = sp.lam[q];
+  for (int q = tid; q < L.off_Gt / 16; q += nall) ((cplx*)smem_diag)[q] = cmake(0, 0);
+  for (int q = tid; q < sp.nT * N; q += nall) ((cplx*)(smem_diag + L.off_lam))[q] = sp.lam[q];
   const int gsz = sp.nD * N;
   const cplx* g0p = sp.g0;
   const cplx* gkp = sp.gk;
   if (sp.stage_g) {
     cplx* gs = (cplx*)(smem_diag + L.off_g);
-    for (int q = tid; q < gsz; q += nth) gs[q] = sp.g0[q];
-    for (int q = tid; q < n_g * gsz; q += nth) gs[gsz + q] = sp.gk[q];
+    for (int q = tid; q < gsz; q += nall) gs[q] = sp.g0[q];
+    for (int q = tid; q < n_g * gsz; q += nall) gs[gsz + q] = sp.gk[q];
     g0p = gs; gkp = gs + gsz;
   }
   const unsigned* eij = sp.e_ij;
@@ -299,13 +367,13 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
   if (sp.stage_e) {
     cplx* ev_s = (cplx*)(smem_diag + L.off_e);
     unsigned* ei_s = (unsigned*)(ev_s + (sp.nnzE > 0 ? sp.nnzE : 1));
-    for (int q = tid; q < sp.nnzE; q += nth) { ev_s[q] = sp.e_val[q]; ei_s[q] = sp.e_ij[q]; }
+    for (int q = tid; q < sp.nnzE; q += nall) { ev_s[q] = sp.e_val[q]; ei_s[q] = sp.e_ij[q]; }
     eij = ei_s; eval_ = ev_s;
   }
   if (sp.stage_tab) {
     double2* ts = (double2*)(smem_diag + L.off_tab);
-    for (int q = tid; q < p.n_ch * p.n_t; q += nth) ts[q] = tabc[q];
-    for (int q = tid; q < p.n_ctd * p.n_t; q += nth) ts[p.n_ch * p.n_t + q] = tabr[q];
+    for (int q = tid; q < p.n_ch * p.n_t; q += nall) ts[q] = tabc[q];
+    for (int q = tid; q < p.n_ctd * p.n_t; q += nall) ts[p.n_ch * p.n_t + q] = tabr[q];
     tabc = ts; tabr = ts + p.n_ch * p.n_t;
   }
 
@@ -317,16 +385,24 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
   // KREG: y, the static weights W and the stage derivatives k1..k6 live in registers (EPT <= 4); otherwise they are
   // thread-private coalesced streams in global memory (L2-resident), slots 0..5: k, 6: y, 7: W
   cplx ys[EPT], kout[EPT];
-  cplx y[KREG ? EPT : 1], W[KREG ? EPT : 1];
-  cplx k[KREG ? 6 : 1][KREG ? EPT : 1];
-  cplx* kst = KREG ? nullptr : p.ws + (long long)blockIdx.x * p.ws_stride;
+  constexpr bool WREG = KREG;            // static weights in registers (else: the shared L2 table)
+  cplx y[KREG ? EPT : 1], W[WREG ? EPT : 1];
+  cplx* wsm = (cplx*)(smem_diag + L.off_w);
+  cplx k[KR > 0 ? KR : 1][KREG ? EPT : 1];
+  // (KREG && CW: k4 .. k6 in shared memory)
+  cplx* kst = KREG ? (CW ? (cplx*)(smem_diag + L.off_w) : nullptr) : p.ws + (long long)blockIdx.x * p.ws_stride;
   // the static weights are the same for every trajectory: ONE table behind the per-trajectory streams, written by
   // every CTA with identical values (keeps 1/8 of the stream footprint out of L2 / HBM)
   cplx* wtab = KREG ? nullptr : p.ws + (long long)gridDim.x * p.ws_stride;
   auto st_at = [&](int slot, int e) -> cplx& {
     return slot == 7 ? wtab[(long long)e * nth + tid] : kst[((long long)slot * EPT + e) * nth + tid];
   };
-  {
+  // stage derivative j of element e: registers below KR; above, shared memory (KREG: slots j - KR) or the L2 stream (slot j)
+  auto kget = [&](int j, int e) -> cplx { return (KREG && j < KR) ? k[j < KR ? j : 0][KREG ? e : 0] : st_at(KREG ? j - KR : j, e); };
+  auto kset = [&](int j, int e, const cplx& v) {
+    if (KREG && j < KR) k[j < KR ? j : 0][KREG ? e : 0] = v; else st_at(KREG ? j - KR : j, e) = v;
+  };
+  if (!is_ctl) {
     const int i_raw = (tid >> 3) * CL + rank, q8 = tid & 7;
     const bool rowok = i_raw < N;
     const int i = rowok ? i_raw : 0;
@@ -349,7 +425,7 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       if (KREG) {
         y[KREG ? e : 0] = ys[e];
 #pragma unroll
-        for (int q = 0; q < 6; q++) k[KREG ? q : 0][KREG ? e : 0] = cmake(0, 0);
+        for (int q = 0; q < KR; q++) k[q < KR ? q : 0][KREG ? e : 0] = cmake(0, 0);
       } else {
         st_at(6, e) = ys[e];
         for (int q = 0; q < 6; q++) st_at(q, e) = cmake(0, 0);
@@ -362,7 +438,7 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
         w.x += a.x * c.x + a.y * c.y;
         w.y += a.y * c.x - a.x * c.y;
       }
-      if (KREG) W[KREG ? e : 0] = w; else st_at(7, e) = w;
+      if (WREG) W[WREG ? e : 0] = w; else if (KREG) wsm[e * nth + tid] = w; else st_at(7, e) = w;
       asm volatile("" : "+r"(oy[e]));
     }
     asm volatile("" : "+r"(oi), "+r"(rowb));
@@ -370,6 +446,7 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
   sync_all();   // guard bands zeroed (in both CTAs) before anything is written into Y
 
   int yb = 0, gb = 0, tog = 0, ycur = 0;
+  const double* cvc = cv;      // spline values of the step being evaluated (CW: one of two buffers)
   PROF_DECL
   // owner writes Y_ij and the mirror Y_ji, into every CTA of the cluster
   auto write_Y = [&](int boff, const cplx (&v)[EPT]) {
@@ -386,12 +463,12 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       }
     }
   };
-  auto build_Gt = [&](cplx* Gb, int st) {
+  auto build_Gt = [&](cplx* Gb, const double* cvs, int st) {
     for (int q = tid; q < gsz; q += nth) {
       cplx g = g0p[q];
       for (int m = 0; m < n_g; m++) {
         const cplx a = gkp[m * gsz + q];
-        const double v = cv[st * n_g + m];
+        const double v = cvs[st * n_g + m];
         g.x = fma(v, a.x, g.x);
         g.y = fma(v, a.y, g.y);
       }
@@ -405,7 +482,7 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
   // kout = W ys - i (G' Y - Y G'^dag) + collapse terms, G' = G minus its static main diagonal
   auto compute_K = [&](const unsigned char* __restrict__ Yb, const unsigned char* __restrict__ Gb, int st) {
 #pragma unroll
-    for (int e = 0; e < EPT; e++) kout[e] = cmul(KREG ? W[KREG ? e : 0] : st_at(7, e), ys[e]);
+    for (int e = 0; e < EPT; e++) kout[e] = cmul(WREG ? W[WREG ? e : 0] : (KREG ? wsm[e * nth + tid] : st_at(7, e)), ys[e]);
     if (sp.g0_tab >= 0) {      // time-dependent main diagonal
       const unsigned char* gv = Gb + sp.g0_tab;
       const cplx vi = *(const cplx*)(gv + oi);
@@ -438,7 +515,7 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
     for (int t = 0; t < sp.nLo; t++) {
       const unsigned char* la = lam + sp.lo_a[t];
       const unsigned char* lbj = lam + sp.lo_b[t] - rowb;
-      const double r = cv[st * n_g + sp.lo_r[t]];
+      const double r = cvc[st * n_g + sp.lo_r[t]];
       const cplx a = seq::cscale(r, *(const cplx*)(la + oi));
       DIAG_FOR_CHUNKED(e) {
         const cplx c = *(const cplx*)(lbj + oy[e]);
@@ -454,7 +531,7 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       const unsigned char* lbj = lam + sp.lg_b[t] - rowb;
       const int off = sp.lg_off[t];
       const int ri = sp.lg_r[t];
-      const double r = ri < 0 ? 1.0 : cv[st * n_g + ri];
+      const double r = ri < 0 ? 1.0 : cvc[st * n_g + ri];
       if (lreal) {
         const double ra = r * (*(const double*)(la + oi));
         DIAG_FOR_CHUNKED(e) {
@@ -502,25 +579,83 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
     }
   };
 
-  DiagCtlState* cst = (DiagCtlState*)(smem_diag + L.off_ctrl + 64);
-  if (tid == 0) {
+  static_assert(sizeof(DiagCtrl) <= 64 && sizeof(DiagCtlState) <= 192, "control blocks outgrew their shared-memory slots");
+  DiagCtrl* ctrl_pred = (DiagCtrl*)(smem_diag + L.off_ctrl + 64);
+  DiagCtlState* cst = (DiagCtlState*)(smem_diag + L.off_ctrl + 128);
+  if (tid == (CW ? nth : 0)) {      // (CW: first lane of the controller warp)
     StepCtl c0;
     ctl_init(c0, p);
     cst->ctl = c0;
-    cst->htry = 0.0; cst->target = 0.0; cst->o = 0; cst->nst = 0; cst->landing = 0; cst->capped = 0; cst->dbg = 0;
+    cst->htry = 0.0; cst->target = 0.0; cst->o = 0; cst->nst = 0; cst->landing = 0; cst->capped = 0; cst->dbg = 0; cst->nstA = 0;
   }
   __syncwarp();
 
-  write_Y(L.off_Y, ys);
-  if (warp == 0) diag_controller(p, cst, ctrl, cv, tabc, tabr, cscale, 0, 0, 0.0);
+  if (!is_ctl) write_Y(L.off_Y, ys);
+  if (CW ? is_ctl : warp == 0) diag_controller(p, cst, ctrl, cv, tabc, tabr, cscale, 0, 0, 0.0, 0);
   sync_all();
+
+  if (CW && is_ctl) {
+    // ---------------- the controller warp ----------------
+    DiagCtlState* S = cst;
+    DiagCtlState* Sp = (DiagCtlState*)(smem_diag + L.off_ctrl + 128 + 192);
+    int cur = 0, ctog = 0;       // spline-value buffer of the step being evaluated; toggle of the partial-sum buffer
+    double es_prev = 0.0;        // the prediction assumes the error estimate of the previous step
+    while (true) {
+      const int cmd = ctrl->cmd;
+      const int nrhs = (ctrl->pair ? 5 : 7) - ctrl->st0;
+      __syncwarp();
+      if (cmd) break;
+      // prediction: the controller on a copy of the state, with the error estimate of the previous step
+      const bool predict = p.max_step > 0 && S->ctl.status == SEQ_STATUS_OK;
+      if (predict) {
+        if (lane == 0) *Sp = *S;
+        __syncwarp();
+        diag_controller(p, Sp, ctrl_pred, cv + (cur ^ 1) * L.cvstride, tabc, tabr, cscale, 1, nrhs, es_prev, cur ^ 1);
+      }
+      if (lane == 0) ctrl_pred->valid = (predict && ctrl_pred->accepted && ctrl_pred->st0 == 1) ? 1 : 0;
+      __syncwarp();
+      const bool valid = ctrl_pred->valid != 0;
+      __threadfence_block();
+      bar_sync(DIAG_BAR_LAST, nall);
+      bar_sync(DIAG_BAR_ERR, nall);
+      double es = (lane < nw) ? red[ctog * 32 + lane] : 0.0;
+      es = warp_sum(es);
+      ctog ^= 1;
+      es_prev = es;
+      const bool ok = valid && diag_verify(p, S, Sp, nrhs, es);
+      if (ok) {
+        if (lane == 0) { *ctrl = *ctrl_pred; ctrl->verdict = 1; }
+        DiagCtlState* t = S; S = Sp; Sp = t;
+        cur ^= 1;
+#ifndef SEQ_PROFILE_REGIONS
+        if (lane == 0) S->dbg += 1;      // stats[3]: confirmed predictions
+#endif
+      } else {
+        diag_controller(p, S, ctrl, cv + cur * L.cvstride, tabc, tabr, cscale, 1, nrhs, es, cur);
+      }
+      __syncwarp();
+      bar_arrive(DIAG_BAR_VERDICT, nall);
+    }
+    if (lane == 0) {
+      p.status[b] = S->ctl.status;
+      p.stats[b * 4 + 0] = S->ctl.nacc;
+      p.stats[b * 4 + 1] = S->ctl.nrej;
+      p.stats[b * 4 + 2] = S->ctl.nrhs;
+      p.stats[b * 4 + 3] = S->dbg;
+    }
+    return;
+  }
+
+  auto sync_stage = [&]() { if (CW) bar_sync(DIAG_BAR_STAGE, nth); else sync_all(); };
 
   // One embedded-RK step with the stage loop unrolled at compile time: static register indices for the stage
   // derivatives, tableau coefficients as immediates (zero entries vanish).  Returns this thread's share of
-  // the weighted squared error.
-  auto run_step = [&](auto tag, const int st0, const double htry) -> double {
+  // the weighted squared error.  `prepped` (CW): the input of the first evaluated stage (st0 == 1) is already in
+  // Y / G(t) and the barrier behind it has been passed.
+  auto run_step = [&](auto tag, const int st0, const double htry, const bool prepped) -> double {
     constexpr int PAIR = decltype(tag)::value;
     constexpr int S = PAIR ? 5 : 7;
+    double isc[EPT];      // error weights (1 or 2 for the mirrored element) / scale^2
 #pragma unroll
     for (int st = 0; st < S; st++) {
       if (st == 0 && st0 != 0) continue;        // FSAL: k1 is known
@@ -531,7 +666,7 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
         for (int j = 0; j < 6; j++) {
           const double aj = rk_a_c(PAIR, st, j);
           if (j < st && aj != 0.0) {
-            const cplx kv = KREG ? k[KREG ? j : 0][KREG ? e : 0] : st_at(j, e);
+            const cplx kv = kget(j, e);
             ax = fma(aj, kv.x, ax);
             ay = fma(aj, kv.y, ay);
           }
@@ -539,23 +674,37 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
         const cplx yv = KREG ? y[KREG ? e : 0] : st_at(6, e);
         ys[e] = (st == 0) ? yv : cmake(fma(htry, ax, yv.x), fma(htry, ay, yv.y));
       }
-      if (sp.ybufs == 2) yb ^= 1;
-      gb ^= 1;
+      if (!(CW && st == 1 && prepped)) {
+        if (sp.ybufs == 2) yb ^= 1;
+        gb ^= 1;
+        if (CL > 1 && sp.ybufs == 1) cg::this_cluster().barrier_wait();   // every gather of the previous stage is done
+        write_Y(L.off_Y + yb * L.ystride, ys);
+        build_Gt((cplx*)(smem_diag + L.off_Gt + gb * L.gtbytes), cvc, st);
+        PROF(1);
+        if (CW && st == S - 1) bar_sync(DIAG_BAR_LAST, nall);      // the controller joins: its prediction becomes visible
+        else sync_stage();
+      }
       const int boff = L.off_Y + yb * L.ystride;
       unsigned char* Gb = smem_diag + L.off_Gt + gb * L.gtbytes;
-      if (CL > 1 && sp.ybufs == 1) cg::this_cluster().barrier_wait();   // every gather of the previous stage is done
-      write_Y(boff, ys);
-      build_Gt((cplx*)Gb, st);
-      PROF(1);
-      sync_all();
       PROF(2);
+      if (st == S - 1) {
+        // the last stage input is the new state: the error scale (square root + division chains) is known here and
+        // overlaps the gathers of the last right-hand side instead of sitting in the serial tail of the step
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+          const cplx yo = KREG ? y[KREG ? e : 0] : st_at(6, e);
+          const double sc = p.atol + p.rtol * sqrt(fmax(cabs2(yo), cabs2(ys[e])));
+          const double wgt = (vmask & (1u << e)) ? ((dmask & (1u << e)) ? 1.0 : 2.0) : 0.0;
+          isc[e] = wgt / (sc * sc);
+        }
+      }
       compute_K(smem_diag + boff, Gb, st);
       if (sp.ybufs == 1) {                      // all gathers done before the next stage overwrites Y
-        if (CL > 1) cg::this_cluster().barrier_arrive(); else __syncthreads();
+        if (CL > 1) cg::this_cluster().barrier_arrive(); else sync_stage();
       }
       if (st < S - 1) {
 #pragma unroll
-        for (int e = 0; e < EPT; e++) { if (KREG) k[KREG ? st : 0][KREG ? e : 0] = kout[e]; else st_at(st, e) = kout[e]; }
+        for (int e = 0; e < EPT; e++) kset(st, e, kout[e]);
       }
       PROF(3);
     }
@@ -568,30 +717,84 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       for (int j = 0; j < S - 1; j++) {
         const double cj = rk_e_c(PAIR, j);
         if (cj != 0.0) {
-          const cplx kv = KREG ? k[KREG ? j : 0][KREG ? e : 0] : st_at(j, e);
+          const cplx kv = kget(j, e);
           ex = fma(cj, kv.x, ex);
           ey = fma(cj, kv.y, ey);
         }
       }
       ex *= htry; ey *= htry;
-      const cplx yo = KREG ? y[KREG ? e : 0] : st_at(6, e);
-      const double sc = p.atol + p.rtol * sqrt(fmax(cabs2(yo), cabs2(ys[e])));
-      const double wgt = (vmask & (1u << e)) ? ((dmask & (1u << e)) ? 1.0 : 2.0) : 0.0;
-      es += wgt * (ex * ex + ey * ey) / (sc * sc);
+      es = fma(ex * ex + ey * ey, isc[e], es);
     }
     return es;
   };
+  auto commit = [&]() {
+#pragma unroll
+    for (int e = 0; e < EPT; e++) {
+      if (KREG) y[KREG ? e : 0] = ys[e]; else st_at(6, e) = ys[e];
+      kset(0, e, kout[e]);
+    }
+    ycur = yb;
+  };
 
+  if (CW) {
+    // ---------------- compute warps next to a controller warp ----------------
+    DiagCtrl c = *ctrl;
+    bool prepped = false;        // commit + outputs done, first stage input of the step staged
+    while (true) {
+      if (!prepped) {
+        if (c.accepted) commit();
+        for (int o = c.emit_lo; o < c.emit_hi; o++) emit(smem_diag + L.off_Y + ycur * L.ystride, o);
+      }
+      PROF(0);
+      if (c.cmd) break;
+      cvc = cv + c.cvbuf * L.cvstride;
+      if (sp.ybufs == 1 && !prepped && c.emit_hi > c.emit_lo) sync_stage();   // the next stage overwrites the buffer emit() read
+      double es;
+      if (c.pair) es = run_step(IntTag<1>(), c.st0, c.htry, prepped);
+      else es = run_step(IntTag<0>(), c.st0, c.htry, prepped);
+      PROF(4);
+      const DiagCtrl pc = *ctrl_pred;         // published before the barrier of the last stage
+      es = warp_sum(es);
+      if (lane == 0) red[tog * 32 + warp] = es;
+      tog ^= 1;
+      bar_arrive(DIAG_BAR_ERR, nall);
+      PROF(5);
+      prepped = false;
+      const bool spec = pc.valid && sp.ybufs == 2;
+      if (spec) {
+        // speculation on "accepted": the outputs of the new state (rewritten later if the step turns out rejected),
+        // then the first stage input of the predicted next step into the free Y / G(t) buffers
+        for (int o = pc.emit_lo; o < pc.emit_hi; o++) emit(smem_diag + L.off_Y + yb * L.ystride, o);
+        if (!pc.cmd) {
+          const double a21 = pc.pair ? rk_a_c(1, 1, 0) : rk_a_c(0, 1, 0);
+          cplx tmp[EPT];
+#pragma unroll
+          for (int e = 0; e < EPT; e++) {
+            const double ax = fma(a21, kout[e].x, 0.0), ay = fma(a21, kout[e].y, 0.0);
+            tmp[e] = cmake(fma(pc.htry, ax, ys[e].x), fma(pc.htry, ay, ys[e].y));
+          }
+          write_Y(L.off_Y + (yb ^ 1) * L.ystride, tmp);
+          build_Gt((cplx*)(smem_diag + L.off_Gt + (gb ^ 1) * L.gtbytes), cv + pc.cvbuf * L.cvstride, 1);
+        }
+      }
+      PROF(6);
+      bar_sync(DIAG_BAR_VERDICT, nall);
+      PROF(7);
+      if (pc.valid && ctrl->verdict) {
+        c = pc;
+        if (spec) {
+          commit();
+          if (!c.cmd) { yb ^= 1; gb ^= 1; }
+          prepped = true;
+        }
+      } else {
+        c = *ctrl;
+      }
+    }
+  } else {
   while (true) {
     const DiagCtrl c = *ctrl;
-    if (c.accepted) {
-#pragma unroll
-      for (int e = 0; e < EPT; e++) {
-        if (KREG) { y[KREG ? e : 0] = ys[e]; k[0][KREG ? e : 0] = kout[e]; }
-        else { st_at(6, e) = ys[e]; st_at(0, e) = kout[e]; }
-      }
-      ycur = yb;
-    }
+    if (c.accepted) commit();
     for (int o = c.emit_lo; o < c.emit_hi; o++) emit(smem_diag + L.off_Y + ycur * L.ystride, o);
     PROF(0);
     if (c.cmd) break;
@@ -602,8 +805,8 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       else if (c.emit_hi > c.emit_lo) __syncthreads();
     }
     double es;
-    if (c.pair) es = run_step(IntTag<1>(), c.st0, c.htry);
-    else es = run_step(IntTag<0>(), c.st0, c.htry);
+    if (c.pair) es = run_step(IntTag<1>(), c.st0, c.htry, false);
+    else es = run_step(IntTag<0>(), c.st0, c.htry, false);
     PROF(4);
     // block (cluster) sum of the error: every warp leaves its partial sum in every CTA, fixed summation order
     es = warp_sum(es);
@@ -618,10 +821,11 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       for (int q = 0; q < nw; q++) es += red[tog * 64 + r * 32 + q];
     tog ^= 1;
     PROF(5);
-    if (warp == 0) diag_controller(p, cst, ctrl, cv, tabc, tabr, cscale, 1, (c.pair ? 5 : 7) - c.st0, es);
+    if (warp == 0) diag_controller(p, cst, ctrl, cv, tabc, tabr, cscale, 1, (c.pair ? 5 : 7) - c.st0, es, 0);
     PROF(6);
     __syncthreads();
     PROF(7);
+  }
   }
 
   cplx* fin = p.final_state + (long long)b * N * N;
@@ -634,13 +838,22 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       if (i != j) fin[j * N + i] = cconj(yf);
     }
   }
-  if (tid == 0 && rank == 0) {
+  if (!CW && tid == 0 && rank == 0) {
     p.status[b] = cst->ctl.status;
     p.stats[b * 4 + 0] = cst->ctl.nacc;
     p.stats[b * 4 + 1] = cst->ctl.nrej;
     p.stats[b * 4 + 2] = cst->ctl.nrhs;
     p.stats[b * 4 + 3] = cst->dbg;
   }
+#ifdef SEQ_PROFILE_REGIONS
+  if (tid == 0) {      // 13: cycles of CTA 0, 14: longest CTA, 15: nanoseconds of CTA 0
+    const unsigned long long dc = clock64() - prof_c0;
+    unsigned long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    if (blockIdx.x == 0) { seq_prof[13] += dc; seq_prof[15] += g1 - prof_g0; }
+    atomicMax(&seq_prof[14], dc);
+  }
+#endif
   if (CL > 1) cg::this_cluster().sync();     // no CTA exits while its shared memory may still be written remotely
 }
 
@@ -651,8 +864,8 @@ struct DiagPlan {
   DiagOps ops;          // offsets / term lists filled in; pointers set at launch
   DiagFill fill;
   int maxoff;
-  int ept, cl, lpr, threads;
-  bool kreg, guard;
+  int ept, cl, lpr, threads;    // threads: compute threads (the controller warp comes on top)
+  bool kreg, guard, cw;
   size_t smem;
   long long macs;       // complex multiply-adds per element (cost model)
 };
@@ -660,7 +873,7 @@ struct DiagPlan {
 // flags: host copy of diag_flags_kernel's output, [1 + n_l][2N - 1].  Returns false if the operators are not
 // diagonal-structured enough (too many diagonals) or no launch shape fits.
 static inline bool diag_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, int n_t, int nnzE, const int* flags, int max_smem,
-                             int cl_override, DiagPlan* pl) {
+                             int cl_override, bool allow_cw, DiagPlan* pl) {
   const int n_l = n_c + n_ctd, W = 2 * N - 1, c = (int)sizeof(cplx);
   if (N < 2 || N > 0x7fff) return false;
   DiagOps& o = pl->ops;
@@ -760,6 +973,14 @@ static inline bool diag_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, int n
   if (o.stage_tab && diag_layout(N, n_g, n_t, o).total > max_smem) o.stage_tab = 0;
   o.stage_e = (nnzE > 0 && nnzE <= DIAG_E_SMEM) ? 1 : 0;
   if (o.stage_e && diag_layout(N, n_g, n_t, o).total > max_smem) o.stage_e = 0;
+  // a controller warp next to the compute warps, where a step is short enough for the controller to matter (N <= 48)
+  pl->cw = allow_cw && pl->cl == 1 && pl->kreg;
+  o.wsm = 0;
+  o.nct = pl->threads;
+  if (pl->cw && pl->kreg) {             // 13 warps: 128 registers per thread - the static weights move to shared memory
+    o.wsm = 3 * pl->ept * pl->threads * c;      // k4, k5, k6
+    if (diag_layout(N, n_g, n_t, o).total > max_smem) { o.wsm = 0; pl->cw = false; }
+  }
   pl->smem = (size_t)diag_layout(N, n_g, n_t, o).total;
   return true;
 }
@@ -781,14 +1002,15 @@ static inline DiagPack diag_pack_layout(int N, int n_g, const DiagPlan& pl) {
   return k;
 }
 
-template <int EPT, int CL, bool GUARD, bool KREG>
+#ifndef SEQ_DIAG_NO_LAUNCH      // (single-instance compile checks define it)
+template <int EPT, int CL, bool GUARD, bool KREG, bool CW>
 static int launch_diag_t(const SolveParams& p, const DiagOps& sp, const DiagPlan& pl, cudaStream_t st) {
-  auto kern = solve_diag_kernel<EPT, CL, GUARD, KREG>;
+  auto kern = solve_diag_kernel<EPT, CL, GUARD, KREG, CW>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) return SEQ_ERR_CUDA;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)p.B * CL, 1, 1);
-  cfg.blockDim = dim3((unsigned)pl.threads, 1, 1);
+  cfg.blockDim = dim3((unsigned)pl.threads + (CW ? 32 : 0), 1, 1);
   cfg.dynamicSmemBytes = pl.smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -799,40 +1021,45 @@ static int launch_diag_t(const SolveParams& p, const DiagOps& sp, const DiagPlan
   return cudaLaunchKernelEx(&cfg, kern, p, sp) == cudaSuccess ? SEQ_OK : SEQ_ERR_CUDA;
 }
 
-static inline int launch_diag_kernel(const SolveParams& p, const DiagOps& sp, const DiagPlan& pl, cudaStream_t st) {
+template <bool CW>
+static inline int launch_diag_cl1(const SolveParams& p, const DiagOps& sp, const DiagPlan& pl, cudaStream_t st) {
   if (!pl.kreg) {
+    if (CW) return SEQ_ERR_UNSUPPORTED;
     switch (pl.ept) {
-      case 4: return launch_diag_t<4, 1, false, false>(p, sp, pl, st);
-      case 5: return launch_diag_t<5, 1, false, false>(p, sp, pl, st);
-      case 6: return launch_diag_t<6, 1, false, false>(p, sp, pl, st);
+      case 4: return launch_diag_t<4, 1, false, false, false>(p, sp, pl, st);
+      case 5: return launch_diag_t<5, 1, false, false, false>(p, sp, pl, st);
+      case 6: return launch_diag_t<6, 1, false, false, false>(p, sp, pl, st);
     }
-  } else if (pl.cl == 1) {
-    if (pl.guard) {
-      switch (pl.ept) {
-        case 1: return launch_diag_t<1, 1, true, true>(p, sp, pl, st);
-        case 2: return launch_diag_t<2, 1, true, true>(p, sp, pl, st);
-        case 3: return launch_diag_t<3, 1, true, true>(p, sp, pl, st);
-        case 4: return launch_diag_t<4, 1, true, true>(p, sp, pl, st);
-      }
-    } else {
-      switch (pl.ept) {
-        case 1: return launch_diag_t<1, 1, false, true>(p, sp, pl, st);
-        case 2: return launch_diag_t<2, 1, false, true>(p, sp, pl, st);
-        case 3: return launch_diag_t<3, 1, false, true>(p, sp, pl, st);
-        case 4: return launch_diag_t<4, 1, false, true>(p, sp, pl, st);
-      }
+  } else if (pl.guard) {
+    switch (pl.ept) {
+      case 1: return launch_diag_t<1, 1, true, true, CW>(p, sp, pl, st);
+      case 2: return launch_diag_t<2, 1, true, true, CW>(p, sp, pl, st);
+      case 3: return launch_diag_t<3, 1, true, true, CW>(p, sp, pl, st);
+      case 4: return launch_diag_t<4, 1, true, true, CW>(p, sp, pl, st);
     }
   } else {
     switch (pl.ept) {
-      case 1: return launch_diag_t<1, 2, false, true>(p, sp, pl, st);
-      case 2: return launch_diag_t<2, 2, false, true>(p, sp, pl, st);
-      case 3: return launch_diag_t<3, 2, false, true>(p, sp, pl, st);
-      case 4: return launch_diag_t<4, 2, false, true>(p, sp, pl, st);
-      case 5: return launch_diag_t<5, 2, false, true>(p, sp, pl, st);
-      case 6: return launch_diag_t<6, 2, false, true>(p, sp, pl, st);
+      case 1: return launch_diag_t<1, 1, false, true, CW>(p, sp, pl, st);
+      case 2: return launch_diag_t<2, 1, false, true, CW>(p, sp, pl, st);
+      case 3: return launch_diag_t<3, 1, false, true, CW>(p, sp, pl, st);
+      case 4: return launch_diag_t<4, 1, false, true, CW>(p, sp, pl, st);
     }
   }
   return SEQ_ERR_UNSUPPORTED;
 }
+
+static inline int launch_diag_kernel(const SolveParams& p, const DiagOps& sp, const DiagPlan& pl, cudaStream_t st) {
+  if (pl.cl == 1) return pl.cw ? launch_diag_cl1<true>(p, sp, pl, st) : launch_diag_cl1<false>(p, sp, pl, st);
+  switch (pl.ept) {
+    case 1: return launch_diag_t<1, 2, false, true, false>(p, sp, pl, st);
+    case 2: return launch_diag_t<2, 2, false, true, false>(p, sp, pl, st);
+    case 3: return launch_diag_t<3, 2, false, true, false>(p, sp, pl, st);
+    case 4: return launch_diag_t<4, 2, false, true, false>(p, sp, pl, st);
+    case 5: return launch_diag_t<5, 2, false, true, false>(p, sp, pl, st);
+    case 6: return launch_diag_t<6, 2, false, true, false>(p, sp, pl, st);
+  }
+  return SEQ_ERR_UNSUPPORTED;
+}
+#endif
 
 }  // namespace seq

@@ -46,6 +46,13 @@ struct seq_engine {
   std::string variant;              // human-readable detail of what the last solve ran
   int sm_count = 0;
   int max_smem_optin = 0;
+  // host-buffer solves of a large batch run as chunks on two internal engines (own streams, own scratch) so that
+  // the H2D / D2H copies of one chunk overlap the kernels of the other
+  seq_engine* sub[2] = {nullptr, nullptr};
+  cudaStream_t sub_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr;
+  int chunks = 1;                   // chunks of the last host-buffer solve
+  float chunk_ms = 0.f;             // their integration kernels' durations, summed
 };
 
 static int fail(seq_engine* e, int code, const char* fmt, ...) {
@@ -412,6 +419,11 @@ int seq_engine_destroy(seq_engine* e) {
   DevBuf* bufs[] = {&e->ws, &e->gbuf, &e->tab, &e->cprime, &e->pack, &e->stage_in, &e->stage_out, &e->large, &e->sched, &e->spinfo, &e->dflags};
   for (DevBuf* b : bufs) if (b->ptr) cudaFree(b->ptr);
   if (e->host_err) cudaFreeHost(e->host_err);
+  for (int q = 0; q < 2; q++) {
+    if (e->sub[q]) seq_engine_destroy(e->sub[q]);
+    if (e->sub_stream[q]) cudaStreamDestroy(e->sub_stream[q]);
+  }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   delete e;
@@ -446,6 +458,7 @@ int seq_engine_last_method(const seq_engine* e) { return e ? e->last_method : 0;
 const char* seq_engine_last_variant(const seq_engine* e) { return e ? e->variant.c_str() : ""; }
 
 float seq_engine_last_kernel_ms(seq_engine* e) {
+  if (e && e->chunks > 1) return e->chunk_ms;
   if (!e || !e->timed) return -1.0f;
   if (cudaEventSynchronize(e->ev1) != cudaSuccess) return -1.0f;
   float ms = -1.0f;
@@ -840,9 +853,13 @@ static int diag_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, 
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   const char* env = getenv("SEQ_DIAG_CL");
   const char* cap = getenv("SEQ_DIAG_SMEM_CAP");
+  // SEQ_DIAG_CW=1: controller-warp variant (N <= 48).  Opt-in: measured neutral on the C2 sweep (5 % faster on
+  // trajectories that stay on the capped 4(3) pair, 4 % slower on those that keep returning to the 5(4) pair - the
+  // 13th warp costs the compute warps 40 registers), see DESIGN.md 4.1b
+  const char* cw = getenv("SEQ_DIAG_CW");
   int max_smem = e->max_smem_optin;
   if (cap && atoi(cap) > 0 && atoi(cap) < max_smem) max_smem = atoi(cap);
-  *usable = diag_plan(N, n_g, d->n_c, d->n_ctd, d->n_ch, d->n_t, nnzE, h.data(), max_smem, env ? atoi(env) : 0, pl);
+  *usable = diag_plan(N, n_g, d->n_c, d->n_ctd, d->n_ch, d->n_t, nnzE, h.data(), max_smem, env ? atoi(env) : 0, cw && atoi(cw) == 1, pl);
   return SEQ_OK;
 }
 
@@ -887,9 +904,10 @@ static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, c
   CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
   sp.lreal = h_imag == 0 ? 1 : 0;
   {
-    char buf[160];
-    snprintf(buf, sizeof(buf), "diag: %d CTA%s x %d threads per trajectory, %d elements/thread, stage vectors in %s, %d Y buffer%s%s, smem %zu B", pl.cl, pl.cl > 1 ? "s (cluster)" : "",
-             pl.threads, pl.ept, pl.kreg ? "registers" : "L2 streams", sp.ybufs, sp.ybufs > 1 ? "s" : "", pl.guard ? " + guard bands" : "", pl.smem);
+    char buf[224];
+    snprintf(buf, sizeof(buf), "diag: %d CTA%s x %d threads%s per trajectory, %d elements/thread, stage vectors in %s, %d Y buffer%s%s, smem %zu B", pl.cl, pl.cl > 1 ? "s (cluster)" : "",
+             pl.threads, pl.cw ? (sp.ybufs > 1 ? " + controller warp (speculative next step)" : " + controller warp") : "", pl.ept, pl.kreg ? "registers" : "L2 streams", sp.ybufs,
+             sp.ybufs > 1 ? "s" : "", pl.guard ? " + guard bands" : "", pl.smem);
     e->variant = buf;
   }
   rc = launch_diag_kernel(p, sp, pl, e->stream);
@@ -1079,8 +1097,8 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   return SEQ_OK;
 }
 
-// end-to-end call on host buffers: stage in, solve, stage out, synchronise
-static int solve_host(seq_engine* e, const seq_solve_desc* d) {
+// end-to-end call on host buffers: stage in, solve, stage out (all on the engine's stream), synchronise if asked to
+static int solve_host_one(seq_engine* e, const seq_solve_desc* d, bool sync) {
   const size_t N2 = (size_t)d->N * d->N, NN = state_elems(d), B = d->B;
   const size_t cz = sizeof(cplx);
   struct Seg { const void* src; size_t bytes; size_t off; };
@@ -1141,7 +1159,96 @@ static int solve_host(seq_engine* e, const seq_solve_desc* d) {
   if (b_sts) CUDA_TRY(e, cudaMemcpyAsync(d->states, dout + o_sts, b_sts, cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(e, cudaMemcpyAsync(d->status, dout + o_status, b_status, cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(e, cudaMemcpyAsync(d->stats, dout + o_stats, b_stats, cudaMemcpyDeviceToHost, e->stream));
-  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  if (sync) CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  return SEQ_OK;
+}
+
+// How many chunks a host-buffer solve is cut into.  One CTA per trajectory (N > 6): every chunk keeps at least two
+// waves of CTAs; thread-per-trajectory (N <= 6): at least eight full CTAs per SM.  SEQ_HOST_CHUNKS overrides.
+static int host_chunks(const seq_engine* e, const seq_solve_desc* d) {
+  const char* env = getenv("SEQ_HOST_CHUNKS");
+  long long n;
+  if (env && atoi(env) > 0) n = atoi(env);
+  else {
+    if (pick_method(e, d) == SEQ_METHOD_LARGE) return 1;
+    const long long per = d->N > 6 ? 2LL * e->sm_count : 8LL * 128 * e->sm_count;
+    n = d->B / per;
+    if (n > 4) n = 4;
+  }
+  if (n > d->B) n = d->B;
+  return n < 1 ? 1 : (int)n;
+}
+
+// Host-buffer solve: the batch is cut into chunks that alternate between two internal engines; chunk c+1's H2D
+// copies and chunk c-1's D2H copies run while chunk c integrates (the per-chunk set-up - operator analysis, spline
+// preparation - is repeated per chunk: microseconds).  Results do not depend on the chunking: trajectories are
+// independent and every chunk runs the same kernel.
+static int solve_host(seq_engine* e, const seq_solve_desc* d) {
+  const int nchunk = host_chunks(e, d);
+  e->chunks = 1;
+  if (nchunk <= 1) return solve_host_one(e, d, true);
+  for (int q = 0; q < 2; q++) {
+    if (e->sub[q]) continue;
+    CUDA_TRY(e, cudaStreamCreateWithFlags(&e->sub_stream[q], cudaStreamNonBlocking));
+    int rc = seq_engine_create(e->device, e->sub_stream[q], &e->sub[q]);
+    if (rc) return fail(e, rc, "could not create the internal engine of a chunked host solve");
+  }
+  if (!e->ev_fork) CUDA_TRY(e, cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(e, cudaEventRecord(e->ev_fork, e->stream));          // everything queued on the caller's stream comes first
+  for (int q = 0; q < 2; q++) CUDA_TRY(e, cudaStreamWaitEvent(e->sub_stream[q], e->ev_fork, 0));
+  const size_t NN = state_elems(d), cz = sizeof(cplx);
+  const size_t esz = (d->flags & SEQ_FLAG_EXPECT_COMPLEX) ? cz : sizeof(double);
+  int launches = 0, rc = SEQ_OK;
+  float ms = 0.f;
+  long long b0 = 0;
+  for (int c = 0; c < nchunk && rc == SEQ_OK; c++) {
+    const long long nb = (d->B - b0 + (nchunk - c) - 1) / (nchunk - c);
+    seq_engine* s = e->sub[c & 1];
+    if (c >= 2) {                       // the handle's counters of chunk c-2 are about to be overwritten
+      launches += s->launches;
+      float m1 = seq_engine_last_kernel_ms(s);
+      if (m1 > 0) ms += m1;
+    }
+    seq_solve_desc dd = *d;
+    dd.B = (int32_t)nb;
+    if (d->H0 && d->H0_batch_stride) dd.H0 = (const char*)d->H0 + (size_t)b0 * d->H0_batch_stride * cz;
+    if (d->coeff && d->coeff_batch_stride) dd.coeff = d->coeff + (size_t)b0 * d->coeff_batch_stride;
+    if (d->coeff_scale) dd.coeff_scale = d->coeff_scale + (size_t)b0 * d->n_ch;
+    if (d->rate && d->rate_batch_stride) dd.rate = d->rate + (size_t)b0 * d->rate_batch_stride;
+    dd.state0 = (const char*)d->state0 + (size_t)b0 * NN * cz;
+    if (d->expect) dd.expect = (char*)d->expect + (size_t)b0 * d->n_e * d->n_out * esz;
+    dd.final_state = (char*)d->final_state + (size_t)b0 * NN * cz;
+    if (d->states) dd.states = (char*)d->states + (size_t)b0 * d->n_out * NN * cz;
+    dd.status = d->status + b0;
+    dd.stats = d->stats + 4 * b0;
+    s->launches = 0;
+    s->timed = false;
+    s->comm = nullptr;
+    if (dd.n_c > 0 && dd.n_ctd > 0) {   // as in seq_engine_solve: room for the packed collapse operators
+      const size_t N2 = (size_t)dd.N * dd.N, nG0 = dd.H0_batch_stride ? (size_t)dd.B : 1;
+      rc = reserve(s, s->gbuf, (nG0 + dd.n_ch + dd.n_ctd + dd.n_c + dd.n_ctd) * N2 * sizeof(cplx));
+    }
+    if (rc == SEQ_OK) rc = solve_host_one(s, &dd, false);
+    if (rc != SEQ_OK) e->err = s->err;
+    b0 += nb;
+  }
+  for (int q = 0; q < 2; q++) {
+    cudaError_t ce = cudaStreamSynchronize(e->sub_stream[q]);
+    if (ce != cudaSuccess && rc == SEQ_OK) rc = fail(e, SEQ_ERR_CUDA, "chunked host solve failed: %s", cudaGetErrorString(ce));
+  }
+  if (rc != SEQ_OK) return rc;
+  for (int q = 0; q < 2 && q < nchunk; q++) {
+    launches += e->sub[q]->launches;
+    float m1 = seq_engine_last_kernel_ms(e->sub[q]);
+    if (m1 > 0) ms += m1;
+  }
+  e->launches = launches;
+  e->last_method = e->sub[0]->last_method;
+  char buf[64];
+  snprintf(buf, sizeof(buf), " [host solve pipelined in %d chunks]", nchunk);
+  e->variant = e->sub[0]->variant + buf;
+  e->chunks = nchunk;
+  e->chunk_ms = ms;
   return SEQ_OK;
 }
 
@@ -1151,6 +1258,7 @@ int seq_engine_solve(seq_engine* e, const seq_solve_desc* d) {
   if (rc) return rc;
   e->launches = 0;
   e->timed = false;
+  e->chunks = 1;
   if (d->B == 0) return SEQ_OK;
   CUDA_TRY(e, cudaSetDevice(e->device));
   // gbuf must also hold the packed collapse operators when both kinds are present

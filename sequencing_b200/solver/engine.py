@@ -102,6 +102,7 @@ class Engine:
         self.last_kernel_ms = -1.0
         self.last_launches = 0
         self.total_launches = 0
+        self._pinned_cache = {}
 
     @classmethod
     def get(cls, device_index: Optional[int] = None) -> "Engine":
@@ -250,11 +251,29 @@ class Engine:
             self._last_method = self.lib.seq_engine_last_method(self.handle)
         return {"out": outs, "in": tens}
 
-    def solve_host_abi(self, bp: BatchProblem) -> BatchOutput:
+    def _pinned_out(self, name, shape, dt, pinned):
+        """Output buffer of a host-ABI solve.  ``pinned``: a page-locked buffer owned by the engine and re-used by
+        the next call of the same shape (page-locking 66 MB per call would cost more than the copy it speeds up;
+        D2H into pageable memory is staged by the driver and cannot overlap the kernels of the next chunk)."""
+        if not pinned or int(np.prod(shape)) == 0:
+            return np.empty(shape, dtype=dt)
+        key = (name, tuple(shape), np.dtype(dt).str)
+        buf = self._pinned_cache.get(key)
+        if buf is None:
+            tdt = {np.float64: self.torch.float64, np.complex128: self.torch.complex128, np.int32: self.torch.int32}[dt]
+            buf = self.torch.empty(tuple(shape), dtype=tdt, pin_memory=True)
+            if len(self._pinned_cache) > 16:
+                self._pinned_cache.clear()
+            self._pinned_cache[key] = buf
+        return buf.numpy()
+
+    def solve_host_abi(self, bp: BatchProblem, pinned_out: bool = False) -> BatchOutput:
         """The reference-facing C-ABI call on HOST buffers (SEQ_FLAG_HOST_POINTERS): the engine
-        itself stages host->device, integrates, and copies results back before returning."""
+        itself stages host->device, integrates, and copies results back before returning.  Large batches
+        are pipelined in chunks (copies of one chunk behind the kernels of another).  ``pinned_out=True``
+        returns views of page-locked buffers the engine re-uses on its next call - copy what must outlive it."""
         arrs = self._host_arrays(bp)
-        outs = {name: np.empty(shape, dtype=dt) for name, (shape, dt) in self._out_shapes(bp).items()}
+        outs = {name: self._pinned_out(name, shape, dt, pinned_out) for name, (shape, dt) in self._out_shapes(bp).items()}
         ptr = {k: (v.ctypes.data if v.size else None) for k, v in arrs.items()}
         ptr.update({k: (v.ctypes.data if v.size else None) for k, v in outs.items()})
         desc = self._desc(bp, ptr, host=True)

@@ -585,3 +585,66 @@ def test_sequence_run_batch_keeps_states_on_device(gpu_engine):
                 assert np.max(np.abs(a.full() - b.full())) < 1e-12
             for a, b in zip(got.expect, ref.expect):
                 np.testing.assert_allclose(a, b, atol=1e-12)
+
+
+def test_diag_kernel_controller_warp_variant(gpu_engine):
+    """The diagonal kernel's controller-warp variant (SEQ_DIAG_CW=1, N <= 48: a 13th warp predicts the next control
+    block while the step is evaluated, the compute warps stage the next step speculatively and pick up the verdict
+    one barrier later) takes bit-identical decisions: against the FP64-FMA kernel on capped and uncapped problems
+    (rejections -> discarded speculation), with time-dependent collapse rates, and bit-for-bit against the default
+    variant on a C2-shaped sweep."""
+    import os
+    from sequencing_b200 import workloads
+    base = gpu_engine.solve(workloads.c2_selective(2, 3, sigma=10, cavity_levels=6))
+    os.environ["SEQ_DIAG_CW"] = "1"
+    try:
+        for N, w_h, w_l, n_c, n_ctd, max_step in ((7, 3, 1, 2, 0, 1.0), (20, 5, 2, 2, 1, 1.0), (31, 3, 1, 3, 0, 0.0), (45, 3, 1, 4, 0, 1.0),
+                                                  (48, 3, 1, 1, 1, 0.0)):
+            def mk():
+                bp = row_sparse_problem(N=N, B=3, n_t=12, w_h=w_h, w_l=w_l, n_ch=2, n_c=n_c, n_ctd=n_ctd, n_e=2, seed=N,
+                                        hscale=0.3 if max_step else 3.0, store_states=True)
+                bp.max_step = max_step
+                return bp
+            _match_generic(gpu_engine, mk, _lib.METHOD_DIAG, "diag", tol=1e-11)
+            forced = mk()
+            forced.method = _lib.METHOD_DIAG
+            # (N = 48: the shared-memory slots of k4..k6 do not fit next to the guarded Y buffers - the plan falls back)
+            assert "controller warp" in gpu_engine.solve(forced).variant or N == 48
+        cw = gpu_engine.solve(workloads.c2_selective(2, 3, sigma=10, cavity_levels=6))
+        assert "controller warp" in cw.variant and cw.stats[:, 3].min() > 0      # confirmed predictions
+    finally:
+        del os.environ["SEQ_DIAG_CW"]
+    np.testing.assert_array_equal(cw.final_state, base.final_state)
+    np.testing.assert_array_equal(cw.expect, base.expect)
+    np.testing.assert_array_equal(cw.stats[:, :3], base.stats[:, :3])
+
+
+def test_host_abi_chunked_pipeline_is_bit_identical(gpu_engine):
+    """Host-buffer solves of a large batch are cut into chunks that alternate between two internal engines (copies of
+    one chunk behind the kernels of the other).  Chunking must not change a bit: ragged chunk sizes, per-trajectory
+    coefficient tables / scales / rates, stored states, pinned and pageable output buffers; CTA-per-trajectory and
+    thread-per-trajectory kernels, kets."""
+    import os
+    cases = [
+        row_sparse_problem(N=12, B=7, n_t=10, w_h=3, w_l=1, n_ch=2, n_c=2, n_ctd=1, n_e=2, seed=3, hscale=0.3, store_states=True),
+        random_problem(N=4, B=11, n_t=20, n_ch=2, n_c=2, n_e=2, seed=8, hscale=0.3, store_states=True),
+        random_problem(N=9, B=5, n_t=12, n_ch=2, n_c=0, n_e=1, seed=4, hscale=0.3, ket=True),
+    ]
+    rng = np.random.default_rng(0)
+    cases[0].coeff_scale = rng.uniform(0.5, 1.5, size=(7, 2))
+    for bp in cases:
+        outs = {}
+        for chunks, pinned in (("1", False), ("3", False), ("4", True), ("2", True)):
+            os.environ["SEQ_HOST_CHUNKS"] = chunks
+            try:
+                o = gpu_engine.solve_host_abi(bp, pinned_out=pinned)
+            finally:
+                del os.environ["SEQ_HOST_CHUNKS"]
+            assert np.all(o.status == 0)
+            assert ("pipelined in %s chunks" % chunks in o.variant) == (chunks != "1")
+            outs[chunks] = {k: np.array(getattr(o, k), copy=True) for k in ("expect", "final_state", "states", "stats")}
+        dev = gpu_engine.solve(bp)
+        for chunks in ("3", "4", "2"):
+            for k in ("expect", "final_state", "states", "stats"):
+                np.testing.assert_array_equal(outs[chunks][k], outs["1"][k])
+        np.testing.assert_array_equal(outs["1"]["final_state"], dev.final_state)
