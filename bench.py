@@ -45,10 +45,21 @@ def hbm_peak():
         return 6650.0, "of fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def ncu_traffic(kernel):
-    """dram bytes read+written per launch of `kernel` from the committed ncu --set full summary, or None."""
+# the committed `ncu --set full` capture that belongs to each workload's integration kernel
+NCU_SUMMARY = {"c2": "r01_diag_c2_cw_ncu_summary.json", "c4": "r01_diag_c4_final_ncu_summary.json",
+               "c1": "r01_small_c1_ncu_summary.json", "c3": "r01_small_c3_ncu_summary.json"}
+
+
+def ncu_traffic(kernel, workload=None, rhs_evals=None):
+    """dram bytes read+written per launch of `kernel` from the committed ncu --set full summary of this workload's
+    kernel, or None.  The captures are shorter launches of the same kernel; when the summary records how many RHS
+    evaluations the captured launch made, `bytes_per_launch_scaled` scales its DRAM bytes to this launch."""
     import glob
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")), reverse=True):
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")), reverse=True)
+    pref = os.path.join(ROOT, "profiles", NCU_SUMMARY.get(workload or "", ""))
+    if os.path.isfile(pref):
+        paths = [pref] + [q for q in paths if q != pref]
+    for path in paths:
         try:
             rows = json.load(open(path))
         except Exception:
@@ -57,11 +68,18 @@ def ncu_traffic(kernel):
             if kernel in r.get("kernel", ""):
                 rd = [float(v) for k, v in r.items() if k.startswith("dram__bytes_read.sum")]
                 wr = [float(v) for k, v in r.items() if k.startswith("dram__bytes_write.sum")]
-                unit = [k for k in r if k.startswith("dram__bytes_read.sum")]
+                def scale_of(prefix):
+                    unit = [k for k in r if k.startswith(prefix)]
+                    return 1e6 if unit and "Mbyte" in unit[0] else (1e9 if unit and "Gbyte" in unit[0] else (1e3 if unit and "Kbyte" in unit[0] else 1.0))
                 if rd and wr:
-                    scale = 1e6 if unit and "Mbyte" in unit[0] else (1e9 if unit and "Gbyte" in unit[0] else (1e3 if unit and "Kbyte" in unit[0] else 1.0))
-                    return {"bytes_per_launch": (rd[0] + wr[0]) * scale, "source": os.path.relpath(path, ROOT),
-                            "note": "ncu capture of a shorter launch of the same kernel (see the file); not the bench launch"}
+                    tot = rd[0] * scale_of("dram__bytes_read.sum") + wr[0] * scale_of("dram__bytes_write.sum")
+                    out = {"bytes_per_launch": tot, "source": os.path.relpath(path, ROOT),
+                           "note": "ncu capture of a shorter launch of the same kernel (see the file); not the bench launch"}
+                    cap = r.get("capture") or {}
+                    if rhs_evals and cap.get("rhs_total"):
+                        out["bytes_per_launch_scaled"] = tot * float(rhs_evals) / float(cap["rhs_total"])
+                        out["note"] += "; bytes_per_launch_scaled = captured DRAM bytes x (RHS evaluations of this launch / of the captured one)"
+                    return out
     return None
 
 
@@ -408,14 +426,14 @@ def ours(args):
         k_ms = float(np.mean(kernel_ms))
         achieved = flops / (k_ms * 1e-3) / 1e12
         s = shape_of(bp)
-        structured_large = out_h.method == "large" and out_h.variant == "large/diagonals"
+        structured_large = out_h.method == "large" and out_h.variant.startswith("large/diagonals")
         kname = ("large_diag_rhs_kernel" if structured_large else "zgemm_dmma_kernel") if out_h.method == "large" else f"solve_{out_h.method}_kernel"
         peak_scale = world if rows_mode else 1     # rows mode: the algorithmic flops of the ONE system are spread over all GPUs
         if out_h.method == "small":
             # N <= 6: below one DMMA tile -> the HBM roofline, FP64-FMA ceiling noted
             peak, src = hbm_peak()
             gbps = bytes_alg / (k_ms * 1e-3) / 1e9
-            roof = {"bound": "hbm", "achieved": gbps, "peak": peak, "unit": "GB/s", "frac": gbps / peak, "traffic": ncu_traffic(kname),
+            roof = {"bound": "hbm", "achieved": gbps, "peak": peak, "unit": "GB/s", "frac": gbps / peak, "traffic": ncu_traffic(kname, args.workload),
                     "kernel": kname, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (total_ms / args.steps),
                     "bytes_per_trajectory": bytes_alg / s["B"], "trajectories_per_launch": s["B"], "peak_source": src,
                     "fp64_fma_algorithmic_TFLOPs": achieved, "fp64_fma_peak_TFLOPs": FP64_FMA_PEAK_TFLOPS,
@@ -423,7 +441,8 @@ def ours(args):
                             "(real superoperator form) instead of the 8 N^3 (1+2 n_c) algorithmic flops"}
         else:
             roof = {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS * peak_scale, "unit": "TFLOP/s",
-                    "frac": achieved / (FP64_DMMA_PEAK_TFLOPS * peak_scale), "traffic": ncu_traffic(kname),
+                    "frac": achieved / (FP64_DMMA_PEAK_TFLOPS * peak_scale),
+                    "traffic": ncu_traffic(kname, args.workload, float(np.sum(stats[:, 2]))),
                     "kernel": kname, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (total_ms / args.steps),
                     "flops_per_rhs": f_rhs, "rhs_evals_per_launch": float(np.sum(stats[:, 2])),
                     "peak_source": "FP64 DMMA.8x8x4 issue-rate microbenchmark tools/fp64_peak.cu on this pool's B200 "
@@ -489,7 +508,9 @@ def ours(args):
             "dtype": "c128 (f64)", "data": "synthetic",
             "config": {"workload": desc, **s, "B_per_gpu": bp.B, "atol": bp.atol, "rtol": bp.rtol, "max_step": bp.max_step,
                        "parallelism": (f"rho row-sharded x{world}, all-gather of the stage state per RHS" if rows_mode else f"batch-sharded x{world}"), "l2": "256 MiB L2 flush between timed steps; per-step scratch 300 MB > L2",
-                       "method": out_h.method, "variant": out_h.variant, "steps_accepted_mean": float(stats[:, 0].mean()), "steps_rejected_mean": float(stats[:, 1].mean())},
+                       "method": out_h.method, "variant": out_h.variant.split(" [host solve")[0],
+                       "e2e_host_pipeline": ("[host solve" + out_h.variant.split(" [host solve")[1]).strip("[]") if " [host solve" in out_h.variant else "single chunk",
+                       "steps_accepted_mean": float(stats[:, 0].mean()), "steps_rejected_mean": float(stats[:, 1].mean())},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "roofline": roof,

@@ -135,7 +135,7 @@ template <int V> struct IntTag { static constexpr int value = V; };
 // error estimate below SEQ_PROBE_ERR; keep it only while it holds the capped step with its own
 // error estimate below SEQ_STAY_ERR (otherwise 6 RHS at the capped step beat 4 RHS at a shorter one).
 #define SEQ_PROBE_ERR 0.02
-#define SEQ_STAY_ERR 0.25
+#define SEQ_STAY_ERR 0.5
 
 // ---- kernel parameter block (device pointers into caller buffers + engine scratch)
 struct SolveParams {

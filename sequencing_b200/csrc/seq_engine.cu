@@ -853,13 +853,13 @@ static int diag_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, 
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   const char* env = getenv("SEQ_DIAG_CL");
   const char* cap = getenv("SEQ_DIAG_SMEM_CAP");
-  // SEQ_DIAG_CW=1: controller-warp variant (N <= 48).  Opt-in: measured neutral on the C2 sweep (5 % faster on
-  // trajectories that stay on the capped 4(3) pair, 4 % slower on those that keep returning to the 5(4) pair - the
-  // 13th warp costs the compute warps 40 registers), see DESIGN.md 4.1b
+  // SEQ_DIAG_CW=0: no controller warp (N <= 48 runs with one by default: 5 % faster on trajectories that stay on the
+  // capped 4(3) pair, 4 % slower on those that keep returning to the 5(4) pair - the 13th warp costs the compute
+  // warps 40 registers; 3 % faster on the C2 sweep), see DESIGN.md 4.1b
   const char* cw = getenv("SEQ_DIAG_CW");
   int max_smem = e->max_smem_optin;
   if (cap && atoi(cap) > 0 && atoi(cap) < max_smem) max_smem = atoi(cap);
-  *usable = diag_plan(N, n_g, d->n_c, d->n_ctd, d->n_ch, d->n_t, nnzE, h.data(), max_smem, env ? atoi(env) : 0, cw && atoi(cw) == 1, pl);
+  *usable = diag_plan(N, n_g, d->n_c, d->n_ctd, d->n_ch, d->n_t, nnzE, h.data(), max_smem, env ? atoi(env) : 0, !(cw && atoi(cw) == 0), pl);
   return SEQ_OK;
 }
 

@@ -588,14 +588,19 @@ def test_sequence_run_batch_keeps_states_on_device(gpu_engine):
 
 
 def test_diag_kernel_controller_warp_variant(gpu_engine):
-    """The diagonal kernel's controller-warp variant (SEQ_DIAG_CW=1, N <= 48: a 13th warp predicts the next control
+    """The diagonal kernel's controller-warp variant (the default for N <= 48, SEQ_DIAG_CW=0 switches it off: a 13th warp predicts the next control
     block while the step is evaluated, the compute warps stage the next step speculatively and pick up the verdict
     one barrier later) takes bit-identical decisions: against the FP64-FMA kernel on capped and uncapped problems
     (rejections -> discarded speculation), with time-dependent collapse rates, and bit-for-bit against the default
     variant on a C2-shaped sweep."""
     import os
     from sequencing_b200 import workloads
-    base = gpu_engine.solve(workloads.c2_selective(2, 3, sigma=10, cavity_levels=6))
+    os.environ["SEQ_DIAG_CW"] = "0"
+    try:
+        base = gpu_engine.solve(workloads.c2_selective(2, 3, sigma=10, cavity_levels=6))
+    finally:
+        del os.environ["SEQ_DIAG_CW"]
+    assert "controller warp" not in base.variant
     os.environ["SEQ_DIAG_CW"] = "1"
     try:
         for N, w_h, w_l, n_c, n_ctd, max_step in ((7, 3, 1, 2, 0, 1.0), (20, 5, 2, 2, 1, 1.0), (31, 3, 1, 3, 0, 0.0), (45, 3, 1, 4, 0, 1.0),

@@ -28,7 +28,8 @@ def subset(idx):
         s.coeff_scale = bp.coeff_scale[idx]
     return s
 
-for name, idx in (("cheapest 148", order[:148]), ("most expensive 148", order[-148:]), ("first 592 in order", np.arange(592))):
+for name, idx in (("cheapest 148", order[:148]), ("most expensive 148", order[-148:]), ("first 592 in order", np.arange(592)),
+                  ("all 1024", np.arange(1024))):
     sb = subset(idx)
     for cw in ("1", "0"):
         os.environ["SEQ_DIAG_CW"] = cw
