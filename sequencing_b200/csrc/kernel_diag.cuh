@@ -136,7 +136,6 @@ struct DiagCtrl {
   int emit_lo, emit_hi;   // outputs [emit_lo, emit_hi) are produced from the committed state
   int cvbuf;          // which buffer of spline values belongs to this step (controller-warp variant)
   int valid;          // prediction slot: a prediction was made
-  int verdict;        // actual slot: the prediction published before was confirmed - use it instead of this block
 };
 
 // controller state, kept in shared memory between calls (warp 0 only)
@@ -246,7 +245,6 @@ __device__ __noinline__ void diag_controller(const SolveParams& p, DiagCtlState*
     ctrl->emit_hi = emit_hi;
     ctrl->cvbuf = cvbuf;
     ctrl->valid = 0;
-    ctrl->verdict = 0;
     S->nstA = nstA;
     S->ctl = ctl;
     S->htry = c_htry; S->target = c_target;
@@ -280,6 +278,19 @@ __device__ __noinline__ bool diag_verify(const SolveParams& p, const DiagCtlStat
   return same;
 }
 
+// Sufficient condition for diag_verify to confirm a prediction, cheap enough for the critical path (no square roots,
+// no divisions).  The step being judged ran on the 4(3) pair at a capped size and was not preceded by a rejection;
+// es <= (0.49 N)^2 means err <= 0.49 < SEQ_STAY_ERR with a margin far above the rounding of the exact expression.
+// Then ctl_update accepts, keeps the pair (probe_backoff = 1), and proposes h = htry * min(10, 0.9 err^(-1/4)) >=
+// 1.07 htry >= max_step (third line).  Two error sums that both pass therefore lead to the same controller state up to
+// h, and h does not bind: exactly what diag_verify checks.
+__device__ __forceinline__ bool diag_fast_state_ok(const SolveParams& p, const DiagCtlState* S) {
+  return S->ctl.pair == 1 && S->capped != 0 && !S->ctl.prev_rejected && S->ctl.status == SEQ_STATUS_OK && SEQ_STAY_ERR >= 0.49 &&
+         p.max_step > 0 && S->nst + 1 <= p.nsteps && S->htry * 1.05 >= p.max_step &&
+         p.max_step >= 1e-10 * fmax(1.0, fabs(S->target) + fabs(S->ctl.t) + S->htry);
+}
+__device__ __forceinline__ bool diag_fast_es_ok(double es, double es_max) { return es >= 0.0 && es <= es_max; }
+
 // named barriers of the controller-warp variant (0 is __syncthreads)
 #define DIAG_BAR_STAGE 1   // compute warps only
 #define DIAG_BAR_LAST 2    // last stage of a step: compute warps + controller (publishes the prediction)
@@ -287,10 +298,9 @@ __device__ __noinline__ bool diag_verify(const SolveParams& p, const DiagCtlStat
 #define DIAG_BAR_VERDICT 4 // the controller arrives with the verdict / the actual control block, compute warps wait
 #define DIAG_BAR_ALL 5     // compute warps + controller (set-up)
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id, int count) {
-  __threadfence_block();
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
+// (producer side of the PTX ISA's bar.arrive / bar.sync example: shared-memory stores before the arrive are visible to
+// the threads that bar.sync on the same barrier - no fence in between)
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // threads per CTA by (elements per thread, stage vectors in registers): 65536 registers / threads, allocated per 4 warps
 // Inner loops over a thread's elements run in chunks of at most 3 with a compiler barrier in between: the loads
@@ -579,8 +589,9 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
     }
   };
 
-  static_assert(sizeof(DiagCtrl) <= 64 && sizeof(DiagCtlState) <= 192, "control blocks outgrew their shared-memory slots");
+  static_assert(sizeof(DiagCtrl) <= 56 && sizeof(DiagCtlState) <= 192, "control blocks outgrew their shared-memory slots");
   DiagCtrl* ctrl_pred = (DiagCtrl*)(smem_diag + L.off_ctrl + 64);
+  volatile int* verdict = (volatile int*)(smem_diag + L.off_ctrl + 56);      // in the padding behind the actual control block
   DiagCtlState* cst = (DiagCtlState*)(smem_diag + L.off_ctrl + 128);
   if (tid == (CW ? nth : 0)) {      // (CW: first lane of the controller warp)
     StepCtl c0;
@@ -600,11 +611,16 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
     DiagCtlState* Sp = (DiagCtlState*)(smem_diag + L.off_ctrl + 128 + 192);
     int cur = 0, ctog = 0;       // spline-value buffer of the step being evaluated; toggle of the partial-sum buffer
     double es_prev = 0.0;        // the prediction assumes the error estimate of the previous step
-    while (true) {
-      const int cmd = ctrl->cmd;
-      const int nrhs = (ctrl->pair ? 5 : 7) - ctrl->st0;
-      __syncwarp();
-      if (cmd) break;
+    bool inconsistent = false;
+#ifdef SEQ_PROFILE_REGIONS
+    unsigned long long _pc = clock64();     // controller-warp regions 8..11 (CTA 0): predict, wait, verify, publish
+#define PROFC(r) do { if (lane == 0 && blockIdx.x == 0) { unsigned long long _n = clock64(); seq_prof[r] += _n - _pc; _pc = _n; } } while (0)
+#else
+#define PROFC(r)
+#endif
+    int cmd = ctrl->cmd, nrhs = (ctrl->pair ? 5 : 7) - ctrl->st0;      // of the step being evaluated
+    __syncwarp();
+    while (!cmd) {
       // prediction: the controller on a copy of the state, with the error estimate of the previous step
       const bool predict = p.max_step > 0 && S->ctl.status == SEQ_STATUS_OK;
       if (predict) {
@@ -615,29 +631,53 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       if (lane == 0) ctrl_pred->valid = (predict && ctrl_pred->accepted && ctrl_pred->st0 == 1) ? 1 : 0;
       __syncwarp();
       const bool valid = ctrl_pred->valid != 0;
+      const int p_cmd = ctrl_pred->cmd, p_nrhs = (ctrl_pred->pair ? 5 : 7) - ctrl_pred->st0;
+      // Steady state of a capped sweep: the step runs on the 4(3) pair at the capped size and both the previous and the
+      // new error estimate are below the stay threshold with a margin.  Then the accept/reject logic provably ends in
+      // the predicted state (accepted, pair kept, proposal above the cap - see diag_fast_state_ok), so the verdict goes out
+      // right after the block sum and the exact bookkeeping (the proposal h) follows off the critical path.
+      const double es_max = 0.2401 * (double)p.N * (double)p.N;
+      const bool fast_prev = valid && diag_fast_state_ok(p, S) && diag_fast_es_ok(es_prev, es_max);
       __threadfence_block();
+      PROFC(8);
       bar_sync(DIAG_BAR_LAST, nall);
       bar_sync(DIAG_BAR_ERR, nall);
+      PROFC(9);
       double es = (lane < nw) ? red[ctog * 32 + lane] : 0.0;
       es = warp_sum(es);
       ctog ^= 1;
+      const bool fast = fast_prev && diag_fast_es_ok(es, es_max);
+      if (fast) {
+        if (lane == 0) *verdict = 1;
+        bar_arrive(DIAG_BAR_VERDICT, nall);
+      }
+      PROFC(10);
       es_prev = es;
-      const bool ok = valid && diag_verify(p, S, Sp, nrhs, es);
+      bool ok = valid && diag_verify(p, S, Sp, nrhs, es);
+      if (fast && !ok) { inconsistent = true; ok = true; }     // cannot happen (the fast conditions imply diag_verify): reported below
       if (ok) {
-        if (lane == 0) { *ctrl = *ctrl_pred; ctrl->verdict = 1; }
         DiagCtlState* t = S; S = Sp; Sp = t;
         cur ^= 1;
+        cmd = p_cmd; nrhs = p_nrhs;
 #ifndef SEQ_PROFILE_REGIONS
         if (lane == 0) S->dbg += 1;      // stats[3]: confirmed predictions
 #endif
+        if (!fast) {
+          if (lane == 0) *verdict = 1;
+          bar_arrive(DIAG_BAR_VERDICT, nall);
+        }
       } else {
         diag_controller(p, S, ctrl, cv + cur * L.cvstride, tabc, tabr, cscale, 1, nrhs, es, cur);
+        __syncwarp();
+        cmd = ctrl->cmd; nrhs = (ctrl->pair ? 5 : 7) - ctrl->st0;
+        if (lane == 0) *verdict = 0;
+        bar_arrive(DIAG_BAR_VERDICT, nall);
       }
       __syncwarp();
-      bar_arrive(DIAG_BAR_VERDICT, nall);
+      PROFC(11);
     }
     if (lane == 0) {
-      p.status[b] = S->ctl.status;
+      p.status[b] = inconsistent ? SEQ_STATUS_NONFINITE : S->ctl.status;     // a fast verdict the exact check rejected: fail loudly
       p.stats[b * 4 + 0] = S->ctl.nacc;
       p.stats[b * 4 + 1] = S->ctl.nrej;
       p.stats[b * 4 + 2] = S->ctl.nrhs;
@@ -780,7 +820,7 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       PROF(6);
       bar_sync(DIAG_BAR_VERDICT, nall);
       PROF(7);
-      if (pc.valid && ctrl->verdict) {
+      if (pc.valid && *verdict) {
         c = pc;
         if (spec) {
           commit();

@@ -45,7 +45,9 @@ names = {0: "commit + outputs (Tr(E rho), stores)", 1: "stage combine + Y write 
          4: "error estimate", 5: "error block sum (barrier)", 6: "controller (warp 0: step control, spline values) - call overhead", 7: "step barrier",
          8: "  controller: state load", 9: "  controller: ctl_update (pow)", 10: "  controller: output bookkeeping + ctl_next", 11: "  controller: spline values", 12: "  controller: state store"}
 if "controller warp" in out.variant:
-    names.update({5: "error partial sums handed to the controller warp", 6: "speculative outputs + first stage input of the next step", 7: "wait for the verdict"})
+    names.update({5: "error partial sums handed to the controller warp", 6: "speculative outputs + first stage input of the next step", 7: "wait for the verdict",
+                  8: "  controller warp: prediction of the next control block", 9: "  controller warp: waiting for the step (last stage + error sums)",
+                  10: "  controller warp: block sum + verification", 11: "  controller warp: publish verdict", 12: "  -"})
 print(out.variant)
 tot = cyc[:8].sum() if "controller warp" in out.variant else cyc.sum()
 d = out.stats[:, 3]
