@@ -1018,7 +1018,7 @@ static inline bool diag_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, int n
   o.wsm = 0;
   o.nct = pl->threads;
   if (pl->cw && pl->kreg) {             // 13 warps: 128 registers per thread - the static weights move to shared memory
-    o.wsm = 3 * pl->ept * pl->threads * c;      // k4, k5, k6
+    o.wsm = 3 * pl->ept * pl->threads * c;      // k4, k5, k6 (k3 as well would be 1 % faster on C2 but no longer fits next to larger operator tables)
     if (diag_layout(N, n_g, n_t, o).total > max_smem) { o.wsm = 0; pl->cw = false; }
   }
   pl->smem = (size_t)diag_layout(N, n_g, n_t, o).total;
