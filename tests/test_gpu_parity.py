@@ -653,3 +653,54 @@ def test_host_abi_chunked_pipeline_is_bit_identical(gpu_engine):
             for k in ("expect", "final_state", "states", "stats"):
                 np.testing.assert_array_equal(outs[chunks][k], outs["1"][k])
         np.testing.assert_array_equal(outs["1"]["final_state"], dev.final_state)
+
+
+def test_diag_kernel_failure_statuses_match_generic(gpu_engine):
+    """Integration failures inside the diagonal kernel - with its controller warp (prediction / fast verdict paths) and
+    without: more than `nsteps` internal steps per output interval, on capped steps (three capped steps per interval
+    against nsteps = 2: the fast-verdict regime must see the limit) and on uncapped ones, and a non-finite state.
+    Status and step counts must equal the FP64-FMA kernel's."""
+    import os
+    def run(mk):
+        outs = []
+        for cw in ("1", "0"):
+            os.environ["SEQ_DIAG_CW"] = cw
+            try:
+                a = mk()
+                a.method = _lib.METHOD_DIAG
+                outs.append(gpu_engine.solve(a))
+                assert outs[-1].method == "diag" and ("controller warp" in outs[-1].variant) == (cw == "1")
+            finally:
+                del os.environ["SEQ_DIAG_CW"]
+        g = mk()
+        g.method = _lib.METHOD_GENERIC
+        outs.append(gpu_engine.solve(g))
+        return outs
+
+    def capped():
+        bp = row_sparse_problem(N=12, B=3, n_t=8, w_h=3, w_l=1, n_ch=2, n_c=2, n_e=2, seed=21, hscale=0.05)
+        bp.max_step, bp.nsteps = bp.dt / 3, 2
+        return bp
+
+    def uncapped():
+        bp = row_sparse_problem(N=12, B=3, n_t=8, w_h=3, w_l=1, n_ch=2, n_c=2, n_e=2, seed=22, hscale=30.0)
+        bp.max_step, bp.nsteps = 0.0, 3
+        return bp
+
+    def nonfinite():
+        bp = row_sparse_problem(N=12, B=3, n_t=8, w_h=3, w_l=1, n_ch=2, n_c=2, n_e=2, seed=23, hscale=0.3)
+        bp.state0 = bp.state0.copy()
+        bp.state0[1, 0, 0] = np.nan
+        return bp
+
+    for mk, expect in ((capped, _lib.STATUS_MAX_STEPS), (uncapped, _lib.STATUS_MAX_STEPS), (nonfinite, None)):
+        cw, nocw, gen = run(mk)
+        np.testing.assert_array_equal(cw.status, gen.status)
+        np.testing.assert_array_equal(nocw.status, gen.status)
+        np.testing.assert_array_equal(cw.stats[:, :3], gen.stats[:, :3])
+        np.testing.assert_array_equal(nocw.stats[:, :3], gen.stats[:, :3])
+        if expect is not None:
+            assert np.all(gen.status == expect)
+        else:
+            assert gen.status[1] == _lib.STATUS_NONFINITE and gen.status[0] == 0 and gen.status[2] == 0
+            np.testing.assert_array_equal(cw.final_state[[0, 2]], nocw.final_state[[0, 2]])
