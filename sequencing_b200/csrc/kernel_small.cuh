@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(64) solve_small_kernel(const __grid_constant__
             }
           }
         const double err = sqrt(es / (double)D);
-        if (ctl_update(ctl, p, err, htry, landing, capped, t_target, nst)) {
+        if (ctl_update<true>(ctl, p, err, htry, landing, capped, t_target, nst)) {
 #pragma unroll
           for (int i = 0; i < D; i++) { y[i] = ys[i]; k[0][i] = k[S - 1][i]; }
         }
