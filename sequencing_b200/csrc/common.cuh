@@ -178,6 +178,21 @@ __device__ __forceinline__ double spline_eval(const double2* __restrict__ tab, i
   return te * (a.y * te * te + (a.x - a.y)) + tb * (b.y * tb * tb + (b.x - b.y));
 }
 
+// The same with a precomputed 1/dt (thread-per-trajectory kernel: 12 evaluations per step and lane, an FP64 division
+// each).  x can differ from (t - t0) / dt by an ulp; at a knot that at most selects the neighbouring interval at its
+// end point, where the C2 spline has the same value.
+__device__ __forceinline__ double spline_eval_inv(const double2* __restrict__ tab, int n_t, double t0, double inv_dt, double t) {
+  double x = (t - t0) * inv_dt;
+  if (x <= 0.0) return tab[0].x;
+  if (x >= (double)(n_t - 1)) return tab[n_t - 1].x;
+  int p = (int)x;
+  double tb = x - (double)p;
+  double te = 1.0 - tb;
+  double2 a = tab[p];
+  double2 b = tab[p + 1];
+  return te * (a.y * te * te + (a.x - a.y)) + tb * (b.y * tb * tb + (b.x - b.y));
+}
+
 // ---- block-wide sum; `scratch` holds >= 33 doubles.  Result is returned to every thread.
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(64) solve_small_kernel(const __grid_constant__
   const double2* tabr = p.tab_rate + (long long)b * p.tab_bstride_r;
   const double* cscale = p.coeff_scale ? p.coeff_scale + (long long)b * p.n_ch : nullptr;
 
+  const double inv_dt = 1.0 / p.dt;
   // out = (M_0 + sum_m c_m(t) M_m) xin
   auto rhs = [&](double t, const double (&xin)[D], double (&out)[D]) {
 #pragma unroll
@@ -136,10 +137,10 @@ __global__ void __launch_bounds__(64) solve_small_kernel(const __grid_constant__
       if (m > 0) {
         const int g = m - 1;
         if (g < p.n_ch) {
-          cm = spline_eval(tabc + (long long)g * p.n_t, p.n_t, p.t0, p.dt, t);
+          cm = spline_eval_inv(tabc + (long long)g * p.n_t, p.n_t, p.t0, inv_dt, t);
           if (cscale) cm *= cscale[g];
         } else {
-          cm = spline_eval(tabr + (long long)(g - p.n_ch) * p.n_t, p.n_t, p.t0, p.dt, t);
+          cm = spline_eval_inv(tabr + (long long)(g - p.n_ch) * p.n_t, p.n_t, p.t0, inv_dt, t);
         }
       }
       const double* Mm = Ms + m * D * DP;
