@@ -51,6 +51,9 @@ struct seq_engine {
   seq_engine* sub[2] = {nullptr, nullptr};
   cudaStream_t sub_stream[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr;
+  cudaStream_t aux = nullptr;       // second stream: the cluster launch of a partial last wave runs next to the main launch
+  cudaEvent_t ev_aux0 = nullptr, ev_aux1 = nullptr;
+  bool is_sub = false;              // an internal engine of a chunked host solve (its launches overlap the other one's)
   int chunks = 1;                   // chunks of the last host-buffer solve
   float chunk_ms = 0.f;             // their integration kernels' durations, summed
 };
@@ -424,6 +427,9 @@ int seq_engine_destroy(seq_engine* e) {
     if (e->sub_stream[q]) cudaStreamDestroy(e->sub_stream[q]);
   }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->aux) cudaStreamDestroy(e->aux);
+  if (e->ev_aux0) cudaEventDestroy(e->ev_aux0);
+  if (e->ev_aux1) cudaEventDestroy(e->ev_aux1);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   delete e;
@@ -837,7 +843,9 @@ static int launch_sparse(seq_engine* e, const seq_solve_desc* d, SolveParams& p,
 }
 
 // Diagonal structure of the operators (device flags -> host plan).  One D2H copy + synchronisation.
-static int diag_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, const cplx* Gk, const cplx* Lall, int nnzE, DiagPlan* pl, bool* usable) {
+// `tail`: a second plan (2-CTA clusters per trajectory) for the last partial wave of a launch, see launch_diag
+static int diag_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, const cplx* Gk, const cplx* Lall, int nnzE, DiagPlan* pl, bool* usable,
+                        DiagPlan* tail, bool* tail_ok) {
   const int N = d->N, n_g = d->n_ch + d->n_ctd, n_l = d->n_c + d->n_ctd;
   const size_t W = 2 * (size_t)N - 1, nflag = (size_t)(2 + n_l) * W;
   *usable = false;
@@ -860,10 +868,20 @@ static int diag_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, 
   int max_smem = e->max_smem_optin;
   if (cap && atoi(cap) > 0 && atoi(cap) < max_smem) max_smem = atoi(cap);
   *usable = diag_plan(N, n_g, d->n_c, d->n_ctd, d->n_ch, d->n_t, nnzE, h.data(), max_smem, env ? atoi(env) : 0, !(cw && atoi(cw) == 0), pl);
+  *tail_ok = false;
+  const int rest = d->B % e->sm_count;
+  if (*usable && pl->cl == 1 && !e->is_sub && !getenv("SEQ_DIAG_NO_TAIL") && d->B > e->sm_count && rest > 0 && 2 * rest <= e->sm_count && N >= 16)
+    *tail_ok = diag_plan(N, n_g, d->n_c, d->n_ctd, d->n_ch, d->n_t, nnzE, h.data(), max_smem, 2, false, tail) && tail->cl == 2 && tail->kreg;
   return SEQ_OK;
 }
 
-static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, const cplx* G0, const cplx* Gk, const SparseInfo& info, DiagPlan& pl) {
+// One CTA per trajectory and one CTA per SM: a batch that is not a multiple of the SM count ends in a partial wave
+// during which most SMs idle (C4: 512 trajectories = 3.46 waves on 148 SMs).  When that rest is at most half a wave
+// its trajectories run on 2-CTA clusters instead (`tail`): both halves of the GPU work on them and the wave takes
+// ~0.63 of the time.  The cluster variant sums the error norm in a different order, so a tail trajectory agrees with
+// the others to rounding (1e-13), not bit for bit; SEQ_DIAG_NO_TAIL=1 switches the split off.
+static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, const cplx* G0, const cplx* Gk, const SparseInfo& info, DiagPlan& pl,
+                       DiagPlan* tail) {
   const int N = d->N, n_g = p.n_g, n_l = p.n_c + p.n_ctd, n_e = p.n_e;
   // expectation operators as COO lists (layout shared with the ELL kernel), operator diagonals behind them
   SparsePlan epl;
@@ -909,6 +927,44 @@ static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, c
              pl.threads, pl.cw ? (sp.ybufs > 1 ? " + controller warp (speculative next step)" : " + controller warp") : "", pl.ept, pl.kreg ? "registers" : "L2 streams", sp.ybufs,
              sp.ybufs > 1 ? "s" : "", pl.guard ? " + guard bands" : "", pl.smem);
     e->variant = buf;
+  }
+  if (tail) {
+    const long long nt = d->B % e->sm_count, b1 = d->B - nt;
+    SolveParams p1 = p, p2 = p;
+    p1.B = (int)b1;
+    p2.B = (int)nt;
+    p2.tab = p.tab + b1 * p.tab_bstride_c;
+    p2.tab_rate = p.tab_rate + b1 * p.tab_bstride_r;
+    if (p.coeff_scale) p2.coeff_scale = p.coeff_scale + b1 * p.n_ch;
+    p2.state0 = p.state0 + b1 * N * N;
+    if (p.expect) p2.expect = (char*)p.expect + (size_t)b1 * p.n_e * p.n_out * ((p.flags & SEQ_FLAG_EXPECT_COMPLEX) ? sizeof(cplx) : sizeof(double));
+    p2.final_state = p.final_state + b1 * N * N;
+    if (p.states) p2.states = p.states + b1 * (long long)p.n_out * N * N;
+    p2.status = p.status + b1;
+    p2.stats = p.stats + 4 * b1;
+    p2.ws_stride = 0;
+    DiagOps& sp2 = tail->ops;
+    sp2.e_off = sp.e_off; sp2.e_ij = sp.e_ij; sp2.e_val = sp.e_val;
+    sp2.g0 = sp.g0; sp2.gk = sp.gk; sp2.lam = sp.lam; sp2.gdiag = sp.gdiag; sp2.lreal = sp.lreal;
+    // the clusters go first, on a second stream, so that they find pairs of free SMs; the main launch fills the rest of
+    // the GPU and both drain together (one stream would put a grid-wide barrier between the main launch and the tail)
+    if (!e->aux) {
+      CUDA_TRY(e, cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
+      CUDA_TRY(e, cudaEventCreateWithFlags(&e->ev_aux0, cudaEventDisableTiming));
+      CUDA_TRY(e, cudaEventCreateWithFlags(&e->ev_aux1, cudaEventDisableTiming));
+    }
+    CUDA_TRY(e, cudaEventRecord(e->ev_aux0, e->stream));
+    CUDA_TRY(e, cudaStreamWaitEvent(e->aux, e->ev_aux0, 0));
+    rc = launch_diag_kernel(p2, sp2, *tail, e->aux);
+    if (rc == SEQ_OK) rc = launch_diag_kernel(p1, sp, pl, e->stream);
+    if (rc) return fail(e, rc, "diagonal kernel launch configuration failed for N=%d (tail split)", N);
+    CUDA_TRY(e, cudaEventRecord(e->ev_aux1, e->aux));
+    CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_aux1, 0));
+    e->launches += 2;
+    char buf[96];
+    snprintf(buf, sizeof(buf), "; last %lld trajectories on 2-CTA clusters x %d threads", nt, tail->threads);
+    e->variant += buf;
+    return SEQ_OK;
   }
   rc = launch_diag_kernel(p, sp, pl, e->stream);
   if (rc) return fail(e, rc, "diagonal kernel launch configuration failed for N=%d", N);
@@ -1006,13 +1062,14 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
 
   // ---- operator sparsity decides between the sparse (FMA) and the dense (tensor-core) formulation
   SparseInfo spi;
-  DiagPlan dpl;
+  DiagPlan dpl, dpl_tail;
+  bool tail_ok = false;
   if (try_sparse) {
     rc = sparse_analyze(e, d, G0, Gk, Lall, &spi);
     if (rc) return rc;
     bool diag_ok = false;
     if (method != SEQ_METHOD_SPARSE) {
-      rc = diag_analyze(e, d, G0, Gk, Lall, spi.plan.nnzE, &dpl, &diag_ok);
+      rc = diag_analyze(e, d, G0, Gk, Lall, spi.plan.nnzE, &dpl, &diag_ok, &dpl_tail, &tail_ok);
       if (rc) return rc;
     }
     if (method == SEQ_METHOD_SPARSE) {
@@ -1067,7 +1124,7 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
     rc = launch_sparse(e, d, p, G0, Gk, spi);
     if (rc) return rc;
   } else if (method == SEQ_METHOD_DIAG) {
-    rc = launch_diag(e, d, p, G0, Gk, spi, dpl);
+    rc = launch_diag(e, d, p, G0, Gk, spi, dpl, tail_ok ? &dpl_tail : nullptr);
     if (rc) return rc;
   } else if (method == SEQ_METHOD_GENERIC) {
     size_t elems = ket ? (size_t)N : N2;
@@ -1192,6 +1249,7 @@ static int solve_host(seq_engine* e, const seq_solve_desc* d) {
     CUDA_TRY(e, cudaStreamCreateWithFlags(&e->sub_stream[q], cudaStreamNonBlocking));
     int rc = seq_engine_create(e->device, e->sub_stream[q], &e->sub[q]);
     if (rc) return fail(e, rc, "could not create the internal engine of a chunked host solve");
+    e->sub[q]->is_sub = true;
   }
   if (!e->ev_fork) CUDA_TRY(e, cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   CUDA_TRY(e, cudaEventRecord(e->ev_fork, e->stream));          // everything queued on the caller's stream comes first

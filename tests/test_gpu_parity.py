@@ -704,3 +704,34 @@ def test_diag_kernel_failure_statuses_match_generic(gpu_engine):
         else:
             assert gen.status[1] == _lib.STATUS_NONFINITE and gen.status[0] == 0 and gen.status[2] == 0
             np.testing.assert_array_equal(cw.final_state[[0, 2]], nocw.final_state[[0, 2]])
+
+
+def test_diag_kernel_tail_wave_on_clusters(gpu_engine):
+    """A batch that ends in at most half a wave of CTAs runs that rest on 2-CTA clusters (both launches in one solve):
+    every trajectory - main launch and tail - against the FP64-FMA kernel, register-resident and streamed main
+    variants; SEQ_DIAG_NO_TAIL=1 and batches without a partial wave keep the single launch."""
+    import os
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for N, w_h, n_c, n_ctd in ((20, 3, 2, 1), (64, 3, 2, 0)):
+        B = sms + 9
+        mk = lambda: row_sparse_problem(N=N, B=B, n_t=6, w_h=w_h, w_l=1, n_ch=2, n_c=n_c, n_ctd=n_ctd, n_e=2, seed=N, hscale=0.3, store_states=True)
+        a, g = mk(), mk()
+        a.method, g.method = _lib.METHOD_DIAG, _lib.METHOD_GENERIC
+        oa, og = gpu_engine.solve(a), gpu_engine.solve(g)
+        assert "last 9 trajectories on 2-CTA clusters" in oa.variant, oa.variant
+        assert np.all(oa.status == 0)
+        for k in ("states", "final_state", "expect"):
+            assert np.max(np.abs(getattr(oa, k) - getattr(og, k))) < 1e-12, (N, k)
+        np.testing.assert_array_equal(oa.stats[:, :2], og.stats[:, :2])
+        os.environ["SEQ_DIAG_NO_TAIL"] = "1"
+        try:
+            ob = gpu_engine.solve(a)
+        finally:
+            del os.environ["SEQ_DIAG_NO_TAIL"]
+        assert "clusters" not in ob.variant
+        assert np.max(np.abs(ob.final_state - oa.final_state)) < 1e-12
+        np.testing.assert_array_equal(ob.final_state[:sms], oa.final_state[:sms])      # the main launch is the same kernel
+    full = row_sparse_problem(N=20, B=sms, n_t=4, w_h=3, w_l=1, n_ch=2, n_c=2, n_e=1, seed=1, hscale=0.3)
+    full.method = _lib.METHOD_DIAG
+    assert "clusters" not in gpu_engine.solve(full).variant
