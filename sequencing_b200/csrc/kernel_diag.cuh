@@ -326,8 +326,9 @@ namespace cg = cooperative_groups;
 // outputs and stage the first RHS input of the predicted next step into the free Y / G(t) buffers (double-buffered
 // Y only), and pick up the verdict at that stage's barrier.  A wrong prediction (rejected step, order switch, a
 // binding step-size proposal) discards the staged input and takes the controller's actual block - decisions are
-// bit-identical to the variant without the controller warp.  With CW the register budget is 128 (13 warps: one scheduler holds four), so
-// k5 / k6 - used by the 5(4) pair only - and the static weights move to thread-private slots in shared memory.
+// bit-identical to the variant without the controller warp.  With CW the register budget is 128 (13 warps: one
+// scheduler holds four), so k4 .. k6 (k5 / k6 are used by the 5(4) pair only) move to thread-private slots in shared
+// memory; y, the static weights and k1 .. k3 stay in registers.
 template <int EPT, int CL, bool GUARD, bool KREG, bool CW>
 __global__ void __launch_bounds__((KREG ? DIAG_MAXT : DIAG_MAXT_STREAM) + (CW ? 32 : 0), 1)
 solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__ DiagOps sp) {
@@ -1017,7 +1018,7 @@ static inline bool diag_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, int n
   pl->cw = allow_cw && pl->cl == 1 && pl->kreg;
   o.wsm = 0;
   o.nct = pl->threads;
-  if (pl->cw && pl->kreg) {             // 13 warps: 128 registers per thread - the static weights move to shared memory
+  if (pl->cw && pl->kreg) {             // 13 warps: 128 registers per thread - k4 .. k6 move to shared memory
     o.wsm = 3 * pl->ept * pl->threads * c;      // k4, k5, k6 (k3 as well would be 1 % faster on C2 but no longer fits next to larger operator tables)
     if (diag_layout(N, n_g, n_t, o).total > max_smem) { o.wsm = 0; pl->cw = false; }
   }
