@@ -24,8 +24,7 @@ struct GenericCtx {
 // G(t) = G0 + sum_m g_m(t) Gk[m]  -> ctx.G ; leaves coefficient values in ctx.cval
 __device__ __forceinline__ void build_G(const GenericCtx& c, double t) {
   const SolveParams& p = *c.p;
-  if ((int)threadIdx.x < p.n_g) {
-    int m = threadIdx.x;
+  for (int m = threadIdx.x; m < p.n_g; m += blockDim.x) {      // (up to 64 terms on as few as 32 threads)
     double v;
     if (m < p.n_ch) {
       v = spline_eval(c.tabc + (long long)m * p.n_t, p.n_t, p.t0, p.dt, t);

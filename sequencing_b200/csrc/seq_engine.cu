@@ -364,6 +364,18 @@ static int validate(seq_engine* e, const seq_solve_desc* d) {
   return SEQ_OK;
 }
 
+// out_idx: strictly increasing sample indices inside [0, n_t) - the kernels index the spline tables and the output
+// arrays with them.  Checked on the host copy (host-pointer solves) or after one small D2H copy (device pointers).
+static int validate_out_idx(seq_engine* e, const int32_t* idx, int n_out, int n_t, bool has_tables) {
+  for (int o = 0; o < n_out; o++) {
+    if (idx[o] < 0 || (has_tables && idx[o] >= n_t))
+      return fail(e, SEQ_ERR_INVALID, "out_idx[%d] = %d is outside the coefficient grid [0, %d)", o, idx[o], n_t);
+    if (o > 0 && idx[o] <= idx[o - 1])
+      return fail(e, SEQ_ERR_INVALID, "out_idx must be strictly increasing (out_idx[%d] = %d after %d)", o, idx[o], idx[o - 1]);
+  }
+  return SEQ_OK;
+}
+
 static int pick_method(const seq_engine* e, const seq_solve_desc* d) {
   if (d->method != SEQ_METHOD_AUTO) return d->method;
   const bool ket = d->flags & SEQ_FLAG_KET;
@@ -1319,6 +1331,18 @@ int seq_engine_solve(seq_engine* e, const seq_solve_desc* d) {
   e->chunks = 1;
   if (d->B == 0) return SEQ_OK;
   CUDA_TRY(e, cudaSetDevice(e->device));
+  {
+    const bool has_tables = d->n_ch + d->n_ctd > 0;
+    if (d->flags & SEQ_FLAG_HOST_POINTERS) {
+      rc = validate_out_idx(e, d->out_idx, d->n_out, d->n_t, has_tables);
+    } else {
+      std::vector<int32_t> h((size_t)d->n_out);
+      CUDA_TRY(e, cudaMemcpyAsync(h.data(), d->out_idx, h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+      CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+      rc = validate_out_idx(e, h.data(), d->n_out, d->n_t, has_tables);
+    }
+    if (rc) return rc;
+  }
   // gbuf must also hold the packed collapse operators when both kinds are present
   if (d->n_c > 0 && d->n_ctd > 0) {
     size_t N2 = (size_t)d->N * d->N;

@@ -128,10 +128,15 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
 
 
-def make_comm(group=None):
+def make_comm(group=None, stream=None):
     """``seq_comm`` hooks backed by torch.distributed (NCCL): the engine calls them with device
-    pointers while it enqueues the stepper on torch's current stream, so the collectives are ordered
-    with the kernels.  Returns (comm, keepalive) - keep ``keepalive`` referenced during the solve."""
+    pointers while it enqueues the stepper on ITS stream (the one captured when the ``Engine`` was
+    created), so the hooks issue the collectives under ``torch.cuda.stream(stream)`` - ordered with the
+    engine's kernels whatever torch's current stream is at call time.  ``stream``: the engine's
+    ``torch.cuda.Stream`` (``Engine.stream``); None = torch's current stream.
+    Returns (comm, keepalive) - keep ``keepalive`` referenced during the solve."""
+    import contextlib
+
     import torch
     import torch.distributed as dist
 
@@ -143,9 +148,13 @@ def make_comm(group=None):
     def _wrap(ptr, n):
         return torch.as_tensor(_DevArray(ptr, n), device=torch.device("cuda", torch.cuda.current_device()))
 
+    def _on_stream():
+        return torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+
     def all_gather(ctx, send, recv, count):
         try:
-            dist.all_gather_into_tensor(_wrap(recv, count * world), _wrap(send, count), group=group)
+            with _on_stream():
+                dist.all_gather_into_tensor(_wrap(recv, count * world), _wrap(send, count), group=group)
             stats["all_gather"] += 1
             stats["bytes_gathered"] += 8 * count * world
             return 0
@@ -155,7 +164,8 @@ def make_comm(group=None):
 
     def all_reduce(ctx, buf, count):
         try:
-            dist.all_reduce(_wrap(buf, count), group=group)
+            with _on_stream():
+                dist.all_reduce(_wrap(buf, count), group=group)
             stats["all_reduce"] += 1
             return 0
         except Exception as exc:
@@ -179,7 +189,7 @@ def solve_rows_sharded(bp: BatchProblem, engine=None, group=None) -> BatchOutput
     engine = engine or Engine.get(torch.cuda.current_device())
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return engine.solve_rows_sharded(bp, None)
-    comm, keep = make_comm(group)
+    comm, keep = make_comm(group, stream=engine.stream)
     out = engine.solve_rows_sharded(bp, comm)
     out.comm_stats = keep[2]
     return out

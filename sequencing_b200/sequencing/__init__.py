@@ -1,7 +1,7 @@
 """Pulse-sequence construction and the solve boundary (reference: ``sequencing/sequencing/``)."""
 from .channels import HamiltonianChannels
 from .compiled import CompiledPulseSequence
-from .containers import PulseSequence, Sequence, SequenceResult, tqdm
+from .containers import PulseSequence, Sequence, SequenceResult, run_sequences, tqdm
 from .ops import (
     CTerm,
     DelayChannelsOperation,

@@ -124,6 +124,8 @@ class _Lowered:
     dims: list
     options: Options
     store_states: bool
+    state_herm: bool = True
+    e_herm: Optional[List[bool]] = None
 
     def signature(self):
         ops = (self.H0, *self.Hk, *self.Lc, *self.Ltd, *self.E)
@@ -138,14 +140,27 @@ def _is_td(term):
     return isinstance(term, (list, tuple)) and len(term) == 2 and isinstance(term[0], qt.Qobj)
 
 
-def _uniform_grid(grid):
+def _uniform_grid(grid, need_uniform=True):
+    """(t0, dt, n_t) of a uniformly spaced grid.  A constant problem (no array coefficients) may come with any
+    increasing ``tlist`` (qutip.mesolve accepts that): it is then placed on the finest uniform grid that holds
+    every output time, or ``ValueError`` if there is none within 2**20 points."""
     grid = np.asarray(grid, dtype=float)
     if grid.size < 2:
         return float(grid[0]) if grid.size else 0.0, 1.0, int(grid.size)
     steps = np.diff(grid)
-    if not np.allclose(steps, steps[0], rtol=1e-9, atol=1e-12):
+    if np.allclose(steps, steps[0], rtol=1e-9, atol=1e-12):
+        return float(grid[0]), float(steps[0]), int(grid.size)
+    if need_uniform:
         raise ValueError("array coefficients need a uniformly spaced time grid")
-    return float(grid[0]), float(steps[0]), int(grid.size)
+    if np.any(steps <= 0):
+        raise ValueError("tlist must be strictly increasing")
+    smin = float(steps.min())
+    for k in range(1, 65):          # the smallest spacing, or a simple fraction of it, as the grid step
+        dt = smin / k
+        pos = (grid - grid[0]) / dt
+        if pos[-1] < (1 << 20) and np.all(np.abs(pos - np.rint(pos)) <= 1e-7):
+            return float(grid[0]), dt, int(np.rint(pos[-1])) + 1
+    raise ValueError("tlist is not commensurate with a uniform grid of <= 2**20 points")
 
 
 def _lower(H, rho0, tlist, c_ops, e_ops, options) -> _Lowered:
@@ -157,7 +172,8 @@ def _lower(H, rho0, tlist, c_ops, e_ops, options) -> _Lowered:
         if isinstance(H, qt.Qobj):
             H = [H]
     tlist = np.asarray(tlist, dtype=float)
-    t0, dt, n_t = _uniform_grid(grid)
+    has_arrays = any(_is_td(term) for term in H) or any(_is_td(term) for term in (c_ops or []))
+    t0, dt, n_t = _uniform_grid(grid, need_uniform=has_arrays)
     if not isinstance(rho0, qt.Qobj):
         raise TypeError("initial state must be a Qobj")
     c_ops = list(c_ops or [])
@@ -225,7 +241,8 @@ def _lower(H, rho0, tlist, c_ops, e_ops, options) -> _Lowered:
         raise ValueError("tlist must be strictly increasing")
     store_states = bool(options.store_states) or not e_ops
     return _Lowered(H0, Hk, coeff, Lc, Ltd, rate, state0, is_ket, E, e_real, t0, dt, n_t,
-                    out_idx.astype(np.int32), tlist, dims, options, store_states)
+                    out_idx.astype(np.int32), tlist, dims, options, store_states, state_herm,
+                    [bool(e.isherm) for e in e_ops])
 
 
 def _stack(ops, N):
@@ -279,12 +296,20 @@ class _Deferral:
     def __init__(self):
         self.items: List[_Lowered] = []
         self.results: List[Result] = []
+        self.combos = []
 
     def add(self, it: _Lowered) -> Result:
         res = Result()
         res._pending = True
         self.items.append(it)
         self.results.append(res)
+        return res
+
+    def add_split(self, part_p: _Lowered, part_q: _Lowered) -> Result:
+        """A non-Hermitian initial operator: two Hermitian trajectories, recombined when the batch has run."""
+        res = Result()
+        res._pending = True
+        self.combos.append((res, self.add(part_p), self.add(part_q)))
         return res
 
     def groups(self):
@@ -303,7 +328,9 @@ class _Deferral:
             out = _solve_maybe_sharded(_to_batch(items))
             for b, i in enumerate(idxs):
                 _fill(self.results[i], self.items[i], out, b)
-        self.items, self.results = [], []
+        for res, rp, rq in self.combos:
+            _combine_parts(res, rp, rq)
+        self.items, self.results, self.combos = [], [], []
 
 
 def _solve_maybe_sharded(bp: BatchProblem) -> BatchOutput:
@@ -341,10 +368,45 @@ def deferred_solves(execute=True):
         d.flush()
 
 
+def _hermitian_parts(it: _Lowered):
+    """Every density-matrix kernel integrates a HERMITIAN operator (the right-hand side is evaluated as
+    ``A + A^dag`` and only one triangle is kept).  The Lindblad map is complex-linear, so a non-Hermitian
+    initial operator X is evolved as its two Hermitian parts, X = P + iQ with P = (X + X^dag)/2 and
+    Q = (X - X^dag)/(2i), and recombined: rho(t) = P(t) + i Q(t), Tr(E rho) = Tr(E P) + i Tr(E Q)."""
+    import dataclasses
+
+    X = it.state0
+    P = 0.5 * (X + X.conj().T)
+    Q = -0.5j * (X - X.conj().T)
+    herm = list(it.e_herm) if it.e_herm is not None else [False] * len(it.E)
+    return (dataclasses.replace(it, state0=P, e_real=herm, state_herm=True),
+            dataclasses.replace(it, state0=Q, e_real=herm, state_herm=True))
+
+
+def _combine_parts(res: Result, rp: Result, rq: Result):
+    res.solver, res.times = rp.solver, rp.times
+    res.num_expect, res.num_collapse = rp.num_expect, rp.num_collapse
+    res.expect = [np.asarray(a, dtype=complex) + 1j * np.asarray(b, dtype=complex) for a, b in zip(rp.expect, rq.expect)]
+    res.states = [qt.Qobj(a.full() + 1j * b.full(), dims=a.dims) for a, b in zip(rp.states, rq.states)]
+    res.final_state = qt.Qobj(rp.final_state.full() + 1j * rq.final_state.full(), dims=rp.final_state.dims)
+    res.stats = rp.stats
+    res._pending = False
+
+
 def mesolve(H, rho0, tlist, c_ops=None, e_ops=None, args=None, options=None, progress_bar=None, _safe_mode=True):
     """Drop-in for ``qutip.mesolve`` on the input forms the reference produces."""
     options = options or Options()
     it = _lower(H, rho0, tlist, c_ops, e_ops, options)
+    if not it.is_ket and not it.state_herm:
+        parts = _hermitian_parts(it)
+        if _active:
+            return _active[-1].add_split(*parts)
+        out = Engine.get().solve(_to_batch(list(parts)))
+        rp, rq, res = Result(), Result(), Result()
+        _fill(rp, parts[0], out, 0)
+        _fill(rq, parts[1], out, 1)
+        _combine_parts(res, rp, rq)
+        return res
     if _active:
         return _active[-1].add(it)
     out = Engine.get().solve(_to_batch([it]))
@@ -395,21 +457,43 @@ def propagator(H, t, c_op_list=None, args=None, options=None, unitary_mode="batc
         # out.states: [N(batch n), n_out, N] -> U_t[:, n]
         props = [qt.Qobj(out.states[:, k, :].T.copy(), dims=dims) for k in range(len(tlist))]
     else:
-        basis_ops = []
-        for j in range(N):
-            for i in range(N):  # column-stacking order: index = i + j*N
+        # Hermitian operator basis (the kernels integrate Hermitian operators only): D_i = |i><i|,
+        # S_ij = |i><j| + |j><i|, T_ij = -i (|i><j| - |j><i|) for i < j, so |i><j| = (S_ij + i T_ij) / 2 and
+        # |j><i| = (S_ij - i T_ij) / 2.  N^2 trajectories, one launch; columns recombined below.
+        basis, where = [], {}
+        for i in range(N):
+            m = np.zeros((N, N), dtype=complex)
+            m[i, i] = 1.0
+            where[("D", i)] = len(basis)
+            basis.append(qt.Qobj(m, dims=dims))
+        for i in range(N):
+            for j in range(i + 1, N):
                 m = np.zeros((N, N), dtype=complex)
-                m[i, j] = 1.0
-                basis_ops.append(qt.Qobj(m, dims=dims))
-        items = [_lower(H, b, tlist, c_ops, [], opt) for b in basis_ops]
+                m[i, j] = m[j, i] = 1.0
+                where[("S", i, j)] = len(basis)
+                basis.append(qt.Qobj(m, dims=dims))
+                m = np.zeros((N, N), dtype=complex)
+                m[i, j], m[j, i] = -1j, 1j
+                where[("T", i, j)] = len(basis)
+                basis.append(qt.Qobj(m, dims=dims))
+        items = [_lower(H, b, tlist, c_ops, [], opt) for b in basis]
         out = Engine.get().solve(_to_batch(items))
         if np.any(out.status != _lib.STATUS_OK):
             raise Exception(ODE_ERROR)
         sdims = [dims, dims]
         props = []
         for k in range(len(tlist)):
-            cols = [out.states[n, k].ravel(order="F") for n in range(N * N)]
-            props.append(qt.Qobj(np.stack(cols, axis=1), dims=[[N * N], [N * N]]))
+            sup = np.zeros((N * N, N * N), dtype=complex)
+            for j in range(N):
+                for i in range(N):      # column-stacking order: column index = i + j*N holds vec_F(evolved |i><j|)
+                    if i == j:
+                        ev = out.states[where[("D", i)], k]
+                    elif i < j:
+                        ev = 0.5 * (out.states[where[("S", i, j)], k] + 1j * out.states[where[("T", i, j)], k])
+                    else:
+                        ev = 0.5 * (out.states[where[("S", j, i)], k] - 1j * out.states[where[("T", j, i)], k])
+                    sup[:, i + j * N] = ev.ravel(order="F")
+            props.append(qt.Qobj(sup, dims=[[N * N], [N * N]]))
             props[-1].superdims = sdims
     if len(tlist) == 1:
         return props[0]

@@ -32,3 +32,43 @@ def gpu_engine():
     from sequencing_b200.solver import Engine
 
     return Engine.get(0)
+
+
+class _RecordingEngine:
+    """The real CUDA engine with the OracleEngine's bookkeeping (how many launches, how large)."""
+
+    def __init__(self, eng):
+        self._eng = eng
+        self.calls = 0
+        self.batch_sizes = []
+
+    def solve(self, bp, *a, **kw):
+        self.calls += 1
+        self.batch_sizes.append(bp.B)
+        return self._eng.solve(bp, *a, **kw)
+
+    def __getattr__(self, name):
+        return getattr(self._eng, name)
+
+
+@pytest.fixture(params=["oracle", pytest.param("cuda", marks=pytest.mark.gpu)])
+def kat_engine(request, monkeypatch):
+    """The reference's known-answer tests run twice: through the CPU oracle (``-m "not gpu"``: pins the host
+    mirror and the oracle) and through the REAL CUDA engine (``-m gpu``: the reference's own acceptance
+    thresholds on the product path)."""
+    from sequencing_b200.solver import engine as engine_mod
+
+    if request.param == "oracle":
+        from helpers import OracleEngine
+
+        fake = OracleEngine()
+        monkeypatch.setattr(engine_mod.Engine, "get", classmethod(lambda cls, device_index=None: fake))
+        return fake
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    real = engine_mod.Engine.get(0)
+    rec = _RecordingEngine(real)
+    monkeypatch.setattr(engine_mod.Engine, "get", classmethod(lambda cls, device_index=None: rec))
+    return rec

@@ -182,3 +182,80 @@ def scattered_sparse_problem(N, B, n_t, seed=0, **kw):
     if bp.Ltd is not None and bp.Ltd.shape[0]:
         bp.Ltd = np.stack([0.2 * perm() for _ in bp.Ltd])
     return bp
+
+
+# ---- sampled parity against the oracle (tests/test_parity_sampled.py and bench.py's `parity` block) ----------
+def take_one(bp: BatchProblem, b: int) -> BatchProblem:
+    """Trajectory ``b`` of a BatchProblem as a one-trajectory problem (small enough to pickle to a worker)."""
+    import copy
+
+    out = copy.copy(bp)
+    out.state0 = np.ascontiguousarray(bp.state0[b:b + 1])
+    if bp.coeff is not None and bp.coeff.shape[0] > 1:
+        out.coeff = np.ascontiguousarray(bp.coeff[b:b + 1])
+    if bp.rate is not None and bp.rate.shape[0] > 1:
+        out.rate = np.ascontiguousarray(bp.rate[b:b + 1])
+    if bp.coeff_scale is not None:
+        out.coeff_scale = np.ascontiguousarray(bp.coeff_scale[b:b + 1])
+    if bp.H0.ndim == 3 and bp.H0.shape[0] > 1:
+        out.H0 = np.ascontiguousarray(bp.H0[b])
+    return out
+
+
+def _oracle_task(args):
+    """Worker: one trajectory through the oracle at (atol, rtol).  Returns (final_state, expect[n_e, n_out])."""
+    one, atol, rtol = args
+    r = oracle_solve(one, 0, atol=atol, rtol=rtol, nsteps=max(int(one.nsteps), 1000000 if atol < 1e-9 else 1000))
+    n_e = one.E.shape[0] if one.E is not None else 0
+    ex = np.stack([np.asarray(r.expect[m]) for m in range(n_e)]) if n_e else np.zeros((0, len(one.out_idx)))
+    return np.asarray(r.final_state), ex
+
+
+def oracle_many(bp: BatchProblem, idx, tolerances, workers=None):
+    """``{(atol, rtol): [(final_state, expect), ...]}`` for trajectories ``idx`` of ``bp``, computed by a pool of
+    SPAWNED worker processes (the parent may hold a CUDA context; the workers never touch CUDA)."""
+    import concurrent.futures as cf
+    import multiprocessing as mp
+
+    tasks = [(take_one(bp, int(b)), a, r) for (a, r) in tolerances for b in idx]
+    workers = workers or min(len(tasks), os.cpu_count() or 1)
+    if workers <= 1:
+        res = [_oracle_task(t) for t in tasks]
+    else:
+        with cf.ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn")) as ex:
+            res = list(ex.map(_oracle_task, tasks, chunksize=1))
+    out, k = {}, 0
+    for tol in tolerances:
+        out[tuple(tol)] = res[k:k + len(idx)]
+        k += len(idx)
+    return out
+
+
+def parity_fractions(bp: BatchProblem, idx, engine_outputs, oracle_outputs, tol=1e-6):
+    """Per tolerance pair: the fraction of sampled OUTPUTS (one final state + n_e expectation traces per
+    trajectory) within ``tol`` of the oracle - final state by trace distance (kets: projector distance),
+    expectation traces by max-abs error - plus the worst values."""
+    rep = {}
+    for key, refs in oracle_outputs.items():
+        out = engine_outputs[key]
+        n_ok = n_all = 0
+        n_traj_ok = 0
+        worst_td = worst_ee = 0.0
+        for q, b in enumerate(idx):
+            fin, ex = refs[q]
+            td = trace_distance(out.final_state[b], fin.reshape(out.final_state[b].shape))
+            ok_traj = td <= tol
+            n_ok += int(td <= tol); n_all += 1
+            worst_td = max(worst_td, td)
+            for m in range(ex.shape[0]):
+                ee = float(np.max(np.abs(out.expect[b, m] - (np.real(ex[m]) if not np.iscomplexobj(out.expect) else ex[m]))))
+                n_ok += int(ee <= tol); n_all += 1
+                ok_traj = ok_traj and ee <= tol
+                worst_ee = max(worst_ee, ee)
+            n_traj_ok += int(ok_traj)
+        rep["atol=%g,rtol=%g" % key] = {
+            "outputs_within_tol": n_ok, "outputs": n_all, "fraction": n_ok / max(n_all, 1),
+            "trajectories_within_tol": n_traj_ok, "trajectories": len(idx),
+            "worst_trace_distance": worst_td, "worst_expect_abs_err": worst_ee, "tol": tol,
+        }
+    return rep

@@ -1,0 +1,71 @@
+"""Sampled parity at the named workloads' sizes: >= 64 trajectories per config spread over
+the sweep (the far-detuned C2 corner rows included), the CUDA engine against the CPU oracle at MATCHED atol/rtol.
+
+* strict assertion, no allowance: at the loosest matched tolerance where the oracle (ZVODE-Adams) is itself
+  converged to < 1e-7 - 1e-10/1e-8 for C1 / C3 / C4, 1e-12/1e-10 for C2 (at 1e-10/1e-8 ZVODE is still 4.7e-6 from
+  the converged solution on C2's 1000-sample pulses) - EVERY sampled output (final-state trace
+  distance and expectation-trace max-abs error) is within 1e-6;
+* at the reference's DEFAULT tolerances (1e-8/1e-6) the pass fraction is measured and printed, not asserted to
+  a fixed number: there the distance is the reference integrator's own error (tests/test_gpu_parity.py
+  attributes it against a converged run);
+* both fractions are written to ``gpurun_out/parity_<config>.json`` (copied to ``profiles/``) and the same
+  block is emitted by ``bench.py`` (``parity``).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import oracle_many, parity_fractions
+
+pytestmark = pytest.mark.gpu
+
+DEFAULT = (1e-8, 1e-6)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _spread(B, n=64):
+    return np.unique(np.round(np.linspace(0, B - 1, n)).astype(int))
+
+
+def _c2_grid_idx(n_amp=32, n_det=32, k=8):
+    ia = np.unique(np.round(np.linspace(0, n_amp - 1, k)).astype(int))
+    idt = np.unique(np.round(np.linspace(0, n_det - 1, k)).astype(int))      # includes the far-detuned rows
+    return np.array([a * n_det + d for a in ia for d in idt])
+
+
+def _cases():
+    from sequencing_b200 import workloads
+    return {
+        "c1": (lambda: workloads.c1_rabi(4096), lambda bp: _spread(bp.B), (1e-10, 1e-8)),
+        "c3": (lambda: workloads.c3_drag(512), lambda bp: (np.arange(64) * 47) % bp.B, (1e-10, 1e-8)),
+        "c2": (lambda: workloads.c2_selective(32, 32), lambda bp: _c2_grid_idx(), (1e-12, 1e-10)),
+        "c4": (lambda: workloads.c4_two_transmons_bus(128), lambda bp: _spread(bp.B), (1e-10, 1e-8)),
+    }
+
+
+@pytest.mark.parametrize("name", ["c1", "c3", "c2", "c4"])
+def test_sampled_parity(gpu_engine, name):
+    make, pick, strict = _cases()[name]
+    bp = make()
+    idx = pick(bp)
+    assert len(idx) >= 64, len(idx)
+    outs = {}
+    for atol, rtol in (DEFAULT, strict):
+        bp.atol, bp.rtol = atol, rtol
+        outs[(atol, rtol)] = gpu_engine.solve(bp)
+        assert np.all(outs[(atol, rtol)].status == 0)
+    bp.atol, bp.rtol = DEFAULT
+    refs = oracle_many(bp, idx, [DEFAULT, strict])
+    rep = parity_fractions(bp, idx, outs, refs)
+    rep = {"config": name, "N": bp.N, "B": bp.B, "sampled": len(idx), "method": outs[DEFAULT].method,
+           "default": rep["atol=%g,rtol=%g" % DEFAULT], "strict": rep["atol=%g,rtol=%g" % strict],
+           "strict_tolerances": {"atol": strict[0], "rtol": strict[1]}}
+    print("PARITY", json.dumps(rep))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"parity_{name}.json"), "w") as f:
+        json.dump(rep, f, indent=1)
+    s = rep["strict"]
+    assert s["fraction"] == 1.0, rep
+    assert s["worst_trace_distance"] <= 1e-6 and s["worst_expect_abs_err"] <= 1e-6, rep

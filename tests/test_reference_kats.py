@@ -1,7 +1,11 @@
 """The reference's own known-answer tests for the hot path, run through the
-host API mirror with the CPU oracle standing in for the GPU (tests only).  They pin BOTH the host
-mirror (System/Mode/pulses/channel compiler/calibration sweeps) and the oracle: these are the
-only result pins the reference holds for this path (it has no golden vectors)."""
+host API mirror twice (fixture ``kat_engine``): with the CPU oracle standing in for the GPU
+(``-m "not gpu"``: pins the host mirror - System/Mode/pulses/channel compiler/calibration sweeps -
+and the oracle; these are the only result pins the reference holds for this path, it has no golden
+vectors) and with the REAL CUDA engine behind the same calls (``-m gpu``: the reference's own
+acceptance thresholds - pi-pulse infidelity < 1e-10, fitted T1 within 0.1 ns with time-dependent
+collapse coefficients over 10 040 samples, propagator vs run < 5e-9, displacement infidelity
+< 1e-7 - on the product path)."""
 import numpy as np
 import pytest
 
@@ -13,7 +17,7 @@ from sequencing_b200.sequencing import CompiledPulseSequence, PulseSequence, Syn
 from sequencing_b200.solver import Result
 
 
-def test_rabi_two_levels(oracle_engine):
+def test_rabi_two_levels(kat_engine):
     """test_calibration.py:16-31: amp converges < 1e-5, pi-pulse infidelity < 1e-10."""
     qubit = Transmon("qubit", levels=2)
     system = System("system", modes=[qubit])
@@ -22,7 +26,7 @@ def test_rabi_two_levels(oracle_engine):
         _, old_amp, new_amp = tune_rabi(system, qubit.fock(0), progbar=False, plot=False)
     assert abs(old_amp - new_amp) < 1e-5
     # every sweep was ONE batched engine call of 51 trajectories
-    assert set(oracle_engine.batch_sizes) == {51}
+    assert set(kat_engine.batch_sizes) == {51}
     init = qubit.fock(0)
     seq = get_sequence(system)
     qubit.rotate_x(np.pi)
@@ -31,7 +35,7 @@ def test_rabi_two_levels(oracle_engine):
     assert abs(1 - fidelity) < 1e-10
 
 
-def test_drag(oracle_engine):
+def test_drag(kat_engine):
     """test_calibration.py:41-61: 3-level transmon, kerr -0.2 GHz."""
     qubit = Transmon("qubit", levels=3, kerr=-200e-3)
     qubit.gaussian_pulse.sigma = 10
@@ -41,7 +45,7 @@ def test_drag(oracle_engine):
     assert abs(old_amp - new_amp) < 1e-7
     _, old_drag, new_drag = tune_drag(system, qubit.fock(0), update=True, progbar=False, plot=False)
     assert abs(new_drag) > 1e-3
-    assert oracle_engine.batch_sizes[-1] == 42   # 21 drag values x 2 sequences in one launch
+    assert kat_engine.batch_sizes[-1] == 42   # 21 drag values x 2 sequences in one launch
     init = qubit.fock(0)
     seq = get_sequence(system)
     qubit.rotate_x(np.pi)
@@ -50,7 +54,7 @@ def test_drag(oracle_engine):
     assert abs(1 - fidelity) < 1e-5
 
 
-def test_displacement(oracle_engine):
+def test_displacement(kat_engine):
     """test_calibration.py:65-79: cavity(12) displacement calibration, infidelity < 1e-7."""
     cavity = Cavity("cavity", levels=12)
     system = System("system", modes=[cavity])
@@ -65,7 +69,7 @@ def test_displacement(oracle_engine):
     assert abs(1 - fidelity) < 1e-7
 
 
-def test_pulse_sequence_and_propagator(oracle_engine):
+def test_pulse_sequence_and_propagator(kat_engine):
     """test_sequencing.py:122-193: sizes, Result type, propagator vs run < 5e-9."""
     qubit = Transmon("qubit", levels=2)
     pulse_len = qubit.gaussian_pulse.sigma * qubit.gaussian_pulse.chop
@@ -92,7 +96,7 @@ def test_pulse_sequence_and_propagator(oracle_engine):
     assert isinstance(cseq.run(qubit.fock(0)), Result)
 
 
-def test_dynamic_collapse_operators(oracle_engine):
+def test_dynamic_collapse_operators(kat_engine):
     """test_sequencing.py:195-257: fitted T1 within 0.1 ns, static and time-dependent CTerm."""
     qubit = Transmon("qubit", levels=2)
     qubit.t1 = 1000
@@ -138,7 +142,7 @@ def test_dynamic_collapse_operators(oracle_engine):
         assert abs(fit_tau(res.expect[0], t0) - pulsed) < 0.1
 
 
-def test_sequence_with_unitaries(oracle_engine):
+def test_sequence_with_unitaries(kat_engine):
     """test_sequencing.py:343-408: interleaved pulses and instantaneous unitaries, N=30."""
     qubit = Transmon("qubit", levels=3, kerr=-200e-3)
     cavity = Cavity("cavity", levels=10, kerr=-10e-6)
@@ -168,7 +172,7 @@ def test_sequence_with_unitaries(oracle_engine):
     assert qt.fidelity(props[-1] * init, qubit.Rx(np.pi) * init) ** 2 > 0.9995
 
 
-def test_rotations_grid(oracle_engine):
+def test_rotations_grid(kat_engine):
     """test_rotations.py: pulsed rotate(theta, phi) vs Raxis, F > 0.999 (3x3 of the 11x11 grid)."""
     qubit = Transmon("qubit", levels=2)
     system = System("system", modes=[qubit])
