@@ -231,31 +231,44 @@ def oracle_many(bp: BatchProblem, idx, tolerances, workers=None):
     return out
 
 
-def parity_fractions(bp: BatchProblem, idx, engine_outputs, oracle_outputs, tol=1e-6):
+def _fraction_report(idx, get_a, get_b, tol):
+    """Outputs (one final state + n_e expectation traces per trajectory) of a within ``tol`` of b."""
+    n_ok = n_all = n_traj_ok = 0
+    worst_td = worst_ee = 0.0
+    for q, b in enumerate(idx):
+        fa, ea = get_a(q, b)
+        fb, eb = get_b(q, b)
+        td = trace_distance(fa, np.asarray(fb).reshape(np.asarray(fa).shape))
+        ok_traj = td <= tol
+        n_ok += int(td <= tol); n_all += 1
+        worst_td = max(worst_td, td)
+        for m in range(len(eb)):
+            ee = float(np.max(np.abs(np.asarray(ea[m]) - np.asarray(eb[m])))) if np.iscomplexobj(ea) else float(np.max(np.abs(np.real(ea[m]) - np.real(eb[m]))))
+            n_ok += int(ee <= tol); n_all += 1
+            ok_traj = ok_traj and ee <= tol
+            worst_ee = max(worst_ee, ee)
+        n_traj_ok += int(ok_traj)
+    return {"outputs_within_tol": n_ok, "outputs": n_all, "fraction": n_ok / max(n_all, 1),
+            "trajectories_within_tol": n_traj_ok, "trajectories": len(idx),
+            "worst_trace_distance": worst_td, "worst_expect_abs_err": worst_ee, "tol": tol}
+
+
+def parity_fractions(bp: BatchProblem, idx, engine_outputs, oracle_outputs, tol=1e-6, converged=None):
     """Per tolerance pair: the fraction of sampled OUTPUTS (one final state + n_e expectation traces per
-    trajectory) within ``tol`` of the oracle - final state by trace distance (kets: projector distance),
-    expectation traces by max-abs error - plus the worst values."""
+    trajectory) of the engine within ``tol`` of the oracle AT THE SAME atol/rtol - final state by trace distance
+    (kets: projector distance), expectation traces by max-abs error - plus the worst values.  ``converged``: the
+    tolerance pair whose oracle run is converged (< 1e-7 from the exact solution); every other pair then also gets
+    ``engine_vs_converged`` and ``oracle_vs_converged`` - who is how far from the exact solution at that pair."""
     rep = {}
     for key, refs in oracle_outputs.items():
         out = engine_outputs[key]
-        n_ok = n_all = 0
-        n_traj_ok = 0
-        worst_td = worst_ee = 0.0
-        for q, b in enumerate(idx):
-            fin, ex = refs[q]
-            td = trace_distance(out.final_state[b], fin.reshape(out.final_state[b].shape))
-            ok_traj = td <= tol
-            n_ok += int(td <= tol); n_all += 1
-            worst_td = max(worst_td, td)
-            for m in range(ex.shape[0]):
-                ee = float(np.max(np.abs(out.expect[b, m] - (np.real(ex[m]) if not np.iscomplexobj(out.expect) else ex[m]))))
-                n_ok += int(ee <= tol); n_all += 1
-                ok_traj = ok_traj and ee <= tol
-                worst_ee = max(worst_ee, ee)
-            n_traj_ok += int(ok_traj)
-        rep["atol=%g,rtol=%g" % key] = {
-            "outputs_within_tol": n_ok, "outputs": n_all, "fraction": n_ok / max(n_all, 1),
-            "trajectories_within_tol": n_traj_ok, "trajectories": len(idx),
-            "worst_trace_distance": worst_td, "worst_expect_abs_err": worst_ee, "tol": tol,
-        }
+        eng = lambda q, b, out=out: (out.final_state[b], out.expect[b])
+        orc_ = lambda q, b, refs=refs: refs[q]
+        r = _fraction_report(idx, eng, orc_, tol)
+        if converged is not None and tuple(converged) != tuple(key):
+            conv = oracle_outputs[tuple(converged)]
+            cv = lambda q, b, conv=conv: conv[q]
+            r["engine_vs_converged"] = _fraction_report(idx, eng, cv, tol)
+            r["oracle_vs_converged"] = _fraction_report(idx, orc_, cv, tol)
+        rep["atol=%g,rtol=%g" % key] = r
     return rep

@@ -6,8 +6,10 @@ the sweep (the far-detuned C2 corner rows included), the CUDA engine against the
   the converged solution on C2's 1000-sample pulses) - EVERY sampled output (final-state trace
   distance and expectation-trace max-abs error) is within 1e-6;
 * at the reference's DEFAULT tolerances (1e-8/1e-6) the pass fraction is measured and printed, not asserted to
-  a fixed number: there the distance is the reference integrator's own error (tests/test_gpu_parity.py
-  attributes it against a converged run);
+  a fixed number: there the distance is the reference integrator's own error - attributed in the same record by
+  comparing BOTH default-tolerance results with the converged (strict) oracle run: ``engine_vs_converged`` and
+  ``oracle_vs_converged``; the engine's default-tolerance outputs must be at least as close to the converged
+  run as the oracle's (asserted on the pass fractions);
 * both fractions are written to ``gpurun_out/parity_<config>.json`` (copied to ``profiles/``) and the same
   block is emitted by ``bench.py`` (``parity``).
 """
@@ -58,7 +60,7 @@ def test_sampled_parity(gpu_engine, name):
         assert np.all(outs[(atol, rtol)].status == 0)
     bp.atol, bp.rtol = DEFAULT
     refs = oracle_many(bp, idx, [DEFAULT, strict])
-    rep = parity_fractions(bp, idx, outs, refs)
+    rep = parity_fractions(bp, idx, outs, refs, converged=strict)
     rep = {"config": name, "N": bp.N, "B": bp.B, "sampled": len(idx), "method": outs[DEFAULT].method,
            "default": rep["atol=%g,rtol=%g" % DEFAULT], "strict": rep["atol=%g,rtol=%g" % strict],
            "strict_tolerances": {"atol": strict[0], "rtol": strict[1]}}
@@ -66,6 +68,8 @@ def test_sampled_parity(gpu_engine, name):
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"parity_{name}.json"), "w") as f:
         json.dump(rep, f, indent=1)
+    d = rep["default"]
+    assert d["engine_vs_converged"]["fraction"] >= d["oracle_vs_converged"]["fraction"], rep
     s = rep["strict"]
     assert s["fraction"] == 1.0, rep
     assert s["worst_trace_distance"] <= 1e-6 and s["worst_expect_abs_err"] <= 1e-6, rep

@@ -64,7 +64,7 @@ def _check_nonhermitian_and_propagator(engine_kind):
     ref = _oracle_final(bp, X)
     assert np.max(np.abs(res.states[-1].full() - ref)) < 2e-8
     assert np.iscomplexobj(res.expect[0])
-    assert abs(res.expect[0][-1] - np.trace(E.full() @ ref)) < 2e-8
+    assert abs(res.expect[0][-1] - np.trace(E.full() @ ref)) < 2e-7        # (|E|_F ~ 17)
     assert abs(res.expect[0][0] - np.trace(E.full() @ X)) < 1e-12
     # (2) propagator with collapse operators = column-stacked superoperator: acts on vec_F(X)
     props = cseq.propagator(options=opt)
