@@ -162,162 +162,8 @@ class Sequence(ValidatedList):
         segment boundaries (``main.py:333-335``) come from ``seq_engine_expect`` - nothing but the boundary
         states' expectation values and the final states crosses PCIe.  Returns one ``SequenceResult`` per state
         (times / states / expect at the segment boundaries, exactly what ``full_evolution=False`` keeps)."""
-        return run_sequences([self] * len(list(init_states)), init_states, e_ops=e_ops, options=options)
-
-    def propagator(self, c_ops=None, options=None, unitary_mode="batch", parallel=False, progress_bar=None):
-        if all(isinstance(op, SyncOperation) for op in self):
-            return [self.system.I()]
-        return self.compile().propagator(c_ops=c_ops, options=options, unitary_mode=unitary_mode, parallel=parallel)
-
-    def plot_coefficients(self, subplots=True, plot_imag=False, step=False):
-        return self.compile().plot_coefficients(subplots=subplots, plot_imag=plot_imag, step=step)
-
-
-class Sequence(ValidatedList):
-    """PulseSequences, Operations and instantaneous unitaries applied in series."""
-
-    VALID_TYPES = (qt.Qobj, Operation, PulseSequence)
-
-    def __init__(self, system, operations=None):
-        self.system = system
-        self.pulse_sequence = get_sequence(system)
-        self._t = 0
-        super().__init__(operations)
-
-    def _validate(self, item):
-        item = super()._validate(item)
-        if item is self.pulse_sequence:
-            # appending the global sequence: keep a snapshot and start a new one
-            item = copy.deepcopy(item)
-            self.reset_pulse_sequence()
-        elif len(self.pulse_sequence):
-            self.capture()
-        return item
-
-    def reset_pulse_sequence(self):
-        self.pulse_sequence = get_sequence(self.system)
-
-    def capture(self):
-        """Append the global pulse sequence if anything was captured into it."""
-        if len(self.pulse_sequence):
-            self.append(self.pulse_sequence)
-
-    def _segment(self, item):
-        """Compile one pulsed item (PulseSequence or Operation) at the current sequence time."""
-        if isinstance(item, PulseSequence):
-            if item.system != self.system:
-                raise ValueError("All operations must have the same system.")
-            item.t0 = self._t
-            seq = item.compile()
-        else:
-            seq = CompiledPulseSequence(self.system, t0=self._t)
-            seq.add_operation(item)
-        seq.sync()
-        return seq
-
-    def run(self, init_state, e_ops=None, options=None, full_evolution=True, progress_bar=False):
-        self.capture()
-        wrap = tqdm if progress_bar else (lambda it, **kw: it)
-        e_ops = e_ops or []
-        self._t = 0
-        times = [self._t]
-        states = [init_state]
-        for item in wrap(self):
-            item = self._validate(item)
-            if isinstance(item, qt.Qobj):
-                state = states[-1]
-                state = item * state if state.isket else item * state * item.dag()
-                new_states, new_times = [state], [times[-1]]
-            else:
-                seq = self._segment(item)
-                result = seq.run(states[-1], options=options, only_final_state=(not full_evolution))
-                keep = slice(None) if full_evolution else slice(-1, None)
-                new_states, new_times = result.states[keep], list(result.times[keep])
-                self._t = seq._t
-            states.extend(new_states)
-            times.extend(new_times)
-        times = np.array(times)
-        order = np.argsort(times, kind="stable")
-        times = times[order]
-        states = [states[i] for i in order]
-        expect = [qt.expect(op, states) for op in e_ops]
-        return SequenceResult(times=times, states=states, expect=expect,
-                              num_collapse=len(self.system.c_ops(clean=True)))
-
-    def run_batch(self, init_states, e_ops=None, options=None):
-        """``run(init_state, e_ops, full_evolution=False)`` for a whole batch of initial states with the states
-        kept on the GPU between segments (replaces the per-state loop over ``main.py:281-335``).
-
-        Pulsed segments are lowered once and integrated for all B states by one engine launch whose initial
-        states are the previous segment's device-resident final states; instantaneous unitaries
-        (``main.py:316-322``) are applied by ``seq_engine_apply_unitary`` and the expectation values at the
-        segment boundaries (``main.py:333-335``) come from ``seq_engine_expect`` - nothing but the boundary
-        states' expectation values and the final states crosses PCIe.  Returns one ``SequenceResult`` per state
-        (times / states / expect at the segment boundaries, exactly what ``full_evolution=False`` keeps)."""
-        from .. import solver
-        from ..solver.engine import Engine
-        from .ops import ops2dms
-
-        self.capture()
         init_states = list(init_states)
-        given = list(init_states)        # states[0] of every result is the initial state as it was passed in
-        B = len(init_states)
-        if B == 0:
-            return []
-        e_ops = ops2dms(e_ops or [])
-        has_cops = len(self.system.c_ops(clean=True)) > 0
-        as_ket = all(st.isket for st in init_states) and not has_cops
-        if not as_ket:
-            init_states = [qt.ket2dm(st) if st.isket else st for st in init_states]
-        eng = Engine.get()
-        torch = eng.torch
-        dims = init_states[0].dims
-        cur = torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(st.full()).reshape(-1) if as_ket else np.asarray(st.full())
-                                                              for st in init_states]), dtype=np.complex128)).to(eng.device)
-        N = cur.shape[1]
-        self._t = 0
-        times = [self._t]
-        snaps = [cur.clone()]
-        for item in self:
-            item = self._validate(item)
-            if isinstance(item, qt.Qobj):
-                tu = torch.from_numpy(np.ascontiguousarray(item.full(), dtype=np.complex128)).to(eng.device)
-                eng._check(eng.lib.seq_engine_apply_unitary(eng.handle, tu.data_ptr(), cur.data_ptr(), N, B, int(as_ket)))
-                times.append(times[-1])
-            else:
-                seq = self._segment(item)
-                with solver.deferred_solves(execute=False) as d:
-                    seq.run(init_states[0], options=options, only_final_state=True)
-                (bp,) = d.batch_problems()
-                bp.state0 = np.broadcast_to(bp.state0[:1], (B,) + bp.state0.shape[1:])
-                tens = eng.to_device(bp)
-                tens["state0"] = cur
-                out = eng.solve_device(tens, bp)["out"]
-                if bool((out["status"] != 0).any()):
-                    raise Exception(solver.ODE_ERROR + " (batched Sequence segment)")
-                cur = out["final_state"]
-                self._t = seq._t
-                times.append(float(seq.times.max()))
-            snaps.append(cur.clone())
-        stack = torch.stack(snaps)                                   # [n_snap, B, ...]
-        n_snap = stack.shape[0]
-        if e_ops:
-            te = torch.from_numpy(np.ascontiguousarray(np.stack([op.full() for op in e_ops]), dtype=np.complex128)).to(eng.device)
-            ex = torch.empty((n_snap * B, len(e_ops)), dtype=torch.complex128, device=eng.device)
-            eng._check(eng.lib.seq_engine_expect(eng.handle, te.data_ptr(), stack.data_ptr(), ex.data_ptr(), N, n_snap * B, len(e_ops), int(as_ket)))
-            ex = ex.cpu().numpy().reshape(n_snap, B, len(e_ops))
-        host = stack.cpu().numpy()
-        times = np.array(times)
-        num_collapse = len(self.system.c_ops(clean=True))
-        results = []
-        for b in range(B):
-            states = [given[b]] + [qt.Qobj(host[q, b].reshape(-1, 1) if as_ket else host[q, b], dims=dims) for q in range(1, n_snap)]
-            expect = []
-            for m, op in enumerate(e_ops):
-                row = ex[:, b, m]
-                expect.append(np.array(row.real if op.isherm else row))
-            results.append(SequenceResult(times=times, states=states, expect=expect, num_collapse=num_collapse))
-        return results
+        return run_sequences([self] * len(init_states), init_states, e_ops=e_ops, options=options)
 
     def propagator(self, c_ops=None, options=None, unitary_mode="batch", parallel=False, progress_bar=False):
         self.capture()

@@ -91,7 +91,8 @@ def test_deferred_nonhermitian_split_gpu(gpu_engine):
     """The split also works inside ``deferred_solves`` (two hidden trajectories per non-Hermitian operator)."""
     system, q, c = _lossy_qubit_cavity()
     rng = np.random.default_rng(4)
-    Xs = [qt.Qobj(rng.normal(size=(12, 12)) + 1j * rng.normal(size=(12, 12)), dims=[[3, 4], [3, 4]]) for _ in range(3)]
+    Xs = [rng.normal(size=(12, 12)) + 1j * rng.normal(size=(12, 12)) for _ in range(3)]
+    Xs = [qt.Qobj(X / np.linalg.norm(X), dims=[[3, 4], [3, 4]]) for X in Xs]       # (unit Frobenius norm: absolute bounds below)
     opt = Options(atol=1e-12, rtol=1e-10, nsteps=100000)
     opt.max_step = system.dt
     res = []
@@ -154,7 +155,7 @@ def test_ket_path_n243_five_qutrits(gpu_engine):
     psi[rng.integers(0, 243, 6)] += 0.3 * (rng.normal(size=6) + 1j * rng.normal(size=6))
     psi /= np.linalg.norm(psi)
     init = qt.Qobj(psi.reshape(-1, 1), dims=[[3] * 5, [1] * 5])
-    opt = Options(atol=1e-11, rtol=1e-9, nsteps=100000)
+    opt = Options(atol=1e-13, rtol=1e-11, nsteps=100000)      # matched with the oracle run below
     opt.max_step = system.dt
     opt.store_states = True
 
@@ -171,12 +172,14 @@ def test_ket_path_n243_five_qutrits(gpu_engine):
     bp = _lowered(system, build, init)
     assert bp.is_ket and bp.N == 243
     H, s0, tlist, c_ops, e_ops, grid = oracle_inputs(bp, 0)
-    ref = orc.sesolve(H, psi, grid, [qs[0].n.full(), qs[1].n.full()], oracle_options(bp, atol=1e-11, rtol=1e-9, nsteps=1000000, store_states=False), coeff_tlist=grid)
+    # the reference trace: the oracle's sesolve CONVERGED (1e-13 / 1e-11).  At 1e-11 / 1e-9 it is still 3e-6 from this
+    # one - sesolve renormalises at every output and restarts ZVODE at order 1, 120 restarts here
+    ref = orc.sesolve(H, psi, grid, [qs[0].n.full(), qs[1].n.full()], oracle_options(bp, atol=1e-13, rtol=1e-11, nsteps=1000000, store_states=False), coeff_tlist=grid)
     got = res.states[-1].full().reshape(-1)
     assert abs(np.linalg.norm(got) - 1) < 1e-12
-    assert np.linalg.norm(got - np.asarray(ref.final_state).reshape(-1)) < 1e-7
+    assert np.linalg.norm(got - np.asarray(ref.final_state).reshape(-1)) < 1e-8
     for m in range(2):
-        assert np.max(np.abs(res.expect[m] - np.real(ref.expect[m]))) < 1e-7
+        assert np.max(np.abs(res.expect[m] - np.real(ref.expect[m]))) < 1e-8
     # default tolerances: within 1e-6 of the same reference trace
     res_d = get_sequence(system)
     build()
