@@ -179,6 +179,11 @@ int seq_engine_last_method(const seq_engine* eng);
 /* One-line description of the kernel variant the last solve ran (launch shape of the diagonal kernel,
  * "large/diagonals" vs "large/zgemm", ...); empty when the method has a single variant. */
 const char* seq_engine_last_variant(const seq_engine* eng);
+/* FP64 pipe instructions (multiply-adds; a lone multiply counts as one) ONE right-hand-side evaluation of ONE trajectory
+ * executes in the structure-exploiting kernel the last solve ran, counted by its host plan from the term lists
+ * (zero terms a thread skips statically are not counted); 0 when the kernel does not report it.  bench.py turns it
+ * into the executed fraction of the FP64-FMA peak. */
+int64_t seq_engine_last_fma_per_rhs(const seq_engine* eng);
 
 /* Number of kernel launches issued by the last seq_engine_solve on this handle, and the
  * duration in milliseconds of its integration kernel measured with CUDA events on the

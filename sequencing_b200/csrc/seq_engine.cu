@@ -20,6 +20,7 @@
 #include "kernel_large.cuh"
 #include "kernel_sparse.cuh"
 #include "kernel_diag.cuh"
+#include "kernel_diagblk.cuh"
 #include "kernel_large_diag.cuh"
 
 using namespace seq;
@@ -43,6 +44,7 @@ struct seq_engine {
   bool timed = false;
   int launches = 0;
   int last_method = 0;
+  long long last_fma_per_rhs = 0;   // FP64 multiply-adds per right-hand side of the last solve's kernel (0: not counted)
   std::string variant;              // human-readable detail of what the last solve ran
   int sm_count = 0;
   int max_smem_optin = 0;
@@ -475,6 +477,8 @@ int seq_engine_last_method(const seq_engine* e) { return e ? e->last_method : 0;
 
 const char* seq_engine_last_variant(const seq_engine* e) { return e ? e->variant.c_str() : ""; }
 
+int64_t seq_engine_last_fma_per_rhs(const seq_engine* e) { return e ? (int64_t)e->last_fma_per_rhs : 0; }
+
 float seq_engine_last_kernel_ms(seq_engine* e) {
   if (e && e->chunks > 1) return e->chunk_ms;
   if (!e || !e->timed) return -1.0f;
@@ -857,7 +861,7 @@ static int launch_sparse(seq_engine* e, const seq_solve_desc* d, SolveParams& p,
 // Diagonal structure of the operators (device flags -> host plan).  One D2H copy + synchronisation.
 // `tail`: a second plan (2-CTA clusters per trajectory) for the last partial wave of a launch, see launch_diag
 static int diag_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, const cplx* Gk, const cplx* Lall, int nnzE, DiagPlan* pl, bool* usable,
-                        DiagPlan* tail, bool* tail_ok) {
+                        DiagPlan* tail, bool* tail_ok, BlkPlan* blk, bool* blk_ok) {
   const int N = d->N, n_g = d->n_ch + d->n_ctd, n_l = d->n_c + d->n_ctd;
   const size_t W = 2 * (size_t)N - 1, nflag = (size_t)(2 + n_l) * W;
   *usable = false;
@@ -881,6 +885,35 @@ static int diag_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, 
   if (cap && atoi(cap) > 0 && atoi(cap) < max_smem) max_smem = atoi(cap);
   *usable = diag_plan(N, n_g, d->n_c, d->n_ctd, d->n_ch, d->n_t, nnzE, h.data(), max_smem, env ? atoi(env) : 0, !(cw && atoi(cw) == 0), pl);
   *tail_ok = false;
+  // block-local variant (kernel_diagblk.cuh): is there a small tensor factor whose operators can stay inside a thread?
+  // Candidates come from the diagonal offsets; which diagonals really are local to a candidate is checked on the data.
+  *blk_ok = false;
+  const char* noblk = getenv("SEQ_DIAG_BLK");
+  if (*usable && !(noblk && atoi(noblk) == 0) && !(env && atoi(env) == 2)) {
+    BlkCands cands;
+    diagblk_candidates(N, n_l, h.data(), &cands);
+    if (cands.n > 0) {
+      const size_t ncross = (size_t)cands.n * (1 + n_l) * W;
+      rc = reserve(e, e->dflags, (nflag + ncross) * sizeof(int) + 64);
+      if (rc) return rc;
+      int* cross = (int*)e->dflags.ptr + nflag;
+      CUDA_TRY(e, cudaMemsetAsync(cross, 0, ncross * sizeof(int), e->stream));
+      dim3 gc((unsigned)grid_for((long long)N * N, e->sm_count), 1 + n_l, cands.n);
+      diagblk_cross_kernel<<<gc, 256, 0, e->stream>>>(cands, G0, Gk, n_g, Lall, N, cross);
+      e->launches++;
+      std::vector<int> hc(ncross);
+      CUDA_TRY(e, cudaMemcpyAsync(hc.data(), cross, ncross * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+      CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+      BlkPlan cand;
+      for (int c = 0; c < cands.n; c++) {
+        if (!diagblk_plan(N, n_g, d->n_c, d->n_ctd, d->n_ch, d->n_t, nnzE, h.data(), hc.data() + (size_t)c * (1 + n_l) * W, cands.s[c], cands.D[c], max_smem,
+                          e->sm_count, &cand))
+          continue;
+        if (cand.gathers >= cand.gathers_plain) continue;      // nothing became local
+        if (!*blk_ok || cand.gathers < blk->gathers || (cand.gathers == blk->gathers && cand.bl.D > blk->bl.D)) { *blk = cand; *blk_ok = true; }
+      }
+    }
+  }
   const int rest = d->B % e->sm_count;
   if (*usable && pl->cl == 1 && !e->is_sub && !getenv("SEQ_DIAG_NO_TAIL") && d->B > e->sm_count && rest > 0 && 2 * rest <= e->sm_count && N >= 16)
     *tail_ok = diag_plan(N, n_g, d->n_c, d->n_ctd, d->n_ch, d->n_t, nnzE, h.data(), max_smem, 2, false, tail) && tail->cl == 2 && tail->kreg;
@@ -892,8 +925,10 @@ static int diag_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, 
 // its trajectories run on 2-CTA clusters instead (`tail`): both halves of the GPU work on them and the wave takes
 // ~0.63 of the time.  The cluster variant sums the error norm in a different order, so a tail trajectory agrees with
 // the others to rounding (1e-13), not bit for bit; SEQ_DIAG_NO_TAIL=1 switches the split off.
-static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, const cplx* G0, const cplx* Gk, const SparseInfo& info, DiagPlan& pl,
-                       DiagPlan* tail) {
+static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, const cplx* G0, const cplx* Gk, const SparseInfo& info, DiagPlan& pl_plain,
+                       DiagPlan* tail, BlkPlan* blk) {
+  DiagPlan& pl = blk ? blk->dp : pl_plain;
+  if (blk) tail = nullptr;
   const int N = d->N, n_g = p.n_g, n_l = p.n_c + p.n_ctd, n_e = p.n_e;
   // expectation operators as COO lists (layout shared with the ELL kernel), operator diagonals behind them
   SparsePlan epl;
@@ -903,7 +938,8 @@ static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, c
   DiagPack dk = diag_pack_layout(N, n_g, pl);
   int rc = reserve(e, e->pack, pk.bytes + dk.bytes);
   if (rc) return rc;
-  rc = reserve(e, e->ws, (diag_ws_elems(pl) * (size_t)d->B + diag_ws_shared_elems(pl)) * sizeof(cplx) + 256);
+  const size_t ws_per = blk ? diagblk_ws_elems(*blk) : diag_ws_elems(pl), ws_shared = blk ? diagblk_ws_shared_elems(*blk) : diag_ws_shared_elems(pl);
+  rc = reserve(e, e->ws, (ws_per * (size_t)d->B + ws_shared) * sizeof(cplx) + 256);
   if (rc) return rc;
   char* base = (char*)e->pack.ptr;
   char* dbase = base + pk.bytes / 16 * 16;
@@ -930,9 +966,22 @@ static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, c
   CUDA_TRY(e, cudaMemcpyAsync(&h_imag, any_imag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   p.ws = (cplx*)e->ws.ptr;
-  p.ws_stride = (long long)diag_ws_elems(pl);
+  p.ws_stride = (long long)ws_per;
   CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
   sp.lreal = h_imag == 0 ? 1 : 0;
+  if (blk) {
+    char buf[384];
+    snprintf(buf, sizeof(buf), "diagblk: local mode dim %d stride %d kept in registers, 1 CTA x %d threads per trajectory (%d CTA%s/SM), %d elements/thread, "
+             "rolled stage loop, %s%d stage-derivative slots in shared memory + %d in L2, %d Y buffer%s%s, %d gathers/element (plain diag: %d), smem %zu B",
+             blk->bl.D, blk->bl.s, blk->threads, blk->minb, blk->minb > 1 ? "s" : "", blk->bl.D * blk->bl.D, blk->k1reg ? "k1 in registers, " : "", blk->bl.kslots, blk->gslots,
+             sp.ybufs, sp.ybufs > 1 ? "s" : "", pl.guard ? " + guard bands" : "", blk->gathers, blk->gathers_plain, pl.smem);
+    e->variant = buf;
+    e->last_fma_per_rhs = blk->fma_per_rhs;
+    rc = launch_diagblk_kernel(p, *blk, e->stream);
+    if (rc) return fail(e, rc, "block-local diagonal kernel launch configuration failed for N=%d", N);
+    e->launches++;
+    return SEQ_OK;
+  }
   {
     char buf[224];
     snprintf(buf, sizeof(buf), "diag: %d CTA%s x %d threads%s per trajectory, %d elements/thread, stage vectors in %s, %d Y buffer%s%s, smem %zu B", pl.cl, pl.cl > 1 ? "s (cluster)" : "",
@@ -1075,13 +1124,14 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   // ---- operator sparsity decides between the sparse (FMA) and the dense (tensor-core) formulation
   SparseInfo spi;
   DiagPlan dpl, dpl_tail;
-  bool tail_ok = false;
+  BlkPlan bpl;
+  bool tail_ok = false, blk_ok = false;
   if (try_sparse) {
     rc = sparse_analyze(e, d, G0, Gk, Lall, &spi);
     if (rc) return rc;
     bool diag_ok = false;
     if (method != SEQ_METHOD_SPARSE) {
-      rc = diag_analyze(e, d, G0, Gk, Lall, spi.plan.nnzE, &dpl, &diag_ok, &dpl_tail, &tail_ok);
+      rc = diag_analyze(e, d, G0, Gk, Lall, spi.plan.nnzE, &dpl, &diag_ok, &dpl_tail, &tail_ok, &bpl, &blk_ok);
       if (rc) return rc;
     }
     if (method == SEQ_METHOD_SPARSE) {
@@ -1096,6 +1146,7 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
     }
   }
   e->last_method = method;
+  e->last_fma_per_rhs = 0;
   e->variant.clear();
 
   const size_t ws_per = ws_elems_per_traj(d, method);
@@ -1136,7 +1187,7 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
     rc = launch_sparse(e, d, p, G0, Gk, spi);
     if (rc) return rc;
   } else if (method == SEQ_METHOD_DIAG) {
-    rc = launch_diag(e, d, p, G0, Gk, spi, dpl, tail_ok ? &dpl_tail : nullptr);
+    rc = launch_diag(e, d, p, G0, Gk, spi, dpl, tail_ok ? &dpl_tail : nullptr, blk_ok ? &bpl : nullptr);
     if (rc) return rc;
   } else if (method == SEQ_METHOD_GENERIC) {
     size_t elems = ket ? (size_t)N : N2;
@@ -1314,6 +1365,7 @@ static int solve_host(seq_engine* e, const seq_solve_desc* d) {
   }
   e->launches = launches;
   e->last_method = e->sub[0]->last_method;
+  e->last_fma_per_rhs = e->sub[0]->last_fma_per_rhs;
   char buf[64];
   snprintf(buf, sizeof(buf), " [host solve pipelined in %d chunks]", nchunk);
   e->variant = e->sub[0]->variant + buf;

@@ -177,9 +177,10 @@ def test_ket_path_n243_five_qutrits(gpu_engine):
     ref = orc.sesolve(H, psi, grid, [qs[0].n.full(), qs[1].n.full()], oracle_options(bp, atol=1e-13, rtol=1e-11, nsteps=1000000, store_states=False), coeff_tlist=grid)
     got = res.states[-1].full().reshape(-1)
     assert abs(np.linalg.norm(got) - 1) < 1e-12
-    assert np.linalg.norm(got - np.asarray(ref.final_state).reshape(-1)) < 1e-8
+    # (the oracle's own 1e-13/1e-11 and 1e-14/1e-12 runs are 1.3e-8 apart on this problem: 5e-8 is its resolution)
+    assert np.linalg.norm(got - np.asarray(ref.final_state).reshape(-1)) < 5e-8
     for m in range(2):
-        assert np.max(np.abs(res.expect[m] - np.real(ref.expect[m]))) < 1e-8
+        assert np.max(np.abs(res.expect[m] - np.real(ref.expect[m]))) < 5e-8
     # default tolerances: within 1e-6 of the same reference trace
     res_d = get_sequence(system)
     build()
