@@ -134,14 +134,17 @@ template <int V> struct IntTag { static constexpr int value = V; };
 // order switching: probe the 4(3) pair when a 5(4) step was accepted at a capped step size with an
 // error estimate below SEQ_PROBE_ERR; keep it only while it holds the capped step with its own
 // error estimate below SEQ_STAY_ERR (otherwise 6 RHS at the capped step beat 4 RHS at a shorter one).
-#define SEQ_PROBE_ERR 0.02
-#define SEQ_STAY_ERR 0.5
+// Defaults of SolveParams::probe_err / stay_err (SEQ_PROBE_ERR / SEQ_STAY_ERR in the environment override them when an
+// engine is created - experiments only).
+#define SEQ_PROBE_ERR_DEFAULT 0.02
+#define SEQ_STAY_ERR_DEFAULT 0.5
 
 // ---- kernel parameter block (device pointers into caller buffers + engine scratch)
 struct SolveParams {
   int N, B, n_t, n_g, n_ch, n_c, n_ctd, n_e, n_out, nsteps;
   unsigned flags;
   double t0, dt, atol, rtol, max_step, first_step, min_step;
+  double probe_err, stay_err;   // order switching thresholds (see ctl_update)
   const cplx* G0;           // [N,N] (or per trajectory): H0 - (i/2) sum_const L^dag L   (kets: H0)
   long long G0_bstride;
   const cplx* Gk;           // [n_g,N,N]: H_k (k < n_ch), then -(i/2) L^dag L of time-dependent collapse ops
@@ -311,8 +314,8 @@ __host__ __device__ __forceinline__ bool ctl_update(StepCtl& c, const SolveParam
     if (switching) {
       if (c.pair == 0) {
         if (c.probe_wait > 0) c.probe_wait--;
-        if (capped && err <= SEQ_PROBE_ERR && c.probe_wait == 0) c.pair = 1;
-      } else if (capped && err <= SEQ_STAY_ERR) {
+        if (capped && err <= p.probe_err && c.probe_wait == 0) c.pair = 1;
+      } else if (capped && err <= p.stay_err) {
         c.probe_backoff = 1;
       } else {
         c.pair = 0;

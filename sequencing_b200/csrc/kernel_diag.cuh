@@ -285,7 +285,7 @@ __device__ __noinline__ bool diag_verify(const SolveParams& p, const DiagCtlStat
 // 1.07 htry >= max_step (third line).  Two error sums that both pass therefore lead to the same controller state up to
 // h, and h does not bind: exactly what diag_verify checks.
 __device__ __forceinline__ bool diag_fast_state_ok(const SolveParams& p, const DiagCtlState* S) {
-  return S->ctl.pair == 1 && S->capped != 0 && !S->ctl.prev_rejected && S->ctl.status == SEQ_STATUS_OK && SEQ_STAY_ERR >= 0.49 &&
+  return S->ctl.pair == 1 && S->capped != 0 && !S->ctl.prev_rejected && S->ctl.status == SEQ_STATUS_OK && p.stay_err <= 0.5 &&
          p.max_step > 0 && S->nst + 1 <= p.nsteps && S->htry * 1.05 >= p.max_step &&
          p.max_step >= 1e-10 * fmax(1.0, fabs(S->target) + fabs(S->ctl.t) + S->htry);
 }
@@ -637,7 +637,7 @@ solve_diag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__
       // new error estimate are below the stay threshold with a margin.  Then the accept/reject logic provably ends in
       // the predicted state (accepted, pair kept, proposal above the cap - see diag_fast_state_ok), so the verdict goes out
       // right after the block sum and the exact bookkeeping (the proposal h) follows off the critical path.
-      const double es_max = 0.2401 * (double)p.N * (double)p.N;
+      const double es_max = 0.9604 * p.stay_err * p.stay_err * (double)p.N * (double)p.N;      // err <= 0.98 stay_err
       const bool fast_prev = valid && diag_fast_state_ok(p, S) && diag_fast_es_ok(es_prev, es_max);
       __threadfence_block();
       PROFC(8);

@@ -66,6 +66,11 @@ __global__ void diagblk_cross_kernel(const __grid_constant__ BlkCands cands, con
   }
 }
 
+// conj(z) with the sign flipped on the integer pipe (the FP64 pipe is the one this kernel is short of)
+__device__ __forceinline__ cplx blk_conj(const cplx& z) {
+  return cmake(z.x, __hiloint2double(__double2hiint(z.y) ^ (int)0x80000000, __double2loint(z.y)));
+}
+
 // compiler-level memory fence: loads are not hoisted across it (bounds the operands in flight, i.e. the registers)
 __device__ __forceinline__ void blk_fence() { asm volatile("" ::: "memory"); }
 
@@ -105,13 +110,10 @@ solve_diagblk_kernel(const __grid_constant__ SolveParams p, const __grid_constan
   for (int q = tid; q < L.off_Gt / 16; q += nth) ((cplx*)smem_diag)[q] = cmake(0, 0);
   for (int q = tid; q < sp.nT * N; q += nth) ((cplx*)(smem_diag + L.off_lam))[q] = sp.lam[q];
   const int gsz = sp.nD * N;
-  const cplx* g0p = sp.g0;
-  const cplx* gkp = sp.gk;
   if (sp.stage_g) {
     cplx* gs = (cplx*)(smem_diag + L.off_g);
     for (int q = tid; q < gsz; q += nth) gs[q] = sp.g0[q];
     for (int q = tid; q < n_g * gsz; q += nth) gs[gsz + q] = sp.gk[q];
-    g0p = gs; gkp = gs + gsz;
   }
   const unsigned* eij = sp.e_ij;
   const cplx* eval_ = sp.e_val;
@@ -199,20 +201,40 @@ solve_diagblk_kernel(const __grid_constant__ SolveParams p, const __grid_constan
 #pragma unroll
         for (int c2 = 0; c2 < D; c2++) {
           *(cplx*)(yo + a * SL + c2 * SR) = v[a * D + c2];
-          if (!isdiag) *(cplx*)(ym + c2 * SL + a * SR) = cconj(v[a * D + c2]);
+          if (!isdiag) *(cplx*)(ym + c2 * SL + a * SR) = blk_conj(v[a * D + c2]);
         }
     }
   };
+  // G(t) diagonals of one stage; two copies of the loop so that the staged tables are read with shared-memory loads
+  // (one pointer that may be either makes every load a generic one)
   auto build_Gt = [&](cplx* Gb, const double* cvs, int st) {
-    for (int q = tid; q < gsz; q += nth) {
-      cplx g = g0p[q];
-      for (int m = 0; m < n_g; m++) {
-        const cplx a = gkp[m * gsz + q];
-        const double v = cvs[st * n_g + m];
-        g.x = fma(v, a.x, g.x);
-        g.y = fma(v, a.y, g.y);
+    if (sp.stage_g) {
+      const cplx* gs = (const cplx*)(smem_diag + L.off_g);
+#pragma unroll 1
+      for (int q = tid; q < gsz; q += nth) {
+        cplx g = gs[q];
+#pragma unroll 1
+        for (int m = 0; m < n_g; m++) {
+          const cplx a = gs[(m + 1) * gsz + q];
+          const double v = cvs[st * n_g + m];
+          g.x = fma(v, a.x, g.x);
+          g.y = fma(v, a.y, g.y);
+        }
+        Gb[q] = g;
       }
-      Gb[q] = g;
+    } else {
+#pragma unroll 1
+      for (int q = tid; q < gsz; q += nth) {
+        cplx g = sp.g0[q];
+#pragma unroll 1
+        for (int m = 0; m < n_g; m++) {
+          const cplx a = sp.gk[m * gsz + q];
+          const double v = cvs[st * n_g + m];
+          g.x = fma(v, a.x, g.x);
+          g.y = fma(v, a.y, g.y);
+        }
+        Gb[q] = g;
+      }
     }
   };
   const int y_hi = L.ybytes - C;
@@ -513,7 +535,8 @@ solve_diagblk_kernel(const __grid_constant__ SolveParams p, const __grid_constan
       if (cj != 0.0) k_axpy(j, cj, er);
     }
     double es = 0.0;
-    // (threads without an element carry zeros and add nothing; a zero weight would send the division to its slow path.
+    // (threads without an element are masked at the end - their gathers read real data, so their numbers are not zero -
+    // because a zero weight would send the division to its slow path.
     // Likewise the square root of an exact zero - most of rho is - takes a slow path: below 1e-280 the floor changes
     // nothing in atol + rtol sqrt(.) as long as atol is not absurdly small)
     const double wgt = isdiag ? 1.0 : 2.0;
@@ -524,7 +547,7 @@ solve_diagblk_kernel(const __grid_constant__ SolveParams p, const __grid_constan
       const double ex = er[e].x * htry, ey = er[e].y * htry;
       es = fma(ex * ex + ey * ey, wgt / (sc * sc), es);
     }
-    return es;
+    return valid ? es : 0.0;
   };
 
   while (true) {
@@ -724,7 +747,11 @@ static inline bool diagblk_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, in
   const int guard_el = maxoff * o.ld + maxoff + 1;
   // launch shape by thread count: small CTAs run two per SM (255 registers each), the largest ones keep nothing but the
   // state, the stage input and the accumulator in registers (128 registers at 512 threads)
-  if (bp->threads <= 128) { bp->maxt = 128; bp->minb = 2; bp->k1reg = true; bp->wreg = true; }
+  if (bp->threads <= 128) {
+    bp->maxt = 128; bp->minb = 2; bp->k1reg = true; bp->wreg = true;
+    const char* mb = getenv("SEQ_BLK_MINB");      // experiments: 3 CTAs per SM (168 registers, more slots in L2)
+    if (mb && atoi(mb) == 3 && D == 3) bp->minb = 3;
+  }
   else if (bp->threads <= 256) { bp->maxt = 256; bp->minb = 1; bp->k1reg = true; bp->wreg = true; }
   else { bp->maxt = 512; bp->minb = 1; bp->k1reg = false; bp->wreg = false; }
   const int slot = E * bp->maxt * c;           // one thread-private stage vector (the kernel runs with maxt threads)
@@ -785,6 +812,7 @@ static int launch_diagblk_t(const SolveParams& p, const BlkPlan& bp, cudaStream_
 template <int D>
 static inline int launch_diagblk_d(const SolveParams& p, const BlkPlan& bp, cudaStream_t st) {
   const bool g = bp.dp.guard;
+  if (bp.maxt == 128 && bp.minb == 3 && D == 3) return g ? launch_diagblk_t<3, true, true, true, 128, 3>(p, bp, st) : launch_diagblk_t<3, true, true, false, 128, 3>(p, bp, st);
   if (bp.maxt == 128) return g ? launch_diagblk_t<D, true, true, true, 128, 2>(p, bp, st) : launch_diagblk_t<D, true, true, false, 128, 2>(p, bp, st);
   if (bp.maxt == 256) return g ? launch_diagblk_t<D, true, true, true, 256, 1>(p, bp, st) : launch_diagblk_t<D, true, true, false, 256, 1>(p, bp, st);
   return g ? launch_diagblk_t<D, false, false, true, 512, 1>(p, bp, st) : launch_diagblk_t<D, false, false, false, 512, 1>(p, bp, st);

@@ -44,6 +44,7 @@ struct seq_engine {
   bool timed = false;
   int launches = 0;
   int last_method = 0;
+  double probe_err = SEQ_PROBE_ERR_DEFAULT, stay_err = SEQ_STAY_ERR_DEFAULT;   // order-switch thresholds handed to every kernel
   long long last_fma_per_rhs = 0;   // FP64 multiply-adds per right-hand side of the last solve's kernel (0: not counted)
   std::string variant;              // human-readable detail of what the last solve ran
   int sm_count = 0;
@@ -1170,6 +1171,14 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   p.n_e = d->n_e; p.n_out = d->n_out; p.nsteps = d->nsteps; p.flags = d->flags;
   p.t0 = d->t0; p.dt = d->dt; p.atol = d->atol; p.rtol = d->rtol;
   p.max_step = d->max_step; p.first_step = d->first_step; p.min_step = d->min_step;
+  p.probe_err = e->probe_err; p.stay_err = e->stay_err;
+  {      // experiments: thresholds from the environment, looked up per solve
+    const char* s1 = getenv("SEQ_STAY_ERR");
+    const char* s2 = getenv("SEQ_PROBE_ERR");
+    if (s1 && atof(s1) > 0) p.stay_err = atof(s1);
+    if (s2 && atof(s2) > 0) p.probe_err = atof(s2);
+    if (p.probe_err > p.stay_err) p.probe_err = p.stay_err;
+  }
   p.G0 = G0; p.G0_bstride = d->H0_batch_stride ? (long long)N2 : 0;
   p.Gk = Gk;
   p.tab = tabc; p.tab_rate = tabr;

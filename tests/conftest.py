@@ -34,6 +34,13 @@ def gpu_engine():
     return Engine.get(0)
 
 
+@pytest.fixture
+def plain_diag(monkeypatch):
+    """SEQ_METHOD_DIAG on the plain diagonal kernel (kernel_diag.cuh) - the block-local variant (kernel_diagblk.cuh),
+    which takes over whenever a small tensor factor can stay inside a thread, switched off."""
+    monkeypatch.setenv("SEQ_DIAG_BLK", "0")
+
+
 class _RecordingEngine:
     """The real CUDA engine with the OracleEngine's bookkeeping (how many launches, how large)."""
 

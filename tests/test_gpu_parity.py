@@ -483,7 +483,7 @@ def test_large_path_structured_rhs_matches_generic_and_zgemm(gpu_engine):
     assert out.method in ("large", "sparse")       # too large for the one-CTA kernels' register budget or ELL streams
 
 
-def test_diag_kernel_two_cta_cluster_variant(gpu_engine):
+def test_diag_kernel_two_cta_cluster_variant(gpu_engine, plain_diag):
     """The diagonal kernel's cluster variant (SEQ_DIAG_CL=2: one trajectory on two CTAs, the stage matrix written into
     both CTAs' shared memory through DSMEM stores, cluster barriers per RHS) against the FP64-FMA kernel, with one and
     two Y buffers and an odd / even number of rows per CTA."""
@@ -587,7 +587,7 @@ def test_sequence_run_batch_keeps_states_on_device(gpu_engine):
                 np.testing.assert_allclose(a, b, atol=1e-12)
 
 
-def test_diag_kernel_controller_warp_variant(gpu_engine):
+def test_diag_kernel_controller_warp_variant(gpu_engine, plain_diag):
     """The diagonal kernel's controller-warp variant (the default for N <= 48, SEQ_DIAG_CW=0 switches it off: a 13th warp predicts the next control
     block while the step is evaluated, the compute warps stage the next step speculatively and pick up the verdict
     one barrier later) takes bit-identical decisions: against the FP64-FMA kernel on capped and uncapped problems
@@ -655,7 +655,7 @@ def test_host_abi_chunked_pipeline_is_bit_identical(gpu_engine):
         np.testing.assert_array_equal(outs["1"]["final_state"], dev.final_state)
 
 
-def test_diag_kernel_failure_statuses_match_generic(gpu_engine):
+def test_diag_kernel_failure_statuses_match_generic(gpu_engine, plain_diag):
     """Integration failures inside the diagonal kernel - with its controller warp (prediction / fast verdict paths) and
     without: more than `nsteps` internal steps per output interval, on capped steps (three capped steps per interval
     against nsteps = 2: the fast-verdict regime must see the limit) and on uncapped ones, and a non-finite state.
@@ -706,7 +706,7 @@ def test_diag_kernel_failure_statuses_match_generic(gpu_engine):
             np.testing.assert_array_equal(cw.final_state[[0, 2]], nocw.final_state[[0, 2]])
 
 
-def test_diag_kernel_tail_wave_on_clusters(gpu_engine):
+def test_diag_kernel_tail_wave_on_clusters(gpu_engine, plain_diag):
     """A batch that ends in at most half a wave of CTAs runs that rest on 2-CTA clusters (both launches in one solve):
     every trajectory - main launch and tail - against the FP64-FMA kernel, register-resident and streamed main
     variants; SEQ_DIAG_NO_TAIL=1 and batches without a partial wave keep the single launch."""

@@ -17,7 +17,7 @@ eng = Engine.get(0)
 
 
 def run(tag, env, method=None):
-    for k in ("SEQ_DIAG_BLK", "SEQ_BLK_SHAPE"):
+    for k in ("SEQ_DIAG_BLK", "SEQ_BLK_MINB"):
         os.environ.pop(k, None)
     os.environ.update(env)
     bp.method = _lib.METHOD_AUTO if method is None else method
@@ -41,4 +41,4 @@ for k in ("plain", "generic"):
         print("blk vs %s: max |d final| %.3g  max |d expect| %.3g  stats equal %s" % (k, np.abs(a.final_state - b.final_state).max(), np.abs(a.expect - b.expect).max(),
                                                                                       np.array_equal(a.stats[:, :3], b.stats[:, :3])))
 for shape in sys.argv[2:]:
-    run("blk shape " + shape, {"SEQ_BLK_SHAPE": shape})
+    run("blk minb " + shape, {"SEQ_BLK_MINB": shape})
