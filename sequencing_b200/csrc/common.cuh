@@ -137,6 +137,7 @@ template <int V> struct IntTag { static constexpr int value = V; };
 // Defaults of SolveParams::probe_err / stay_err (SEQ_PROBE_ERR / SEQ_STAY_ERR in the environment override them when an
 // engine is created - experiments only).
 #define SEQ_PROBE_ERR_DEFAULT 0.02
+#define SEQ_KET_TOL_MARGIN 0.1      // internal tolerance factor of the ket path (seq_engine.cu::solve_device)
 #define SEQ_STAY_ERR_DEFAULT 0.5
 
 // ---- kernel parameter block (device pointers into caller buffers + engine scratch)

@@ -1172,6 +1172,13 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   p.t0 = d->t0; p.dt = d->dt; p.atol = d->atol; p.rtol = d->rtol;
   p.max_step = d->max_step; p.first_step = d->first_step; p.min_step = d->min_step;
   p.probe_err = e->probe_err; p.stay_err = e->stay_err;
+  // Kets: the weighted RMS norm averages over N components of which a handful carry the state, so the controller admits
+  // local errors several times rtol on those, and over the many free (uncapped) steps of a ket solve the embedded pair ends
+  // up further from the converged solution than the reference's variable-order Adams integrator does at the same
+  // tolerances (five-qutrit problem of test_qasm.py:463-530: expectation traces 9e-5 vs 1.7e-5).  A factor 10 on the
+  // internal tolerances (1.6x the steps of an N-vector integration) puts the ket path at or below the reference
+  // integrator's error there; density matrices keep the caller's tolerances as they are.
+  if (ket) { p.atol *= SEQ_KET_TOL_MARGIN; p.rtol *= SEQ_KET_TOL_MARGIN; }
   {      // experiments: thresholds from the environment, looked up per solve
     const char* s1 = getenv("SEQ_STAY_ERR");
     const char* s2 = getenv("SEQ_PROBE_ERR");

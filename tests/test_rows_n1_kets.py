@@ -181,13 +181,20 @@ def test_ket_path_n243_five_qutrits(gpu_engine):
     assert np.linalg.norm(got - np.asarray(ref.final_state).reshape(-1)) < 5e-8
     for m in range(2):
         assert np.max(np.abs(res.expect[m] - np.real(ref.expect[m]))) < 5e-8
-    # default tolerances: within 1e-6 of the same reference trace
+    # default tolerances (atol 1e-8, rtol 1e-6): neither integrator is within 1e-6 of the converged trace on 120 ns of
+    # free stepping (the oracle's ZVODE run: trace distance 4e-4, expectation traces 1.7e-5) - the engine must be at least
+    # as close to it as the reference integrator is
+    ref_d = orc.sesolve(H, psi, grid, [qs[0].n.full(), qs[1].n.full()], oracle_options(bp, store_states=False), coeff_tlist=grid)
     res_d = get_sequence(system)
     build()
     res_d = res_d.run(init, e_ops=[qs[0].n, qs[1].n])
-    for m in range(2):
-        assert np.max(np.abs(res_d.expect[m] - np.real(ref.expect[m]))) < 1e-6
-    assert orc.trace_distance(res_d.states[-1].full().reshape(-1), np.asarray(ref.final_state).reshape(-1)) < 1e-6
+    fin = np.asarray(ref.final_state).reshape(-1)
+    e_eng = max(np.max(np.abs(res_d.expect[m] - np.real(ref.expect[m]))) for m in range(2))
+    e_orc = max(np.max(np.abs(np.real(ref_d.expect[m]) - np.real(ref.expect[m]))) for m in range(2))
+    td_eng = orc.trace_distance(res_d.states[-1].full().reshape(-1), fin)
+    td_orc = orc.trace_distance(np.asarray(ref_d.final_state).reshape(-1), fin)
+    print(f"ket N=243 default tolerances vs converged: engine td {td_eng:.2e} expect {e_eng:.2e} | oracle td {td_orc:.2e} expect {e_orc:.2e}")
+    assert e_eng <= max(1e-6, e_orc) and td_eng <= max(1e-6, td_orc)
 
 
 @pytest.mark.gpu
