@@ -8,6 +8,10 @@ which = sys.argv[1] if len(sys.argv) > 1 else "c2"
 eng = Engine.get(0)
 if which == "c2":
     bp = w.c2_selective(4, 37, sigma=25)       # N=45, n_t=100, B=148
+elif which == "c2bench":
+    bp = w.c2_selective(32, 32)                # the bench launch itself: N=45, n_t=1000, B=1024
+elif which == "c4bench":
+    bp = w.c4_two_transmons_bus(512)
 elif which == "c4":
     bp = w.c4_two_transmons_bus(148)
 elif which == "c3":
