@@ -119,17 +119,32 @@ def _setup(system, init_state, e_ops, mode_name, pulse_name):
     return init_state, mode, pulse_name, pulse, e_ops
 
 
+def _use_device_synthesis(flag, pulse):
+    """``device_synthesis`` argument of the sweep drivers: None = automatic."""
+    if flag is False or not synth.supported(pulse):
+        return False
+    if flag:
+        return True
+    from .solver.engine import Engine
+    try:
+        return hasattr(Engine.get(), "synth_gaussian")      # (tests route Engine.get() to a CPU oracle stand-in without it)
+    except Exception:
+        return False
+
+
 def tune_rabi(system, init_state, e_ops=None, mode_name="qubit", pulse_name=None, amp_range=(-2, 2, 51),
-              progbar=True, plot=True, ax=None, ylabel=None, update=True, verify=True, device_synthesis=False):
+              progbar=True, plot=True, ax=None, ylabel=None, update=True, verify=True, device_synthesis=None):
     """Amplitude-Rabi calibration of a qubit pulse; returns ``((fig, ax), old_amp, new_amp)``.
 
-    ``device_synthesis=True`` (an addition to the reference's signature): ONE template sequence is lowered and the
+    ``device_synthesis`` (an addition to the reference's signature): ONE template sequence is lowered and the
     coefficient tables of all sweep points are generated on the GPU (``solver/synth.py``)
-    instead of compiling one sequence per point in Python."""
+    instead of compiling one sequence per point in Python.  Default (``None``): on whenever the pulse is one the
+    device synthesis covers (noise-free Gaussian / DRAG) and the engine is the CUDA one; ``False`` forces the
+    reference's per-point host compilation."""
     init_state, qubit, pulse_name, pulse, e_ops = _setup(system, init_state, e_ops, mode_name, pulse_name)
     amps = np.linspace(*amp_range)
     prog = tqdm if progbar else (lambda x, **kw: x)
-    if device_synthesis and synth.supported(pulse):
+    if _use_device_synthesis(device_synthesis, pulse):
         def template():
             with deferred_solves(execute=False) as d:
                 seq = get_sequence(system)
@@ -235,7 +250,7 @@ def tune_repeated_pio2_pulses(system, init_state, e_ops=None, mode_name="qubit",
 
 
 def tune_drag(system, init_state, e_ops=None, mode_name="qubit", pulse_name=None, drag_range=(-5, 5, 21),
-              progbar=True, plot=True, ax=None, ylabel=None, update=True, device_synthesis=False):
+              progbar=True, plot=True, ax=None, ylabel=None, update=True, device_synthesis=None):
     """DRAG calibration: ``Rx(pi);Ry(pi/2)`` vs ``Ry(pi);Rx(pi/2)`` over a DRAG sweep; the crossing
     of the two fitted lines is the optimum.  Returns ``((fig, ax), old_drag, new_drag)``.
     ``device_synthesis``: see ``tune_rabi``."""
@@ -243,7 +258,7 @@ def tune_drag(system, init_state, e_ops=None, mode_name="qubit", pulse_name=None
     old_drag = pulse.drag
     drags = np.linspace(*drag_range)
     prog = tqdm if progbar else (lambda x, **kw: x)
-    if device_synthesis and synth.supported(pulse):
+    if _use_device_synthesis(device_synthesis, pulse):
         def template():
             with deferred_solves(execute=False) as d:
                 seq = get_sequence(system)

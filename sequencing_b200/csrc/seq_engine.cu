@@ -8,9 +8,12 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "common.cuh"
 #include "kernel_generic.cuh"
@@ -21,6 +24,7 @@
 #include "kernel_sparse.cuh"
 #include "kernel_diag.cuh"
 #include "kernel_diagblk.cuh"
+#include "kernel_ket.cuh"
 #include "kernel_large_diag.cuh"
 
 using namespace seq;
@@ -1034,6 +1038,65 @@ static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, c
   return SEQ_OK;
 }
 
+// Kets (sesolve path): operators by diagonals when they have that structure (kernel_ket.cuh).  `forced`: SEQ_METHOD_DIAG was
+// asked for.  *ran = false: the operators are not diagonal-structured enough - the caller falls back to the generic kernel.
+static int launch_ket(seq_engine* e, const seq_solve_desc* d, SolveParams& p, const cplx* G0, const cplx* Gk, bool forced, bool* ran) {
+  const int N = d->N, n_ch = d->n_ch, n_e = d->n_e;
+  *ran = false;
+  if (d->n_c + d->n_ctd > 0 || N > 0x7fff) return SEQ_OK;
+  const size_t W = 2 * (size_t)N - 1, nflag = (size_t)(1 + n_ch) * W;
+  int rc = reserve(e, e->dflags, nflag * sizeof(int) + 64);
+  if (rc) return rc;
+  int* flags = (int*)e->dflags.ptr;
+  CUDA_TRY(e, cudaMemsetAsync(flags, 0, nflag * sizeof(int), e->stream));
+  dim3 grid((unsigned)grid_for((long long)N * N, e->sm_count), 1 + n_ch);
+  ket_flags_kernel<<<grid, 256, 0, e->stream>>>(G0, Gk, N, flags);
+  e->launches++;
+  std::vector<int> h(nflag);
+  CUDA_TRY(e, cudaMemcpyAsync(h.data(), flags, nflag * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  SparseInfo spi;
+  rc = sparse_analyze(e, d, G0, Gk, nullptr, &spi);      // (synchronises; only the expectation operators' row counts are used)
+  if (rc) return rc;
+  KetPlan pl;
+  if (!ket_plan(N, n_ch, p.n_g, spi.plan.nnzE, h.data(), e->max_smem_optin, &pl)) return SEQ_OK;
+  if (!forced && pl.macs * 4 > (long long)N) return SEQ_OK;      // not sparse enough to beat the dense product
+  SparsePlan epl;
+  memset(&epl, 0, sizeof(epl));
+  epl.wG = 1; epl.wL = 1; epl.nnzE = spi.plan.nnzE;
+  SparsePack pk = sparse_pack_layout(N, 0, 0, n_e, epl);
+  const size_t tab_bytes = (size_t)pl.ops.nTab * N * sizeof(cplx);
+  rc = reserve(e, e->pack, pk.bytes + tab_bytes + 256);
+  if (rc) return rc;
+  char* base = (char*)e->pack.ptr;
+  KetOps& ko = pl.ops;
+  ko.e_off = (int*)(base + pk.o_eoff); ko.e_ij = (unsigned*)(base + pk.o_eij); ko.e_val = (cplx*)(base + pk.o_eval);
+  ko.tabs = (cplx*)(base + (pk.bytes + 15) / 16 * 16);
+  const int n_ops = 1 + n_e;
+  int* rowoff = spi.rowcnt + (size_t)n_ops * N + 2 * (size_t)n_ops;
+  sparse_escan_kernel<<<1, 32, 0, e->stream>>>(spi.rowcnt, 0, n_e, N, rowoff, (int*)ko.e_off);
+  e->launches++;
+  if (n_e > 0) {
+    dim3 ge(N, n_e);
+    sparse_fill_kernel<<<ge, 32, 0, e->stream>>>(G0, Gk, p.n_g, p.L, 0, p.E, N, 1, 1, nullptr, nullptr, nullptr, nullptr, nullptr, rowoff,
+                                               (unsigned*)ko.e_ij, (cplx*)ko.e_val, 1);
+    e->launches++;
+  }
+  dim3 gf((N + 127) / 128, pl.fill.nTab);
+  ket_fill_kernel<<<gf, 128, 0, e->stream>>>(pl.fill, G0, Gk, N, (cplx*)ko.tabs);
+  e->launches++;
+  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  char buf[256];
+  snprintf(buf, sizeof(buf), "ketdiag: operators by diagonals, %d terms per element (dense product: %d), 1 CTA x %d threads per trajectory, %d element%s/thread, "
+           "all vectors in shared memory, smem %zu B", pl.ops.nTerm + pl.ops.has_w, N, pl.threads, pl.ept, pl.ept > 1 ? "s" : "", pl.smem);
+  e->variant = buf;
+  e->last_fma_per_rhs = 4LL * (pl.ops.nTerm + pl.ops.has_w) * N;
+  rc = launch_ket_kernel(p, pl, e->stream);
+  if (rc) return fail(e, rc, "ket kernel launch configuration failed for N=%d", N);
+  e->launches++;
+  *ran = true;
+  return SEQ_OK;
+}
+
 static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   const int N = d->N, B = d->B;
   const size_t N2 = (size_t)N * N;
@@ -1041,6 +1104,15 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   const bool ket = d->flags & SEQ_FLAG_KET;
   int method = pick_method(e, d);
   const bool sharded = e->comm && e->comm->world > 1;
+  // kets: the operators-by-diagonals kernel is tried whenever the choice is the engine's (or SEQ_METHOD_DIAG is asked for);
+  // SEQ_KET_DIAG=0 keeps the dense generic kernel
+  const char* kd = getenv("SEQ_KET_DIAG");
+  const bool ket_diag_wanted = ket && !d->H0_batch_stride && !sharded && (d->method == SEQ_METHOD_AUTO || d->method == SEQ_METHOD_DIAG) &&
+                               !(kd && atoi(kd) == 0 && d->method != SEQ_METHOD_DIAG);
+  if (ket && d->method == SEQ_METHOD_DIAG) {
+    if (!ket_diag_wanted) return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_DIAG on kets needs a shared H0 on one GPU");
+    method = SEQ_METHOD_GENERIC;      // (scratch sizing; launch_ket runs first and fails loudly if it cannot)
+  }
   // the sparse kernel is tried for density matrices with a shared H0 whenever the choice is the engine's
   const bool try_sparse = !ket && !d->H0_batch_stride && !sharded &&
                           (method == SEQ_METHOD_SPARSE || method == SEQ_METHOD_DIAG ||
@@ -1198,13 +1270,22 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   p.status = d->status; p.stats = d->stats;
   p.ws = (cplx*)e->ws.ptr; p.ws_stride = (long long)ws_per;
 
-  if (method != SEQ_METHOD_SPARSE && method != SEQ_METHOD_DIAG) CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  bool ket_ran = false;
+  if (ket && ket_diag_wanted) {
+    rc = launch_ket(e, d, p, G0, Gk, d->method == SEQ_METHOD_DIAG, &ket_ran);
+    if (rc) return rc;
+    if (ket_ran) e->last_method = SEQ_METHOD_DIAG;
+    else if (d->method == SEQ_METHOD_DIAG) return fail(e, SEQ_ERR_UNSUPPORTED, "SEQ_METHOD_DIAG (kets): the operators are not sums of a few diagonals (N=%d)", N);
+  }
+  if (method != SEQ_METHOD_SPARSE && method != SEQ_METHOD_DIAG && !ket_ran) CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
   if (method == SEQ_METHOD_SPARSE) {
     rc = launch_sparse(e, d, p, G0, Gk, spi);
     if (rc) return rc;
   } else if (method == SEQ_METHOD_DIAG) {
     rc = launch_diag(e, d, p, G0, Gk, spi, dpl, tail_ok ? &dpl_tail : nullptr, blk_ok ? &bpl : nullptr);
     if (rc) return rc;
+  } else if (method == SEQ_METHOD_GENERIC && ket && ket_ran) {
+    // (launched above)
   } else if (method == SEQ_METHOD_GENERIC) {
     size_t elems = ket ? (size_t)N : N2;
     int threads = (int)((elems + 31) / 32 * 32);
@@ -1390,8 +1471,43 @@ static int solve_host(seq_engine* e, const seq_solve_desc* d) {
   return SEQ_OK;
 }
 
+// NVTX range around every C-ABI solve (visible in Nsight Systems / ncu --nvtx) and, when SEQ_PERF_LOG names a file, one
+// JSON line per call appended to it: shape, method, kernel variant, launches, integration-kernel time, wall time of the call
+// (per-call perf record).  Logging synchronises the engine's stream to read the kernel time.
+struct SolveScope {
+  seq_engine* e; const seq_solve_desc* d; const char* what; int* rc;
+  std::chrono::steady_clock::time_point t0;
+  SolveScope(seq_engine* e_, const seq_solve_desc* d_, const char* what_, int* rc_) : e(e_), d(d_), what(what_), rc(rc_), t0(std::chrono::steady_clock::now()) {
+    nvtxRangePushA(what_);
+  }
+  ~SolveScope() {
+    nvtxRangePop();
+    const char* path = getenv("SEQ_PERF_LOG");
+    if (!path || !*path || !e || !d || (e->is_sub)) return;
+    const float kms = (*rc == SEQ_OK) ? seq_engine_last_kernel_ms(e) : -1.0f;      // (synchronises on the kernel's end event)
+    const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (FILE* f = fopen(path, "a")) {
+      fprintf(f, "{\"call\": \"%s\", \"rc\": %d, \"N\": %d, \"B\": %d, \"n_t\": %d, \"n_ch\": %d, \"n_c\": %d, \"n_ctd\": %d, \"n_e\": %d, \"n_out\": %d, "
+                 "\"ket\": %d, \"host_pointers\": %d, \"atol\": %.3g, \"rtol\": %.3g, \"method\": %d, \"variant\": \"%s\", \"launches\": %d, "
+                 "\"kernel_ms\": %.4f, \"call_wall_ms\": %.4f}\n",
+              what, *rc, d->N, d->B, d->n_t, d->n_ch, d->n_c, d->n_ctd, d->n_e, d->n_out, (d->flags & SEQ_FLAG_KET) ? 1 : 0,
+              (d->flags & SEQ_FLAG_HOST_POINTERS) ? 1 : 0, d->atol, d->rtol, e->last_method, e->variant.c_str(), e->launches, kms, wall);
+      fclose(f);
+    }
+  }
+};
+
+static int seq_engine_solve_impl(seq_engine* e, const seq_solve_desc* d);
+
 int seq_engine_solve(seq_engine* e, const seq_solve_desc* d) {
   if (!e) return SEQ_ERR_INVALID;
+  int rc = SEQ_OK;
+  SolveScope scope(e, d, "seq_engine_solve", &rc);
+  rc = seq_engine_solve_impl(e, d);
+  return rc;
+}
+
+static int seq_engine_solve_impl(seq_engine* e, const seq_solve_desc* d) {
   int rc = validate(e, d);
   if (rc) return rc;
   e->launches = 0;
