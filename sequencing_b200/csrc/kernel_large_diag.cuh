@@ -45,7 +45,8 @@ __global__ void large_diag_gt_kernel(const cplx* __restrict__ g0, const cplx* __
 }
 
 // one thread per element of this rank's row block (padding included: it is written as zero)
-__global__ void __launch_bounds__(256) large_diag_rhs_kernel(const __grid_constant__ LargeDiagArgs a) {
+// (K and cval as separate arguments: the device-controlled stepper picks them per attempt; a stays in the constant bank)
+__device__ __forceinline__ void large_diag_rhs_body(const LargeDiagArgs& a, double* __restrict__ Kout, const double* __restrict__ cval) {
   const int N = a.N, NP = a.NP;
   const long long total = (long long)a.m * NP;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(256) large_diag_rhs_kernel(const __grid_consta
         w.y -= vi.x - vj.x;
       }
       for (int t = 0; t < a.nLo; t++) {
-        const double rr = a.cval[a.lo_r[t]];
+        const double rr = cval[a.lo_r[t]];
         const cplx la = a.lam[(long long)a.lo_a[t] * N + i], lb = a.lam[(long long)a.lo_b[t] * N + j];
         w.x += rr * (la.x * lb.x + la.y * lb.y);
         w.y += rr * (la.y * lb.x - la.x * lb.y);
@@ -97,17 +98,18 @@ __global__ void __launch_bounds__(256) large_diag_rhs_kernel(const __grid_consta
         const int jj = j + a.lg_ob[t];
         if (ii >= 0 && ii < N && jj >= 0 && jj < N) {
           const int ri = a.lg_r[t];
-          const double rr = ri < 0 ? 1.0 : a.cval[ri];
+          const double rr = ri < 0 ? 1.0 : cval[ri];
           const cplx la = a.lam[(long long)a.lg_a[t] * N + i], lb = a.lam[(long long)a.lg_b[t] * N + j];
           const cplx wv = cmake(rr * (la.x * lb.x + la.y * lb.y), rr * (la.y * lb.x - la.x * lb.y));
           cfma(acc, wv, cmake(Yr[ii * NP + jj], Yi[ii * NP + jj]));
         }
       }
     }
-    a.K[idx] = acc.x;
-    a.K[a.k_plane + idx] = acc.y;
+    Kout[idx] = acc.x;
+    Kout[a.k_plane + idx] = acc.y;
   }
 }
+__global__ void __launch_bounds__(256) large_diag_rhs_kernel(const __grid_constant__ LargeDiagArgs a) { large_diag_rhs_body(a, a.K, a.cval); }
 
 // term lists in element units from the host copy of diag_flags_kernel's output (same walk as diag_plan)
 static inline bool large_diag_terms(int N, int n_c, int n_ctd, int n_ch, const int* flags, LargeDiagArgs* a, DiagFill* f) {

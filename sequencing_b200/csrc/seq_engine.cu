@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
+#include <cstddef>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -26,6 +27,7 @@
 #include "kernel_diagblk.cuh"
 #include "kernel_ket.cuh"
 #include "kernel_large_diag.cuh"
+#include "kernel_large_dev.cuh"
 
 using namespace seq;
 
@@ -543,6 +545,47 @@ __global__ void large_store_expect_kernel(const cplx* __restrict__ acc, void* __
   else ((double*)expect)[base + e * stride] = acc[e].x;
 }
 
+// Row statistics of the operators (device) -> ELL widths; decides whether SEQ_METHOD_SPARSE applies.
+// One small D2H copy + stream synchronisation.
+struct SparseInfo {
+  bool usable = false;       // widths within the kernel's limits and a launch plan exists
+  bool worthwhile = false;   // fewer multiply-adds than the dense tensor-core formulation by a wide margin
+  SparsePlan plan;
+  int* rowcnt = nullptr;     // device: [n_ops][N]
+};
+
+static int sparse_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, const cplx* Gk, const cplx* Lall, SparseInfo* info) {
+  const int N = d->N, n_g = d->n_ch + d->n_ctd, n_l = d->n_c + d->n_ctd, n_e = d->n_e;
+  const int n_ops = 1 + n_l + n_e;
+  size_t ints = (size_t)n_ops * N + 2 * (size_t)n_ops + (size_t)(n_e > 0 ? n_e : 1) * N + 16;
+  int rc = reserve(e, e->spinfo, ints * sizeof(int));
+  if (rc) return rc;
+  int* rowcnt = (int*)e->spinfo.ptr;
+  int* maxw = rowcnt + (size_t)n_ops * N;
+  int* total = maxw + n_ops;
+  CUDA_TRY(e, cudaMemsetAsync(maxw, 0, 2 * (size_t)n_ops * sizeof(int), e->stream));
+  dim3 grid(N, n_ops);
+  sparse_count_kernel<<<grid, 32, 0, e->stream>>>(G0, Gk, n_g, Lall, n_l, (const cplx*)d->E, N, rowcnt, maxw, total);
+  e->launches++;
+  std::vector<int> h(2 * (size_t)n_ops);
+  CUDA_TRY(e, cudaMemcpyAsync(h.data(), maxw, h.size() * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  int wL = 1;
+  for (int l = 0; l < n_l; l++) wL = h[1 + l] > wL ? h[1 + l] : wL;
+  long long nnzE = 0;
+  for (int q = 0; q < n_e; q++) nnzE += h[n_ops + 1 + n_l + q];
+  info->rowcnt = rowcnt;
+  const int wG = h[0] < 1 ? 1 : h[0];
+  info->worthwhile = sparse_worthwhile(N, n_l, wG, h.data() + 1);
+  info->plan.nnzE = (int)nnzE;
+  info->usable = wG <= SPARSE_MAX_WG && wL <= SPARSE_MAX_WL && nnzE < (1LL << 30) &&
+                 sparse_plan(N, n_g, n_l, wG, wL, (int)nnzE, e->max_smem_optin, &info->plan);
+  info->plan.nnzE = (int)nnzE;
+  info->plan.macs = 2LL * wG;
+  for (int l = 0; l < n_l; l++) info->plan.macs += (long long)h[1 + l] * h[1 + l];
+  return SEQ_OK;
+}
+
 static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams& p, const cplx* G0, const cplx* Gk) {
   const seq_comm* comm = e->comm;
   const int world = (comm && comm->world > 1) ? comm->world : 1;
@@ -595,7 +638,7 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
   size_t total = (size_t)(structured ? 0 : (1 + n_g + n_l + 1)) * opsz + ysz + (world > 1 ? lsz : 0) + (size_t)(2 + 7 + 1) * lsz + 64 + 2 + 2 * (size_t)(n_e + 1);
   rc = reserve(e, e->large, total * sizeof(double) + 256);
   if (rc) return rc;
-  if (!e->host_err) CUDA_TRY(e, cudaMallocHost((void**)&e->host_err, 2 * sizeof(double)));
+  if (!e->host_err) CUDA_TRY(e, cudaMallocHost((void**)&e->host_err, sizeof(LargeDev) + 64));      // error norm / control block read-backs
   double* base = (double*)e->large.ptr;
   double *G0p = nullptr, *Gkp = nullptr, *Lp = nullptr, *Gt = nullptr;
   if (!structured) {
@@ -658,6 +701,36 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
   CUDA_TRY(e, cudaMemcpyAsync(out_idx.data(), d->out_idx, sizeof(int) * d->n_out, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(e, cudaStreamSynchronize(st));
 
+  // ---- one GPU + structured operators: the step controller lives on the device (kernel_large_dev.cuh) - no per-step
+  // D2H copy / synchronisation; the host enqueues attempts ahead of the GPU.  SEQ_LARGE_HOST=1 keeps the host-driven loop.
+  const bool devctl = structured && world == 1 && n_g <= LDEV_MAXG && N <= 0xffff && !getenv("SEQ_LARGE_HOST");
+  LargeDev* ddev = nullptr;
+  int *e_off = nullptr; unsigned* e_ij = nullptr; cplx* e_val = nullptr;
+  if (devctl) {
+    SparseInfo spi;
+    rc = sparse_analyze(e, d, G0, Gk, p.L, &spi);      // row counts of the expectation operators -> COO lists
+    if (rc) return rc;
+    SparsePlan epl;
+    memset(&epl, 0, sizeof(epl));
+    epl.wG = 1; epl.wL = 1; epl.nnzE = spi.plan.nnzE;
+    SparsePack pk = sparse_pack_layout(N, 0, 0, n_e, epl);
+    rc = reserve(e, e->sched, pk.bytes + sizeof(LargeDev) + 512);
+    if (rc) return rc;
+    char* sb = (char*)e->sched.ptr;
+    e_off = (int*)(sb + pk.o_eoff); e_ij = (unsigned*)(sb + pk.o_eij); e_val = (cplx*)(sb + pk.o_eval);
+    ddev = (LargeDev*)(sb + (pk.bytes + 255) / 256 * 256);
+    const int n_ops = 1 + n_l + n_e;
+    int* rowoff = spi.rowcnt + (size_t)n_ops * N + 2 * (size_t)n_ops;
+    sparse_escan_kernel<<<1, 32, 0, st>>>(spi.rowcnt, n_l, n_e, N, rowoff, e_off);
+    e->launches++;
+    if (n_e > 0) {
+      dim3 ge(N, n_e);
+      sparse_fill_kernel<<<ge, 32, 0, st>>>(G0, Gk, n_g, p.L, n_l, p.E, N, 1, 1, nullptr, nullptr, nullptr, nullptr, nullptr, rowoff, e_ij, e_val, 1 + n_l);
+      e->launches++;
+    }
+    e->variant = "large/diagonals (device-resident step control)";
+  }
+
   for (int b = 0; b < B; b++) {
     // rho0 -> full stage buffer and this rank's rows
     large_pack_kernel<<<grid_for(yplane, sms), 256, 0, st>>>(p.state0 + (size_t)b * N * N, Yfull, N, NP, rows_full);
@@ -715,6 +788,61 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
 
     StepCtl ctl;
     ctl_init_at(ctl, p, p.t0 + p.dt * (double)out_idx[0]);
+    if (devctl) {
+      LargeDev h;
+      memset(&h, 0, sizeof(h));
+      h.ctl = ctl;
+      for (int j = 0; j < 7; j++) h.kmap[j] = j;
+      CUDA_TRY(e, cudaMemcpyAsync(ddev, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(e, cudaStreamSynchronize(st));      // (h lives on this stack frame)
+      LargeDevBufs bf;
+      bf.ybuf[0] = ycur; bf.ybuf[1] = ynew;
+      for (int j = 0; j < 7; j++) bf.kbuf[j] = kbuf[j];
+      bf.Yfull = Yfull; bf.mplane = mplane; bf.yplane = yplane;
+      LargeDiagArgs a = la;
+      a.N = N; a.NP = NP; a.m = m; a.Mrows = Mrows; a.row0 = row0; a.y_plane = yplane; a.k_plane = mplane;
+      a.Y = Yfull; a.K = nullptr; a.gt = dgt; a.lam = dlam; a.gdiag = dgdiag; a.cval = nullptr;
+      const int nDN = dfill.nD * N;
+      const int g_elem = grid_for(mplane, sms), g_comb = grid_for(lsz, sms);
+      auto outputs = [&]() {
+        if (n_e > 0) {
+          ldev_expect_kernel<<<n_e, 256, 0, st>>>(ddev, e_off, e_ij, e_val, Yfull, yplane, NP, p.expect, (long long)b * n_e * d->n_out, d->n_out,
+                                                  (p.flags & SEQ_FLAG_EXPECT_COMPLEX) ? 1 : 0);
+          e->launches++;
+        }
+        if (p.flags & SEQ_FLAG_STORE_STATES) {
+          ldev_store_kernel<<<grid_for((long long)N * N, sms), 256, 0, st>>>(ddev, Yfull, p.states + (size_t)b * d->n_out * N * N, N, NP, rows_full);
+          e->launches++;
+        }
+      };
+      ldev_ctl_kernel<<<1, 32, 0, st>>>(p, b, ddev, 1);
+      e->launches++;
+      outputs();
+      LargeDev* hdev = (LargeDev*)e->host_err;
+      const int chunk = 32;
+      long long guard_attempts = 0;
+      while (true) {
+        for (int q = 0; q < chunk; q++) {
+          for (int s_ = 0; s_ < 7; s_++) {
+            if (s_ > 0) { ldev_combine_kernel<<<g_comb, 256, 0, st>>>(ddev, bf, s_); e->launches++; }
+            ldev_gt_kernel<<<(nDN + 255) / 256, 256, 0, st>>>(ddev, s_, dg0, dgk, n_g, nDN, dgt);
+            e->launches++;
+            ldev_rhs_kernel<<<g_elem, 256, 0, st>>>(ddev, bf, s_, a);
+            e->launches++;
+          }
+          ldev_err_kernel<<<g_elem, 256, 0, st>>>(ddev, bf, p.atol, p.rtol, m, NP, N);
+          ldev_ctl_kernel<<<1, 32, 0, st>>>(p, b, ddev, 0);
+          e->launches += 2;
+          outputs();
+        }
+        CUDA_TRY(e, cudaMemcpyAsync(hdev, ddev, offsetof(LargeDev, cval), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(e, cudaStreamSynchronize(st));
+        if (!hdev->active) break;
+        guard_attempts += chunk;
+        if (guard_attempts > 100000000LL) return fail(e, SEQ_ERR_CUDA, "large path: the device step controller does not terminate");
+      }
+      ctl = hdev->ctl;
+    } else
     for (int o = 0; o < d->n_out; o++) {
       if (o > 0) {
         const double t_target = p.t0 + p.dt * (double)out_idx[o];
@@ -788,47 +916,6 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
     CUDA_TRY(e, cudaStreamSynchronize(st));   // h_status / h_stats live on this stack frame
   }
   CUDA_TRY(e, cudaGetLastError());
-  return SEQ_OK;
-}
-
-// Row statistics of the operators (device) -> ELL widths; decides whether SEQ_METHOD_SPARSE applies.
-// One small D2H copy + stream synchronisation.
-struct SparseInfo {
-  bool usable = false;       // widths within the kernel's limits and a launch plan exists
-  bool worthwhile = false;   // fewer multiply-adds than the dense tensor-core formulation by a wide margin
-  SparsePlan plan;
-  int* rowcnt = nullptr;     // device: [n_ops][N]
-};
-
-static int sparse_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, const cplx* Gk, const cplx* Lall, SparseInfo* info) {
-  const int N = d->N, n_g = d->n_ch + d->n_ctd, n_l = d->n_c + d->n_ctd, n_e = d->n_e;
-  const int n_ops = 1 + n_l + n_e;
-  size_t ints = (size_t)n_ops * N + 2 * (size_t)n_ops + (size_t)(n_e > 0 ? n_e : 1) * N + 16;
-  int rc = reserve(e, e->spinfo, ints * sizeof(int));
-  if (rc) return rc;
-  int* rowcnt = (int*)e->spinfo.ptr;
-  int* maxw = rowcnt + (size_t)n_ops * N;
-  int* total = maxw + n_ops;
-  CUDA_TRY(e, cudaMemsetAsync(maxw, 0, 2 * (size_t)n_ops * sizeof(int), e->stream));
-  dim3 grid(N, n_ops);
-  sparse_count_kernel<<<grid, 32, 0, e->stream>>>(G0, Gk, n_g, Lall, n_l, (const cplx*)d->E, N, rowcnt, maxw, total);
-  e->launches++;
-  std::vector<int> h(2 * (size_t)n_ops);
-  CUDA_TRY(e, cudaMemcpyAsync(h.data(), maxw, h.size() * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-  int wL = 1;
-  for (int l = 0; l < n_l; l++) wL = h[1 + l] > wL ? h[1 + l] : wL;
-  long long nnzE = 0;
-  for (int q = 0; q < n_e; q++) nnzE += h[n_ops + 1 + n_l + q];
-  info->rowcnt = rowcnt;
-  const int wG = h[0] < 1 ? 1 : h[0];
-  info->worthwhile = sparse_worthwhile(N, n_l, wG, h.data() + 1);
-  info->plan.nnzE = (int)nnzE;
-  info->usable = wG <= SPARSE_MAX_WG && wL <= SPARSE_MAX_WL && nnzE < (1LL << 30) &&
-                 sparse_plan(N, n_g, n_l, wG, wL, (int)nnzE, e->max_smem_optin, &info->plan);
-  info->plan.nnzE = (int)nnzE;
-  info->plan.macs = 2LL * wG;
-  for (int l = 0; l < n_l; l++) info->plan.macs += (long long)h[1 + l] * h[1 + l];
   return SEQ_OK;
 }
 

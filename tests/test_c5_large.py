@@ -97,7 +97,7 @@ def _check_large(gpu_engine, bp, tag):
     fin, ex, nrhs = sparse_truth(bp, rtol=1e-12, atol=1e-14)
     print(f"{tag}: sparse CPU truth, {nrhs} RHS evaluations in {time.time() - t0:.1f} s")
     out = gpu_engine.solve(bp)
-    assert out.method == "large" and out.variant == "large/diagonals" and out.status[0] == 0
+    assert out.method == "large" and out.variant.startswith("large/diagonals") and out.status[0] == 0
     td, de = _trace_distance(out.final_state[0], fin), float(np.max(np.abs(out.expect[0] - ex)))
     bp.atol, bp.rtol, bp.nsteps = 1e-13, 1e-11, 100000
     tight = gpu_engine.solve(bp)

@@ -466,14 +466,28 @@ def test_large_path_structured_rhs_matches_generic_and_zgemm(gpu_engine):
             return bp
         a, g, z = mk(), mk(), mk()
         a.method, g.method, z.method = _lib.METHOD_LARGE, _lib.METHOD_GENERIC, _lib.METHOD_LARGE
+
+        def mk_large():
+            bp = mk()
+            bp.method = _lib.METHOD_LARGE
+            return bp
         oa, og = gpu_engine.solve(a), gpu_engine.solve(g)
         os.environ["SEQ_LARGE_DENSE"] = "1"
         try:
             oz = gpu_engine.solve(z)
         finally:
             del os.environ["SEQ_LARGE_DENSE"]
-        assert oa.method == "large" and oa.variant == "large/diagonals" and oz.variant == "large/zgemm"
+        assert oa.method == "large" and oa.variant.startswith("large/diagonals") and "device-resident" in oa.variant and oz.variant == "large/zgemm"
         assert np.all(oa.status == 0)
+        os.environ["SEQ_LARGE_HOST"] = "1"      # the host-driven stepper (one D2H + sync per step): same decisions, same numbers
+        try:
+            oh = gpu_engine.solve(mk_large())
+        finally:
+            del os.environ["SEQ_LARGE_HOST"]
+        assert oh.variant == "large/diagonals"
+        for k in ("states", "expect", "final_state"):
+            assert np.max(np.abs(getattr(oa, k) - getattr(oh, k))) < 1e-14, k
+        np.testing.assert_array_equal(oa.stats[:, :3], oh.stats[:, :3])
         for other in (og, oz):
             assert np.max(np.abs(oa.states - other.states)) < 1e-12, N
             assert np.max(np.abs(oa.expect - other.expect)) < 1e-12, N
