@@ -39,10 +39,13 @@ struct BlkOps {
   int ll_a[BLK_ND][BLK_MAXLL], ll_b[BLK_ND][BLK_MAXLL], ll_r[BLK_ND][BLK_MAXLL];
   int kslots;               // stage-derivative slots in shared memory (the remaining ones are global-memory streams)
   int wslot;                // static weights: 0 registers, 1 shared memory (behind the slots), 2 one global table for the batch
+  int mirror;               // owners also write the mirrored (conjugated) block into Y: needed unless every gather stays inside the owned band
 };
 
 // flags[(c * n_ops + op) * (2N - 1) + o + N - 1] = 1 if operator `op` (numbering of diag_flags_kernel) has a non-zero on
-// diagonal o = da * s_c, |da| < D_c, that leaves its block of D_c * s_c indices (then the diagonal is not local)
+// diagonal o = da * s_c, |da| < D_c, that leaves its block of D_c * s_c indices (then the diagonal is not local);
+// flags[((n_cands + c) * n_ops + op) * (2N - 1) + ..] = 1 if diagonal o has a non-zero whose row and column differ in the
+// local index (a gathered term on such a diagonal does not move every outer pair by the same shift)
 struct BlkCands { int n; int s[8], D[8]; };
 __global__ void diagblk_cross_kernel(const __grid_constant__ BlkCands cands, const cplx* __restrict__ G0, const cplx* __restrict__ Gk, int n_g,
                                      const cplx* __restrict__ L, int N, int* __restrict__ flags) {
@@ -61,6 +64,8 @@ __global__ void diagblk_cross_kernel(const __grid_constant__ BlkCands cands, con
     }
     if (!nz) continue;
     const int i = (int)(t / N), j = (int)(t - (long long)i * N), o = j - i;
+    // second half of `flags`: the diagonal changes the LOCAL index somewhere (then its outer shift is not one constant)
+    if ((i / s) % D != (j / s) % D) flags[((long long)(gridDim.z + c) * n_ops + op) * (2 * N - 1) + (o + N - 1)] = 1;
     if (o % s != 0 || abs(o / s) >= D) continue;
     if (i / (D * s) != j / (D * s)) flags[((long long)c * n_ops + op) * (2 * N - 1) + (o + N - 1)] = 1;
   }
@@ -120,7 +125,22 @@ solve_diagblk_kernel(const __grid_constant__ SolveParams p, const __grid_constan
   if (sp.stage_e) {
     cplx* ev_s = (cplx*)(smem_diag + L.off_e);
     unsigned* ei_s = (unsigned*)(ev_s + (sp.nnzE > 0 ? sp.nnzE : 1));
-    for (int q = tid; q < sp.nnzE; q += nth) { ev_s[q] = sp.e_val[q]; ei_s[q] = sp.e_ij[q]; }
+    // staged lists hold RESOLVED locations: element index of rho_ji inside a Y buffer, bit 31 = "stored as its mirror
+    // rho_ij, conjugate it" (without mirror writes only the owned orientation of an outer pair exists in Y)
+    for (int q = tid; q < sp.nnzE; q += nth) {
+      ev_s[q] = sp.e_val[q];
+      const unsigned code = sp.e_ij[q];
+      int row = (int)(code >> 16), col = (int)(code & 0xffffu);      // rho[row][col] = rho_ji
+      unsigned flag = 0;
+      if (!bl.mirror) {
+        const int R = bl.R, s = bl.s, Ds = D * s;
+        const int r1 = (row / Ds) * s + row % s, r2 = (col / Ds) * s + col % s;
+        const int dd = (r2 - r1 + R) % R;
+        const bool owned = dd < (R + 1) / 2 || ((R & 1) == 0 && dd == R / 2 && r1 < R / 2);
+        if (!owned) { const int t = row; row = col; col = t; flag = 0x80000000u; }
+      }
+      ei_s[q] = (unsigned)(row * ld + col) | flag;
+    }
     eij = ei_s; eval_ = ev_s;
   }
   if (sp.stage_tab) {
@@ -187,6 +207,7 @@ solve_diagblk_kernel(const __grid_constant__ SolveParams p, const __grid_constan
   int yb = 0, gb = 0, tog = 0, ycur = 0;
   PROF_DECL
   // owner writes its block and (off the outer diagonal) the mirrored block
+  const bool wmirror = !isdiag && bl.mirror != 0;
   auto write_Y = [&](int boff, const cplx (&v)[EPT]) {
     if (valid) {
       // (offsets laundered through an empty asm: derived addresses are recomputed here instead of living in registers
@@ -201,7 +222,7 @@ solve_diagblk_kernel(const __grid_constant__ SolveParams p, const __grid_constan
 #pragma unroll
         for (int c2 = 0; c2 < D; c2++) {
           *(cplx*)(yo + a * SL + c2 * SR) = v[a * D + c2];
-          if (!isdiag) *(cplx*)(ym + c2 * SL + a * SR) = blk_conj(v[a * D + c2]);
+          if (wmirror) *(cplx*)(ym + c2 * SL + a * SR) = blk_conj(v[a * D + c2]);
         }
     }
   };
@@ -410,7 +431,13 @@ solve_diagblk_kernel(const __grid_constant__ SolveParams p, const __grid_constan
       const int q0 = sp.e_off[e], q1 = sp.e_off[e + 1];
       for (int q = q0 + lane; q < q1; q += 32) {
         const unsigned code = eij[q];
-        cfma(acc, eval_[q], ((const cplx*)Yb)[(code >> 16) * ld + (code & 0xffffu)]);   // E_ij rho_ji
+        if (sp.stage_e) {      // resolved at kernel start
+          cplx r = ((const cplx*)Yb)[code & 0x7fffffffu];
+          if (code >> 31) r.y = -r.y;
+          cfma(acc, eval_[q], r);
+        } else {
+          cfma(acc, eval_[q], ((const cplx*)Yb)[(code >> 16) * ld + (code & 0xffffu)]);   // E_ij rho_ji
+        }
       }
       if (q1 - q0 > 1) {          // projectors (the sweeps' e_ops) have a single entry: nothing to reduce
         acc.x = warp_sum(acc.x);
@@ -648,7 +675,7 @@ static inline void diagblk_candidates(int N, int n_l, const int* flags, BlkCands
 }
 
 // flags: diag_flags_kernel's output; cross: diagblk_cross_kernel's output for candidate (s, D) ([1 + n_l][2N-1]).
-static inline bool diagblk_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, int n_t, int nnzE, const int* flags, const int* cross, int s, int D,
+static inline bool diagblk_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, int n_t, int nnzE, const int* flags, const int* cross, const int* irreg, int s, int D,
                                 int max_smem, int sm_count, BlkPlan* bp) {
   const int n_l = n_c + n_ctd, Wd = 2 * N - 1, c = (int)sizeof(cplx);
   if (N < 2 || N > 0x7fff || D < 2 || D > 3 || N % (s * D) != 0) return false;
@@ -665,6 +692,7 @@ static inline bool diagblk_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, in
   bl.SL = s * o.ld * c; bl.SR = s * c;
   auto is_local = [&](int op, int off) { return off % s == 0 && abs(off / s) < D && !cross[(long long)op * Wd + off + N - 1]; };
   int maxoff = 0, gath = 0, gath_plain = 0;
+  bool need_mirror = false;      // some gather may read a block in the orientation its owner does not store
   long long fma = 0;      // per outer pair (D x D block)
   const int E2 = D * D;
   fma += 4LL * E2;        // static weight product
@@ -690,6 +718,7 @@ static inline bool diagblk_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, in
       maxoff = abs(off) > maxoff ? abs(off) : maxoff;
       fma += 2LL * 4 * E2;
       gath += 2; gath_plain += 2;
+      need_mirror = true;      // (a row or a column alone is shifted: the pair changes its band position)
     }
     o.nD++;
   }
@@ -724,6 +753,7 @@ static inline bool diagblk_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, in
           o.lg_a[o.nLg] = a * N * c; o.lg_b[o.nLg] = b2 * N * c; o.lg_r[o.nLg] = rate;
           o.lg_off[o.nLg] = (oa * o.ld + ob) * c;
           o.nLg++;
+          if (oa != ob || irreg[(long long)(1 + l) * Wd + oa + N - 1]) need_mirror = true;
           maxoff = abs(oa) > maxoff ? abs(oa) : maxoff;
           maxoff = abs(ob) > maxoff ? abs(ob) : maxoff;
           fma += 3LL * E2;
@@ -735,6 +765,7 @@ static inline bool diagblk_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, in
   o.nnzE = nnzE;
   bp->dp.maxoff = maxoff;
   bp->gathers = gath; bp->gathers_plain = gath_plain;
+  bl.mirror = need_mirror ? 1 : 0;      // (launch_diag also switches it on for stored states and unstaged expectation lists)
   o.n_el = N * (N + 1) / 2;
   // launch shape: one thread per outer pair, lpr lanes per outer row
   const int R = bl.R, Lb = R / 2 + 1;

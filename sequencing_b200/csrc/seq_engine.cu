@@ -985,7 +985,7 @@ static int diag_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, 
     BlkCands cands;
     diagblk_candidates(N, n_l, h.data(), &cands);
     if (cands.n > 0) {
-      const size_t ncross = (size_t)cands.n * (1 + n_l) * W;
+      const size_t ncross = 2 * (size_t)cands.n * (1 + n_l) * W;      // crossing flags, then local-index-change flags
       rc = reserve(e, e->dflags, (nflag + ncross) * sizeof(int) + 64);
       if (rc) return rc;
       int* cross = (int*)e->dflags.ptr + nflag;
@@ -998,7 +998,8 @@ static int diag_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, 
       CUDA_TRY(e, cudaStreamSynchronize(e->stream));
       BlkPlan cand;
       for (int c = 0; c < cands.n; c++) {
-        if (!diagblk_plan(N, n_g, d->n_c, d->n_ctd, d->n_ch, d->n_t, nnzE, h.data(), hc.data() + (size_t)c * (1 + n_l) * W, cands.s[c], cands.D[c], max_smem,
+        if (!diagblk_plan(N, n_g, d->n_c, d->n_ctd, d->n_ch, d->n_t, nnzE, h.data(), hc.data() + (size_t)c * (1 + n_l) * W,
+                          hc.data() + (size_t)(cands.n + c) * (1 + n_l) * W, cands.s[c], cands.D[c], max_smem,
                           e->sm_count, &cand))
           continue;
         if (cand.gathers >= cand.gathers_plain) continue;      // nothing became local
@@ -1018,7 +1019,7 @@ static int diag_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, 
 // ~0.63 of the time.  The cluster variant sums the error norm in a different order, so a tail trajectory agrees with
 // the others to rounding (1e-13), not bit for bit; SEQ_DIAG_NO_TAIL=1 switches the split off.
 static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, const cplx* G0, const cplx* Gk, const SparseInfo& info, DiagPlan& pl_plain,
-                       DiagPlan* tail, BlkPlan* blk) {
+                       DiagPlan* tail, BlkPlan* blk, bool plain_ok = true) {
   DiagPlan& pl = blk ? blk->dp : pl_plain;
   if (blk) tail = nullptr;
   const int N = d->N, n_g = p.n_g, n_l = p.n_c + p.n_ctd, n_e = p.n_e;
@@ -1062,13 +1063,64 @@ static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, c
   CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
   sp.lreal = h_imag == 0 ? 1 : 0;
   if (blk) {
-    char buf[384];
+    const char* why_mirror = blk->bl.mirror ? ", mirrored blocks written (a gather leaves the owned band)" : "";
+    if (p.flags & SEQ_FLAG_STORE_STATES) { blk->bl.mirror = 1; why_mirror = ", mirrored blocks written (stored states read the full matrix)"; }
+    else if (!sp.stage_e && sp.nnzE > 0) { blk->bl.mirror = 1; why_mirror = ", mirrored blocks written (expectation lists not staged)"; }
+    char buf[448];
     snprintf(buf, sizeof(buf), "diagblk: local mode dim %d stride %d kept in registers, 1 CTA x %d threads per trajectory (%d CTA%s/SM), %d elements/thread, "
-             "rolled stage loop, %s%d stage-derivative slots in shared memory + %d in L2, %d Y buffer%s%s, %d gathers/element (plain diag: %d), smem %zu B",
+             "rolled stage loop, %s%d stage-derivative slots in shared memory + %d in L2, %d Y buffer%s%s%s, %d gathers/element (plain diag: %d), smem %zu B",
              blk->bl.D, blk->bl.s, blk->threads, blk->minb, blk->minb > 1 ? "s" : "", blk->bl.D * blk->bl.D, blk->k1reg ? "k1 in registers, " : "", blk->bl.kslots, blk->gslots,
-             sp.ybufs, sp.ybufs > 1 ? "s" : "", pl.guard ? " + guard bands" : "", blk->gathers, blk->gathers_plain, pl.smem);
+             sp.ybufs, sp.ybufs > 1 ? "s" : "", pl.guard ? " + guard bands" : "", blk->bl.mirror ? why_mirror : ", owned half only (no mirror writes)", blk->gathers,
+             blk->gathers_plain, pl.smem);
     e->variant = buf;
     e->last_fma_per_rhs = blk->fma_per_rhs;
+    // Partial last wave.  Two CTAs per SM integrate two trajectories in the time one CTA alone needs for one (the kernel is
+    // latency-bound per CTA), so a batch that ends in at most half a wave of CTA slots leaves every SM half empty for a whole
+    // trajectory time (C2: 1024 = 3 x 296 + 136).  The plain diagonal kernel - 12 warps on ONE trajectory, one CTA per SM -
+    // finishes a trajectory in 0.72 of that time when it has the SM to itself: the rest runs on it, on a second stream, next
+    // to the main launch.  Same equations and step decisions; the two kernels order their sums differently, so a tail
+    // trajectory agrees with the block-local kernel to rounding (1e-15), not bit for bit.  SEQ_DIAG_NO_TAIL=1 switches it off.
+    const long long slots = (long long)blk->minb * e->sm_count, rest = d->B % slots;
+    const bool plain_tail = blk->minb > 1 && !e->is_sub && !getenv("SEQ_DIAG_NO_TAIL") && d->B > slots && rest > 0 && rest <= e->sm_count &&
+                            plain_ok && pl_plain.cl == 1 && pl_plain.kreg;
+    if (plain_tail) {
+      const long long b1 = d->B - rest;
+      SolveParams p1 = p, p2 = p;
+      p1.B = (int)b1;
+      p2.B = (int)rest;
+      p2.tab = p.tab + b1 * p.tab_bstride_c;
+      p2.tab_rate = p.tab_rate + b1 * p.tab_bstride_r;
+      if (p.coeff_scale) p2.coeff_scale = p.coeff_scale + b1 * p.n_ch;
+      p2.state0 = p.state0 + b1 * N * N;
+      if (p.expect) p2.expect = (char*)p.expect + (size_t)b1 * p.n_e * p.n_out * ((p.flags & SEQ_FLAG_EXPECT_COMPLEX) ? sizeof(cplx) : sizeof(double));
+      p2.final_state = p.final_state + b1 * N * N;
+      if (p.states) p2.states = p.states + b1 * (long long)p.n_out * N * N;
+      p2.status = p.status + b1;
+      p2.stats = p.stats + 4 * b1;
+      p2.ws_stride = 0;
+      DiagOps& sp2 = pl_plain.ops;      // same tables: both plans walk the diagonals in the same order
+      sp2.e_off = sp.e_off; sp2.e_ij = sp.e_ij; sp2.e_val = sp.e_val;
+      sp2.g0 = sp.g0; sp2.gk = sp.gk; sp2.lam = sp.lam; sp2.gdiag = sp.gdiag; sp2.lreal = sp.lreal;
+      if (!e->aux) {
+        CUDA_TRY(e, cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
+        CUDA_TRY(e, cudaEventCreateWithFlags(&e->ev_aux0, cudaEventDisableTiming));
+        CUDA_TRY(e, cudaEventCreateWithFlags(&e->ev_aux1, cudaEventDisableTiming));
+      }
+      CUDA_TRY(e, cudaEventRecord(e->ev_aux0, e->stream));
+      CUDA_TRY(e, cudaStreamWaitEvent(e->aux, e->ev_aux0, 0));
+      // (the main launch first: its CTAs fill whole waves of CTA slots; the tail's CTAs - one per SM, they need the whole
+      // shared memory - start as SMs drain at the end of the last full wave)
+      rc = launch_diagblk_kernel(p1, *blk, e->stream);
+      if (rc == SEQ_OK) rc = launch_diag_kernel(p2, sp2, pl_plain, e->aux);
+      if (rc) return fail(e, rc, "block-local diagonal kernel launch configuration failed for N=%d (tail split)", N);
+      CUDA_TRY(e, cudaEventRecord(e->ev_aux1, e->aux));
+      CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_aux1, 0));
+      e->launches += 2;
+      char b2[128];
+      snprintf(b2, sizeof(b2), "; last %lld trajectories on the plain diagonal kernel (%d threads%s, 1 CTA/SM)", rest, pl_plain.threads, pl_plain.cw ? " + controller warp" : "");
+      e->variant += b2;
+      return SEQ_OK;
+    }
     rc = launch_diagblk_kernel(p, *blk, e->stream);
     if (rc) return fail(e, rc, "block-local diagonal kernel launch configuration failed for N=%d", N);
     e->launches++;

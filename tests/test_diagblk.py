@@ -28,7 +28,8 @@ def _same(a, g, tol=1e-12):
     np.testing.assert_array_equal(a.stats[:, :3], g.stats[:, :3])
 
 
-def kron_problem(dims, local, B=3, n_t=10, seed=0, drive_other=False, complex_l=False, td_collapse=False, store_states=True, hscale=0.3, max_step=None):
+def kron_problem(dims, local, B=3, n_t=10, seed=0, drive_other=False, complex_l=False, td_collapse=False, store_states=True, hscale=0.3, max_step=None,
+                 exchange=True):
     """A product space ``dims`` with ladder-operator drives on mode ``local`` (and optionally on another mode), Kerr /
     cross-Kerr / exchange terms in H0, decay + excitation + dephasing on every mode - the operator structure of
     ``System.H0`` / ``System.c_ops`` - at random strengths."""
@@ -47,7 +48,7 @@ def kron_problem(dims, local, B=3, n_t=10, seed=0, drive_other=False, complex_l=
     for p in range(len(dims)):
         for q in range(p + 1, len(dims)):
             H0 = H0 + rng.normal() * 0.05 * n[p] @ n[q]
-    if len(dims) > 1:
+    if len(dims) > 1 and exchange:
         other = (local + 1) % len(dims)
         g = 0.02 * rng.normal()
         H0 = H0 + g * (a[local] @ a[other].conj().T + a[local].conj().T @ a[other])      # exchange coupling: a gathered diagonal
@@ -93,6 +94,28 @@ def test_blk_matches_generic_and_plain_on_product_spaces(gpu_engine, dims, local
             del os.environ["SEQ_DIAG_BLK"]
         assert not plain.variant.startswith("diagblk")
         _same(blk, plain, tol=1e-11 if "hscale" in kw else 1e-12)
+
+
+@pytest.mark.parametrize("dims,local", [((3, 5), 0), ((3, 4), 0), ((4, 3), 1), ((2, 3, 4), 1), ((3, 3, 3), 0), ((3, 15), 0)])
+def test_blk_owned_half_only_when_every_gather_stays_in_the_band(gpu_engine, dims, local):
+    """Only the local mode is driven and nothing couples the modes by exchange: every gathered term is a collapse pair
+    (o, o) of another mode, which moves an outer pair along its own band position - the kernel then writes the owned
+    orientation of every block only (no mirror writes) and resolves the expectation operators' entries at kernel start.
+    Odd and even outer dimensions (the half-way band position is owned by the lower rows only), one and several
+    hi-blocks, expectation operators with off-diagonal entries, against the FP64-FMA kernel."""
+    def mk():
+        bp = kron_problem(dims, local, seed=3 + sum(dims), exchange=False, store_states=False, n_t=14)
+        rng = np.random.default_rng(1)
+        h = rng.normal(size=bp.E[0].shape) + 1j * rng.normal(size=bp.E[0].shape)
+        bp.E = bp.E.copy()
+        bp.E[1] = bp.E[1] + 0.1 * (h + h.conj().T) * (np.abs(np.subtract.outer(np.arange(bp.N), np.arange(bp.N))) <= 2)      # a few off-diagonals
+        return bp
+    blk = _solve(gpu_engine, mk(), _lib.METHOD_DIAG)
+    assert blk.variant.startswith("diagblk") and "no mirror writes" in blk.variant, blk.variant
+    _same(blk, _solve(gpu_engine, mk(), _lib.METHOD_GENERIC), tol=1e-10)
+    st = mk()
+    st.store_states = True          # stored states read the full matrix: the mirror comes back
+    assert "no mirror writes" not in _solve(gpu_engine, st, _lib.METHOD_DIAG).variant
 
 
 def test_blk_is_what_auto_runs_on_the_named_workloads(gpu_engine):
