@@ -383,7 +383,7 @@ def cpu_baseline_child(workload):
 STRICT_TOL = {"c1": (1e-10, 1e-8), "c3": (1e-10, 1e-8), "c4": (1e-10, 1e-8), "c2": (1e-12, 1e-10), "c2small": (1e-12, 1e-10)}
 
 
-def parity_block(eng, bp, workload, n_samples):
+def parity_block(eng, bp, workload, n_samples, method=None):
     """Engine vs the CPU oracle at MATCHED atol/rtol on trajectories spread over the sweep: pass fraction of the
     outputs (final-state trace distance and expectation-trace max-abs error <= 1e-6) at the reference's default
     tolerances and at the strict pair, both attributed against the converged (strict) oracle run.  The oracle is the
@@ -399,6 +399,8 @@ def parity_block(eng, bp, workload, n_samples):
         arr = getattr(sub, name)
         if arr is not None and arr.shape[0] == bp.B:
             setattr(sub, name, np.ascontiguousarray(arr[idx]))
+    if method is not None:
+        sub.method = method      # (the kernel the bench timed: AUTO would keep the plain diagonal kernel for so small a batch)
     outs = {}
     for atol, rtol in (default, strict):
         sub.atol, sub.rtol = atol, rtol
@@ -642,6 +644,14 @@ def ours(args):
                                              "lists (seq_engine_last_fma_per_rhs; terms a thread skips statically are not counted; stage "
                                              "combinations, error norm and outputs are not counted either)")
                 ex = sw["executed_flops_per_rhs"] * float(np.sum(stats[:, 2])) / (k_ms * 1e-3) / 1e12
+                extra = int(eng.lib.seq_engine_last_step_extra_ops(eng.handle))
+                if extra > 0:
+                    # everything the FP64 pipe executes: + stage combinations and error estimate of every step (counted per 4(3)
+                    # step; the few 5(4) steps execute more).  ncu's sm__pipe_fp64_cycles_active of the same launch is in
+                    # profiles/r02_diagblk_c2_ncu_summary.json (17.2 % before the tail split / owned-half changes).
+                    steps_all = float(np.sum(stats[:, 0]) + np.sum(stats[:, 1]))
+                    roof["fp64_pipe_instructions_TFLOP_equiv"] = ex + 2.0 * extra * steps_all / (k_ms * 1e-3) / 1e12
+                    roof["fp64_pipe_frac_counted"] = roof["fp64_pipe_instructions_TFLOP_equiv"] / FP64_FMA_PEAK_TFLOPS
                 roof.update({"bound": "fp64-fma", "achieved": ex, "peak": FP64_FMA_PEAK_TFLOPS * peak_scale, "frac": ex / (FP64_FMA_PEAK_TFLOPS * peak_scale),
                              "structured": sw, "executed_fp64_TFLOPs": ex, "executed_fp64_frac_of_fma_peak": ex / FP64_FMA_PEAK_TFLOPS,
                              "dense_equivalent_TFLOPs": achieved, "dense_equivalent_speedup": achieved / (FP64_DMMA_PEAK_TFLOPS * peak_scale),
@@ -675,7 +685,8 @@ def ours(args):
         parity = None
         if world == 1 and args.parity_samples > 0 and not rows_mode and args.workload in STRICT_TOL:
             try:
-                parity = parity_block(eng, bp, args.workload, args.parity_samples)
+                parity = parity_block(eng, bp, args.workload, args.parity_samples, seqlib.METHOD_DIAG if out_h.method == "diag" else None)
+                parity["engine_kernel"] = kname
             except Exception as exc:
                 parity = {"error": repr(exc)}
         line = {

@@ -184,6 +184,9 @@ const char* seq_engine_last_variant(const seq_engine* eng);
  * (zero terms a thread skips statically are not counted); 0 when the kernel does not report it.  bench.py turns it
  * into the executed fraction of the FP64-FMA peak. */
 int64_t seq_engine_last_fma_per_rhs(const seq_engine* eng);
+/* FP64 pipe instructions of one accepted 4(3) step of one trajectory OUTSIDE its right-hand sides (stage combinations, error
+ * estimate incl. the IEEE square root / division sequences), counted the same way; 0 when not reported. */
+int64_t seq_engine_last_step_extra_ops(const seq_engine* eng);
 
 /* Number of kernel launches issued by the last seq_engine_solve on this handle, and the
  * duration in milliseconds of its integration kernel measured with CUDA events on the

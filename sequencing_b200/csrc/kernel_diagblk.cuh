@@ -651,6 +651,8 @@ struct BlkPlan {
   int gathers;          // shared-memory gathers per element and RHS that remain
   int gathers_plain;    // ... of the plain diagonal kernel on the same operators
   long long fma_per_rhs;   // FP64 multiply-adds one right-hand side executes (all threads of a trajectory)
+  long long fp64_step_extra;   // FP64 pipe instructions of one 4(3) step outside the right-hand sides: stage combinations (28 per element) and
+                               // the error estimate (41 per element, of which ~18 are the IEEE square root and division sequences)
 };
 
 // Candidate local modes from the diagonal offsets that occur: (s, D) with D in {3, 2, 4} and N a multiple of s D.
@@ -773,6 +775,7 @@ static inline bool diagblk_plan(int N, int n_g, int n_c, int n_ctd, int n_ch, in
   bp->threads = (R * bl.lpr + 31) / 32 * 32;
   if (bp->threads > 512) return false;
   bp->fma_per_rhs = fma * ((long long)R * (R + 1) / 2);
+  bp->fp64_step_extra = 69LL * D * D * ((long long)R * (R + 1) / 2);
   o.nct = bp->threads;
   const int E = D * D;
   const int guard_el = maxoff * o.ld + maxoff + 1;

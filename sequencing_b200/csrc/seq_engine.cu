@@ -51,7 +51,7 @@ struct seq_engine {
   int launches = 0;
   int last_method = 0;
   double probe_err = SEQ_PROBE_ERR_DEFAULT, stay_err = SEQ_STAY_ERR_DEFAULT;   // order-switch thresholds handed to every kernel
-  long long last_fma_per_rhs = 0;   // FP64 multiply-adds per right-hand side of the last solve's kernel (0: not counted)
+  long long last_fma_per_rhs = 0, last_fp64_step_extra = 0;   // FP64 multiply-adds per right-hand side of the last solve's kernel (0: not counted)
   std::string variant;              // human-readable detail of what the last solve ran
   int sm_count = 0;
   int max_smem_optin = 0;
@@ -485,6 +485,7 @@ int seq_engine_last_method(const seq_engine* e) { return e ? e->last_method : 0;
 const char* seq_engine_last_variant(const seq_engine* e) { return e ? e->variant.c_str() : ""; }
 
 int64_t seq_engine_last_fma_per_rhs(const seq_engine* e) { return e ? (int64_t)e->last_fma_per_rhs : 0; }
+int64_t seq_engine_last_step_extra_ops(const seq_engine* e) { return e ? (int64_t)e->last_fp64_step_extra : 0; }
 
 float seq_engine_last_kernel_ms(seq_engine* e) {
   if (e && e->chunks > 1) return e->chunk_ms;
@@ -1007,6 +1008,10 @@ static int diag_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, 
       }
     }
   }
+  // A batch that does not even fill one CTA per SM is latency-bound per trajectory, and there the plain kernel's twelve warps
+  // on one trajectory finish it in 0.72 of the time the block-local kernel's four do (which wins by running two trajectories
+  // per SM).  Under AUTO such batches keep the plain kernel - e.g. a 1024-point sweep strong-scaled over 8 GPUs.
+  if (*blk_ok && blk->minb > 1 && d->method == SEQ_METHOD_AUTO && d->B <= e->sm_count) *blk_ok = false;
   const int rest = d->B % e->sm_count;
   if (*usable && pl->cl == 1 && !e->is_sub && !getenv("SEQ_DIAG_NO_TAIL") && d->B > e->sm_count && rest > 0 && 2 * rest <= e->sm_count && N >= 16)
     *tail_ok = diag_plan(N, n_g, d->n_c, d->n_ctd, d->n_ch, d->n_t, nnzE, h.data(), max_smem, 2, false, tail) && tail->cl == 2 && tail->kreg;
@@ -1074,6 +1079,7 @@ static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, c
              blk->gathers_plain, pl.smem);
     e->variant = buf;
     e->last_fma_per_rhs = blk->fma_per_rhs;
+    e->last_fp64_step_extra = blk->fp64_step_extra;
     // Partial last wave.  Two CTAs per SM integrate two trajectories in the time one CTA alone needs for one (the kernel is
     // latency-bound per CTA), so a batch that ends in at most half a wave of CTA slots leaves every SM half empty for a whole
     // trajectory time (C2: 1024 = 3 x 296 + 136).  The plain diagonal kernel - 12 warps on ONE trajectory, one CTA per SM -
@@ -1359,6 +1365,7 @@ static int solve_device(seq_engine* e, const seq_solve_desc* d) {
   }
   e->last_method = method;
   e->last_fma_per_rhs = 0;
+  e->last_fp64_step_extra = 0;
   e->variant.clear();
 
   const size_t ws_per = ws_elems_per_traj(d, method);
@@ -1602,6 +1609,7 @@ static int solve_host(seq_engine* e, const seq_solve_desc* d) {
   e->launches = launches;
   e->last_method = e->sub[0]->last_method;
   e->last_fma_per_rhs = e->sub[0]->last_fma_per_rhs;
+  e->last_fp64_step_extra = e->sub[0]->last_fp64_step_extra;
   char buf[64];
   snprintf(buf, sizeof(buf), " [host solve pipelined in %d chunks]", nchunk);
   e->variant = e->sub[0]->variant + buf;

@@ -23,7 +23,7 @@ EXPORTS = (
     "seq_engine_last_error", "seq_engine_workspace_bytes", "seq_engine_solve",
     "seq_engine_select_method", "seq_engine_last_launch_count", "seq_engine_last_kernel_ms",
     "seq_engine_spline_prep", "seq_engine_apply_unitary", "seq_engine_expect", "seq_engine_solve_sharded",
-    "seq_engine_last_method", "seq_engine_last_variant", "seq_engine_last_fma_per_rhs", "seq_engine_synth_gaussian",
+    "seq_engine_last_method", "seq_engine_last_variant", "seq_engine_last_fma_per_rhs", "seq_engine_last_step_extra_ops", "seq_engine_synth_gaussian",
 )
 
 
@@ -107,6 +107,8 @@ def load():
     lib.seq_engine_last_variant.restype = C.c_char_p
     lib.seq_engine_last_fma_per_rhs.argtypes = [vp]
     lib.seq_engine_last_fma_per_rhs.restype = C.c_int64
+    lib.seq_engine_last_step_extra_ops.argtypes = [vp]
+    lib.seq_engine_last_step_extra_ops.restype = C.c_int64
     lib.seq_engine_last_kernel_ms.argtypes = [vp]
     lib.seq_engine_last_kernel_ms.restype = C.c_float
     lib.seq_engine_spline_prep.argtypes = [vp, vp, vp, i64, i32, C.c_double]

@@ -121,7 +121,7 @@ def test_blk_owned_half_only_when_every_gather_stays_in_the_band(gpu_engine, dim
 def test_blk_is_what_auto_runs_on_the_named_workloads(gpu_engine):
     """C2 (transmon(3) x cavity(15)) keeps the qubit inside a thread: 1 shared-memory gather per element instead of 6; C4
     (two transmons + bus) keeps one transmon.  Against the plain diagonal kernel: identical step counts, 1e-13."""
-    for bp_mk, gath in ((lambda: workloads.c2_selective(3, 5, sigma=20), "1 gathers/element (plain diag: 6)"), (lambda: workloads.c4_two_transmons_bus(5), None)):
+    for bp_mk, gath in ((lambda: workloads.c2_selective(13, 12, sigma=20), "1 gathers/element (plain diag: 6)"), (lambda: workloads.c4_two_transmons_bus(5), None)):
         auto = gpu_engine.solve(bp_mk())
         assert auto.method == "diag" and auto.variant.startswith("diagblk"), auto.variant
         if gath:
@@ -133,6 +133,8 @@ def test_blk_is_what_auto_runs_on_the_named_workloads(gpu_engine):
             del os.environ["SEQ_DIAG_BLK"]
         assert plain.method == "diag" and not plain.variant.startswith("diagblk")
         _same(auto, plain, tol=1e-13)
+    small = gpu_engine.solve(workloads.c2_selective(3, 5, sigma=20))      # fewer trajectories than SMs: latency-bound, the plain kernel is faster
+    assert small.method == "diag" and not small.variant.startswith("diagblk")
 
 
 def test_blk_random_diagonals_take_it_only_when_a_diagonal_is_local(gpu_engine):
