@@ -1087,7 +1087,7 @@ static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, c
     // to the main launch.  Same equations and step decisions; the two kernels order their sums differently, so a tail
     // trajectory agrees with the block-local kernel to rounding (1e-15), not bit for bit.  SEQ_DIAG_NO_TAIL=1 switches it off.
     const long long slots = (long long)blk->minb * e->sm_count, rest = d->B % slots;
-    const bool plain_tail = blk->minb > 1 && !e->is_sub && !getenv("SEQ_DIAG_NO_TAIL") && d->B > slots && rest > 0 && rest <= e->sm_count &&
+    const bool plain_tail = blk->minb > 1 && !getenv("SEQ_DIAG_NO_TAIL") && d->B > slots && rest > 0 && rest <= e->sm_count &&
                             plain_ok && pl_plain.cl == 1 && pl_plain.kreg;
     if (plain_tail) {
       const long long b1 = d->B - rest;
@@ -1534,7 +1534,7 @@ static int host_chunks(const seq_engine* e, const seq_solve_desc* d) {
   if (env && atoi(env) > 0) n = atoi(env);
   else {
     if (pick_method(e, d) == SEQ_METHOD_LARGE) return 1;
-    const long long per = d->N > 6 ? 2LL * e->sm_count : 8LL * 128 * e->sm_count;
+    const long long per = d->N > 6 ? 3LL * e->sm_count : 8LL * 128 * e->sm_count;      // (N > 6: 2 chunks for the 1024-point C2 sweep - measured best: 19.4 k vs 19.15 k with 3, 19.0 k unchunked)
     n = d->B / per;
     if (n > 4) n = 4;
   }
@@ -1565,8 +1565,17 @@ static int solve_host(seq_engine* e, const seq_solve_desc* d) {
   int launches = 0, rc = SEQ_OK;
   float ms = 0.f;
   long long b0 = 0;
+  // CTA-per-trajectory kernels (N > 6): chunks of whole waves of CTA slots (two CTAs per SM for the block-local diagonal
+  // kernel, one otherwise - 2 x SMs is a multiple of both), the rest goes with the last chunk, where the kernel's own
+  // partial-wave handling sees it; equal chunks of 341 trajectories would each end in a 0.15 wave of their own
+  const long long wave = d->N > 6 ? 2LL * e->sm_count : 0;
+  const long long full_waves = wave ? d->B / wave : 0;
   for (int c = 0; c < nchunk && rc == SEQ_OK; c++) {
-    const long long nb = (d->B - b0 + (nchunk - c) - 1) / (nchunk - c);
+    long long nb = (d->B - b0 + (nchunk - c) - 1) / (nchunk - c);
+    if (wave && full_waves >= nchunk) {
+      const long long w_c = full_waves / nchunk + (c < full_waves % nchunk ? 1 : 0);
+      nb = (c == nchunk - 1) ? d->B - b0 : w_c * wave;
+    }
     seq_engine* s = e->sub[c & 1];
     if (c >= 2) {                       // the handle's counters of chunk c-2 are about to be overwritten
       launches += s->launches;
