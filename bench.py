@@ -469,8 +469,12 @@ def ours(args):
 
     comm = keep = None
     if rows_mode and world > 1:
-        from sequencing_b200.distributed import make_comm
-        comm, keep = make_comm()
+        # NCCL issued by the engine itself (seq_engine_nccl_init); --hooks keeps the torch.distributed callbacks of round 1
+        if args.hooks:
+            from sequencing_b200.distributed import make_comm
+            comm, keep = make_comm(stream=eng.stream)
+        else:
+            eng.init_native_comm()
 
     gathered = {}
 
@@ -725,6 +729,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--hooks", action="store_true", help="c5 on N > 1 GPUs: collectives through torch.distributed callbacks instead of the engine's own NCCL communicator")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1: every GPU its own full sweep (weak) or the named sweep cut into N slices (strong)")
     ap.add_argument("--parity-samples", type=int, default=8, help="trajectories of the sweep checked against the CPU oracle for the `parity` block (0: skip)")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense tensor-core kernel run reported in roofline.dense_kernel")

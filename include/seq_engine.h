@@ -170,6 +170,15 @@ typedef struct seq_comm {
 } seq_comm;
 int seq_engine_solve_sharded(seq_engine* eng, const seq_solve_desc* desc, const seq_comm* comm);
 
+/* Native NCCL communicator for seq_engine_solve_sharded (no hooks, no host callback per collective): the engine opens
+ * libnccl.so.2 at run time (the library the host process already carries - no link-time dependency) and issues
+ * ncclAllGather / ncclAllReduce on its own stream.  Rank 0 obtains an id (128 bytes), the host broadcasts it by whatever
+ * means it has (torch.distributed, MPI, a file), every rank calls _init with its rank; afterwards
+ * seq_engine_solve_sharded(eng, desc, NULL) shards over that communicator.  _destroy releases it. */
+int seq_engine_nccl_unique_id(void* id_out_128_bytes);
+int seq_engine_nccl_init(seq_engine* eng, const void* id_128_bytes, int32_t rank, int32_t world);
+int seq_engine_nccl_destroy(seq_engine* eng);
+
 /* Method the engine would pick for this descriptor (SEQ_METHOD_*), without running it. */
 int seq_engine_select_method(const seq_engine* eng, const seq_solve_desc* desc);
 

@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
 #include <nvtx3/nvToolsExt.h>
 
 #include "common.cuh"
@@ -45,6 +46,9 @@ struct seq_engine {
   std::string err;
   DevBuf ws, gbuf, tab, cprime, pack, stage_in, stage_out, large, sched, spinfo, dflags;
   const seq_comm* comm = nullptr;   // set for the duration of seq_engine_solve_sharded
+  void* nccl_comm = nullptr;        // native communicator (seq_engine_nccl_init), used when solve_sharded gets comm == NULL
+  int nccl_rank = 0, nccl_world = 1;
+  seq_comm nccl_hooks;              // hooks that issue NCCL calls on this engine's stream
   double* host_err = nullptr;       // pinned: error norm read back once per step by the large-N stepper
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
@@ -409,9 +413,80 @@ static size_t ws_elems_per_traj(const seq_solve_desc* d, int method) {
 }
 
 // ------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen of the library the host process already carries): no link-time dependency
+// ------------------------------------------------------------------------------------------
+struct NcclId { char internal[128]; };      // ncclUniqueId (passed by value)
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static bool nccl_load() {
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    void* h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) continue;
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllGather && g_nccl.AllReduce && g_nccl.CommDestroy) { g_nccl.lib = h; return true; }
+    dlclose(h);
+  }
+  return false;
+}
+#define SEQ_NCCL_DOUBLE 8   /* ncclFloat64 */
+#define SEQ_NCCL_SUM 0      /* ncclSum */
+static int nccl_hook_all_gather(void* ctx, const double* send, double* recv, int64_t count) {
+  seq_engine* e = (seq_engine*)ctx;
+  return g_nccl.AllGather(send, recv, (size_t)count, SEQ_NCCL_DOUBLE, e->nccl_comm, e->stream);
+}
+static int nccl_hook_all_reduce(void* ctx, double* buf, int64_t count) {
+  seq_engine* e = (seq_engine*)ctx;
+  return g_nccl.AllReduce(buf, buf, (size_t)count, SEQ_NCCL_DOUBLE, SEQ_NCCL_SUM, e->nccl_comm, e->stream);
+}
+
+// ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
 extern "C" {
+
+int seq_engine_nccl_unique_id(void* id_out) {
+  if (!id_out || !nccl_load()) return SEQ_ERR_UNSUPPORTED;
+  return g_nccl.GetUniqueId(id_out) == 0 ? SEQ_OK : SEQ_ERR_CUDA;
+}
+
+int seq_engine_nccl_init(seq_engine* e, const void* id, int32_t rank, int32_t world) {
+  if (!e || !id || world < 1 || rank < 0 || rank >= world) return SEQ_ERR_INVALID;
+  if (!nccl_load()) return fail(e, SEQ_ERR_UNSUPPORTED, "libnccl.so.2 could not be opened: %s", dlerror());
+  if (e->nccl_comm) { g_nccl.CommDestroy(e->nccl_comm); e->nccl_comm = nullptr; }
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  NcclId nid;
+  memcpy(&nid, id, sizeof(nid));
+  const int rc = g_nccl.CommInitRank(&e->nccl_comm, world, nid, rank);
+  if (rc != 0) { e->nccl_comm = nullptr; return fail(e, SEQ_ERR_CUDA, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"); }
+  e->nccl_rank = rank; e->nccl_world = world;
+  e->nccl_hooks.rank = rank; e->nccl_hooks.world = world; e->nccl_hooks.ctx = e;
+  e->nccl_hooks.all_gather = nccl_hook_all_gather;
+  e->nccl_hooks.all_reduce_sum = nccl_hook_all_reduce;
+  return SEQ_OK;
+}
+
+int seq_engine_nccl_destroy(seq_engine* e) {
+  if (!e) return SEQ_ERR_INVALID;
+  if (e->nccl_comm && g_nccl.lib) { cudaStreamSynchronize(e->stream); g_nccl.CommDestroy(e->nccl_comm); }
+  e->nccl_comm = nullptr;
+  e->nccl_world = 1;
+  return SEQ_OK;
+}
 
 int seq_engine_abi_version(void) { return SEQ_ENGINE_ABI_VERSION; }
 
@@ -440,6 +515,7 @@ int seq_engine_destroy(seq_engine* e) {
   if (!e) return SEQ_OK;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
+  if (e->nccl_comm && g_nccl.lib) { g_nccl.CommDestroy(e->nccl_comm); e->nccl_comm = nullptr; }
   DevBuf* bufs[] = {&e->ws, &e->gbuf, &e->tab, &e->cprime, &e->pack, &e->stage_in, &e->stage_out, &e->large, &e->sched, &e->spinfo, &e->dflags};
   for (DevBuf* b : bufs) if (b->ptr) cudaFree(b->ptr);
   if (e->host_err) cudaFreeHost(e->host_err);
@@ -1696,6 +1772,7 @@ static int seq_engine_solve_impl(seq_engine* e, const seq_solve_desc* d) {
 
 int seq_engine_solve_sharded(seq_engine* e, const seq_solve_desc* d, const seq_comm* comm) {
   if (!e) return SEQ_ERR_INVALID;
+  if (!comm && e->nccl_comm && e->nccl_world > 1) comm = &e->nccl_hooks;      // the native communicator
   if (comm && comm->world > 1) {
     if (comm->rank < 0 || comm->rank >= comm->world || !comm->all_gather || !comm->all_reduce_sum)
       return fail(e, SEQ_ERR_INVALID, "bad communicator (rank %d of %d, hooks %p %p)", comm->rank, comm->world,

@@ -177,7 +177,7 @@ def make_comm(group=None, stream=None):
     return comm, (ag, ar, stats)
 
 
-def solve_rows_sharded(bp: BatchProblem, engine=None, group=None) -> BatchOutput:
+def solve_rows_sharded(bp: BatchProblem, engine=None, group=None, native=True) -> BatchOutput:
     """Integrate ONE large Lindblad system with rho row-sharded over every rank of the process group
     (config C5: transmon + two cavities, N = 1875, 8 x B200).  Every rank passes the same problem and
     receives the full result.  Without an initialised process group this is a single-GPU solve."""
@@ -189,6 +189,13 @@ def solve_rows_sharded(bp: BatchProblem, engine=None, group=None) -> BatchOutput
     engine = engine or Engine.get(torch.cuda.current_device())
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return engine.solve_rows_sharded(bp, None)
+    if native:
+        # NCCL calls issued by the engine itself (C, its own stream): no Python callback per collective
+        if getattr(engine, "native_world", 0) != dist.get_world_size(group):
+            engine.init_native_comm(group)
+        out = engine.solve_rows_sharded(bp, None)
+        out.comm_stats = {"native_nccl": True}
+        return out
     comm, keep = make_comm(group, stream=engine.stream)
     out = engine.solve_rows_sharded(bp, comm)
     out.comm_stats = keep[2]

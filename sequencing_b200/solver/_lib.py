@@ -23,6 +23,7 @@ EXPORTS = (
     "seq_engine_last_error", "seq_engine_workspace_bytes", "seq_engine_solve",
     "seq_engine_select_method", "seq_engine_last_launch_count", "seq_engine_last_kernel_ms",
     "seq_engine_spline_prep", "seq_engine_apply_unitary", "seq_engine_expect", "seq_engine_solve_sharded",
+    "seq_engine_nccl_unique_id", "seq_engine_nccl_init", "seq_engine_nccl_destroy",
     "seq_engine_last_method", "seq_engine_last_variant", "seq_engine_last_fma_per_rhs", "seq_engine_last_step_extra_ops", "seq_engine_synth_gaussian",
 )
 
@@ -105,6 +106,9 @@ def load():
     lib.seq_engine_last_method.argtypes = [vp]
     lib.seq_engine_last_variant.argtypes = [vp]
     lib.seq_engine_last_variant.restype = C.c_char_p
+    lib.seq_engine_nccl_unique_id.argtypes = [vp]
+    lib.seq_engine_nccl_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
+    lib.seq_engine_nccl_destroy.argtypes = [vp]
     lib.seq_engine_last_fma_per_rhs.argtypes = [vp]
     lib.seq_engine_last_fma_per_rhs.restype = C.c_int64
     lib.seq_engine_last_step_extra_ops.argtypes = [vp]

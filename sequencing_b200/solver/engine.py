@@ -283,6 +283,24 @@ class Engine:
         self._last_method = self.lib.seq_engine_last_method(self.handle)
         return self._finish(bp, outs)
 
+    def init_native_comm(self, group=None):
+        """NCCL communicator INSIDE the engine (``seq_engine_nccl_init``: libnccl opened at run time, collectives issued
+        from C on the engine's stream - no Python callback per all-gather).  Rank 0's id is broadcast over the
+        ``torch.distributed`` group.  Afterwards ``solve_rows_sharded(bp, None)`` shards over it."""
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        buf = (C.c_char * 128)()
+        if rank == 0:
+            self._check(self.lib.seq_engine_nccl_unique_id(buf))
+        box = [bytes(buf)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        idb = (C.c_char * 128).from_buffer_copy(box[0])
+        with self.torch.cuda.device(self.device):
+            self._check(self.lib.seq_engine_nccl_init(self.handle, idb, rank, world))
+        self.native_world = world
+        return world
+
     def solve_rows_sharded(self, bp: BatchProblem, comm: "_lib.Comm", tens=None, to_host=True):
         """ONE large system with rho row-sharded across the ranks of ``comm`` (C5): every rank calls
         this with the same ``bp`` and gets the full result.  ``comm`` carries the all-gather /
