@@ -1102,7 +1102,7 @@ static int diag_analyze(seq_engine* e, const seq_solve_desc* d, const cplx* G0, 
 static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, const cplx* G0, const cplx* Gk, const SparseInfo& info, DiagPlan& pl_plain,
                        DiagPlan* tail, BlkPlan* blk, bool plain_ok = true) {
   DiagPlan& pl = blk ? blk->dp : pl_plain;
-  if (blk) tail = nullptr;
+  if (blk && blk->minb > 1) tail = nullptr;      // (two CTAs per SM: the partial last wave goes to the plain kernel instead, below)
   const int N = d->N, n_g = p.n_g, n_l = p.n_c + p.n_ctd, n_e = p.n_e;
   // expectation operators as COO lists (layout shared with the ELL kernel), operator diagonals behind them
   SparsePlan epl;
@@ -1203,12 +1203,14 @@ static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, c
       e->variant += b2;
       return SEQ_OK;
     }
-    rc = launch_diagblk_kernel(p, *blk, e->stream);
-    if (rc) return fail(e, rc, "block-local diagonal kernel launch configuration failed for N=%d", N);
-    e->launches++;
-    return SEQ_OK;
-  }
-  {
+    if (!tail) {
+      rc = launch_diagblk_kernel(p, *blk, e->stream);
+      if (rc) return fail(e, rc, "block-local diagonal kernel launch configuration failed for N=%d", N);
+      e->launches++;
+      return SEQ_OK;
+    }
+    // (one CTA per SM: a rest of at most half a wave runs on the plain kernel's 2-CTA clusters, as it does for the plain kernel)
+  } else {
     char buf[224];
     snprintf(buf, sizeof(buf), "diag: %d CTA%s x %d threads%s per trajectory, %d elements/thread, stage vectors in %s, %d Y buffer%s%s, smem %zu B", pl.cl, pl.cl > 1 ? "s (cluster)" : "",
              pl.threads, pl.cw ? (sp.ybufs > 1 ? " + controller warp (speculative next step)" : " + controller warp") : "", pl.ept, pl.kreg ? "registers" : "L2 streams", sp.ybufs,
@@ -1243,7 +1245,7 @@ static int launch_diag(seq_engine* e, const seq_solve_desc* d, SolveParams& p, c
     CUDA_TRY(e, cudaEventRecord(e->ev_aux0, e->stream));
     CUDA_TRY(e, cudaStreamWaitEvent(e->aux, e->ev_aux0, 0));
     rc = launch_diag_kernel(p2, sp2, *tail, e->aux);
-    if (rc == SEQ_OK) rc = launch_diag_kernel(p1, sp, pl, e->stream);
+    if (rc == SEQ_OK) rc = blk ? launch_diagblk_kernel(p1, *blk, e->stream) : launch_diag_kernel(p1, sp, pl, e->stream);
     if (rc) return fail(e, rc, "diagonal kernel launch configuration failed for N=%d (tail split)", N);
     CUDA_TRY(e, cudaEventRecord(e->ev_aux1, e->aux));
     CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_aux1, 0));
