@@ -25,6 +25,7 @@ struct KetOps {
   int nTerm, nTab, has_w, maxoff;
   int t_tab[KET_MAXT], t_off[KET_MAXT], t_ch[KET_MAXT];
   int nnzE, stage_e;
+  int tpc, nt;               // trajectories per CTA (they share the tables), threads per trajectory
   const cplx* tabs;          // [nTab][N]; row 0: H0's main diagonal
   const int* e_off;          // COO lists of the expectation operators (layout shared with the ELL / diagonal kernels)
   const unsigned* e_ij;
@@ -57,64 +58,80 @@ __global__ void ket_fill_kernel(const __grid_constant__ KetFill f, const cplx* _
   tabs[(long long)t * N + i] = (j >= 0 && j < N) ? A[(long long)i * N + j] : cmake(0, 0);
 }
 
-struct KetLayout { int off_tabs, off_Y, off_y, off_k, off_cv, off_red, off_ctrl, off_e, total; };
+struct KetLayout { int off_tabs, off_e, traj0, traj_bytes, off_Y, off_y, off_k, off_cv, off_red, off_ctrl, total; };      // off_Y.. are relative to a trajectory's region
 __host__ __device__ inline KetLayout ket_layout(int N, int n_g, const KetOps& ko) {
   KetLayout L;
   const int c = (int)sizeof(cplx);
+  // shared by the trajectories of a CTA: the diagonal tables and the expectation lists
   L.off_tabs = 0;
-  L.off_Y = ko.nTab * N * c + ko.maxoff * c;                 // guard band of maxoff zeros on either side of the stage input
+  L.off_e = ko.nTab * N * c;
+  L.traj0 = L.off_e + (ko.stage_e ? (ko.nnzE > 0 ? ko.nnzE : 1) * 32 : 0);
+  // per trajectory: stage input between zero guard bands of maxoff elements, y, k1..k7, spline values, reduction scratch, control
+  L.off_Y = ko.maxoff * c;
   L.off_y = L.off_Y + N * c + ko.maxoff * c;
   L.off_k = L.off_y + N * c;
   L.off_cv = L.off_k + 7 * N * c;
   L.off_red = L.off_cv + 7 * (n_g > 0 ? n_g : 1) * (int)sizeof(double);
   L.off_red = (L.off_red + 15) / 16 * 16;
   L.off_ctrl = L.off_red + 64 * (int)sizeof(double);
-  L.off_e = L.off_ctrl + 128 + 192;
-  L.total = L.off_e + (ko.stage_e ? (ko.nnzE > 0 ? ko.nnzE : 1) * 32 : 0);
+  L.traj_bytes = (L.off_ctrl + 128 + 192 + 15) / 16 * 16;
+  L.total = L.traj0 + ko.tpc * L.traj_bytes;
   return L;
 }
 
+// named barrier of one trajectory's threads (0 is __syncthreads)
+__device__ __forceinline__ void ket_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// Up to two trajectories per CTA: the diagonal tables (the largest shared-memory item: terms x N x 16 B) are shared, every
+// trajectory has its own vectors, controller and named barrier - twice the warps per SM for a latency-bound kernel.
 template <int EPT>
-__global__ void __launch_bounds__(256) solve_ketdiag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__ KetOps ko) {
+__global__ void __launch_bounds__(512) solve_ketdiag_kernel(const __grid_constant__ SolveParams p, const __grid_constant__ KetOps ko) {
   extern __shared__ __align__(16) unsigned char smem_ket[];
-  const int N = p.N, n_g = p.n_g, nth = (int)blockDim.x, tid = threadIdx.x, b = blockIdx.x;
+  const int N = p.N, n_g = p.n_g, nth = ko.nt;
+  const int half = (int)threadIdx.x / nth, tid = (int)threadIdx.x - half * nth;
+  const int b = blockIdx.x * ko.tpc + half;
+  const bool live = b < p.B;                       // (an odd batch leaves the last CTA's second half idle)
   const int lane = tid & 31, warp = tid >> 5, nw = nth >> 5;
   const KetLayout L = ket_layout(N, n_g, ko);
   cplx* tabs = (cplx*)(smem_ket + L.off_tabs);
-  cplx* Ys = (cplx*)(smem_ket + L.off_Y);
-  cplx* y = (cplx*)(smem_ket + L.off_y);
-  cplx* kv = (cplx*)(smem_ket + L.off_k);
-  double* cv = (double*)(smem_ket + L.off_cv);
-  double* red = (double*)(smem_ket + L.off_red);
-  DiagCtrl* ctrl = (DiagCtrl*)(smem_ket + L.off_ctrl);
-  DiagCtlState* cst = (DiagCtlState*)(smem_ket + L.off_ctrl + 128);
-  const double2* tabc = p.tab + (long long)b * p.tab_bstride_c;
-  const double2* tabr = p.tab_rate + (long long)b * p.tab_bstride_r;
-  const double* cscale_b = p.coeff_scale ? p.coeff_scale + (long long)b * p.n_ch : nullptr;
+  unsigned char* mine = smem_ket + L.traj0 + half * L.traj_bytes;
+  cplx* Ys = (cplx*)(mine + L.off_Y);
+  cplx* y = (cplx*)(mine + L.off_y);
+  cplx* kv = (cplx*)(mine + L.off_k);
+  double* cv = (double*)(mine + L.off_cv);
+  double* red = (double*)(mine + L.off_red);
+  DiagCtrl* ctrl = (DiagCtrl*)(mine + L.off_ctrl);
+  DiagCtlState* cst = (DiagCtlState*)(mine + L.off_ctrl + 128);
+  const int bb = live ? b : 0;
+  const double2* tabc = p.tab + (long long)bb * p.tab_bstride_c;
+  const double2* tabr = p.tab_rate + (long long)bb * p.tab_bstride_r;
+  const double* cscale_b = p.coeff_scale ? p.coeff_scale + (long long)bb * p.n_ch : nullptr;
+  auto sync_traj = [&]() { ket_bar(1 + half, nth); };
 
-  for (int q = tid; q < L.off_y / 16; q += nth) ((cplx*)smem_ket)[q] = cmake(0, 0);      // guard bands (and everything before y)
+  for (int q = threadIdx.x; q < L.total / 16; q += blockDim.x) ((cplx*)smem_ket)[q] = cmake(0, 0);      // guard bands and everything else
   __syncthreads();
-  for (int q = tid; q < ko.nTab * N; q += nth) tabs[q] = ko.tabs[q];
+  for (int q = threadIdx.x; q < ko.nTab * N; q += blockDim.x) tabs[q] = ko.tabs[q];
   const unsigned* eij = ko.e_ij;
   const cplx* eval_ = ko.e_val;
   if (ko.stage_e) {
     cplx* ev_s = (cplx*)(smem_ket + L.off_e);
     unsigned* ei_s = (unsigned*)(ev_s + (ko.nnzE > 0 ? ko.nnzE : 1));
-    for (int q = tid; q < ko.nnzE; q += nth) { ev_s[q] = ko.e_val[q]; ei_s[q] = ko.e_ij[q]; }
+    for (int q = threadIdx.x; q < ko.nnzE; q += blockDim.x) { ev_s[q] = ko.e_val[q]; ei_s[q] = ko.e_ij[q]; }
     eij = ei_s; eval_ = ev_s;
   }
+  __syncthreads();
+  if (!live) return;                               // (after the CTA-wide barriers: the other half only uses its own named barrier from here on)
   const cplx* y0 = p.state0 + (long long)b * N;
   for (int i = tid; i < N; i += nth) { y[i] = y0[i]; Ys[i] = y0[i]; }
-  for (int q = tid; q < 7 * N; q += nth) kv[q] = cmake(0, 0);
   if (tid == 0) {
     StepCtl c0;
     ctl_init(c0, p);
     cst->ctl = c0;
     cst->htry = 0.0; cst->target = 0.0; cst->o = 0; cst->nst = 0; cst->landing = 0; cst->capped = 0; cst->dbg = 0; cst->nstA = 0;
   }
-  __syncthreads();
+  sync_traj();
   if (warp == 0) diag_controller(p, cst, ctrl, cv, tabc, tabr, cscale_b, 0, 0, 0.0, 0);
-  __syncthreads();
+  sync_traj();
 
   auto slot = [&](int j) -> cplx* { return kv + j * N; };      // slot j: k_{j+1}; FSAL: the last stage's slot is copied into slot 0 on commit
   // K = -i H(t) Ys for this thread's elements, stage values cvs[0..n_g)
@@ -146,10 +163,15 @@ __global__ void __launch_bounds__(256) solve_ketdiag_kernel(const __grid_constan
     if (p.flags & SEQ_FLAG_NORMALIZE) {
       double s = 0.0;
       for (int i = tid; i < N; i += nth) s += cabs2(y[i]);
-      s = block_sum(s, red);
+      s = warp_sum(s);
+      sync_traj();                 // (red may still be read by the error sum of the step before)
+      if (lane == 0) red[32 + warp] = s;
+      sync_traj();
+      s = 0.0;
+      for (int q = 0; q < nw; q++) s += red[32 + q];
       const double inv = 1.0 / sqrt(s);
       for (int i = tid; i < N; i += nth) y[i] = seq::cscale(inv, y[i]);
-      __syncthreads();
+      sync_traj();
     }
     for (int e = warp; e < p.n_e; e += nw) {      // <psi|E|psi> = sum_ij conj(psi_i) E_ij psi_j, one warp per operator
       cplx acc = cmake(0, 0);
@@ -179,7 +201,7 @@ __global__ void __launch_bounds__(256) solve_ketdiag_kernel(const __grid_constan
     const DiagCtrl c = *ctrl;
     if (c.accepted) {        // commit: y <- new state, k1 <- derivative of the last stage
       for (int i = tid; i < N; i += nth) { y[i] = Ys[i]; kv[i] = kv[(Slast - 1) * N + i]; }
-      __syncthreads();
+      sync_traj();
     }
     for (int o = c.emit_lo; o < c.emit_hi; o++) {
       emit(o);
@@ -205,9 +227,9 @@ __global__ void __launch_bounds__(256) solve_ketdiag_kernel(const __grid_constan
         const cplx v = y[i];
         Ys[i] = cmake(fma(htry, ax, v.x), fma(htry, ay, v.y));
       }
-      __syncthreads();
+      sync_traj();
       rhs(cv + st * n_g, slot(st));
-      __syncthreads();
+      sync_traj();
     }
     // error estimate (weighted RMS norm, as every other kernel)
     double es = 0.0;
@@ -225,13 +247,13 @@ __global__ void __launch_bounds__(256) solve_ketdiag_kernel(const __grid_constan
     }
     es = warp_sum(es);
     if (lane == 0) red[tog * 32 + warp] = es;
-    __syncthreads();
+    sync_traj();
     es = 0.0;
     for (int q = 0; q < nw; q++) es += red[tog * 32 + q];
     tog ^= 1;
     // (diag_controller normalises the error sum by N^2, the element count of a density matrix: a ket has N)
     if (warp == 0) diag_controller(p, cst, ctrl, cv, tabc, tabr, cscale_b, 1, S - st0, es * (double)N, 0);
-    __syncthreads();
+    sync_traj();
   }
 
   cplx* fin = p.final_state + (long long)b * N;
@@ -289,7 +311,11 @@ static inline bool ket_plan(int N, int n_ch, int n_g, int nnzE, const int* flags
   if (pl->threads > 256) pl->threads = 256;
   pl->ept = (N + pl->threads - 1) / pl->threads;
   if (pl->ept > KET_MAX_EPT) return false;
+  o.nt = pl->threads;
+  o.tpc = 2;                   // two trajectories per CTA when their vectors fit next to the shared tables
   o.stage_e = (nnzE > 0 && nnzE <= 2048) ? 1 : 0;
+  if (ket_layout(N, n_g, o).total > max_smem) o.stage_e = 0;
+  if (ket_layout(N, n_g, o).total > max_smem) { o.tpc = 1; o.stage_e = (nnzE > 0 && nnzE <= 2048) ? 1 : 0; }
   if (ket_layout(N, n_g, o).total > max_smem) o.stage_e = 0;
   if (ket_layout(N, n_g, o).total > max_smem) return false;
   pl->smem = (size_t)ket_layout(N, n_g, o).total;
@@ -301,7 +327,7 @@ template <int EPT>
 static int launch_ket_t(const SolveParams& p, const KetPlan& pl, cudaStream_t st) {
   auto kern = solve_ketdiag_kernel<EPT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) return SEQ_ERR_CUDA;
-  kern<<<(unsigned)p.B, (unsigned)pl.threads, pl.smem, st>>>(p, pl.ops);
+  kern<<<(unsigned)((p.B + pl.ops.tpc - 1) / pl.ops.tpc), (unsigned)(pl.threads * pl.ops.tpc), pl.smem, st>>>(p, pl.ops);
   return cudaGetLastError() == cudaSuccess ? SEQ_OK : SEQ_ERR_CUDA;
 }
 static inline int launch_ket_kernel(const SolveParams& p, const KetPlan& pl, cudaStream_t st) {
