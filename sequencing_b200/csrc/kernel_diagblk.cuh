@@ -220,10 +220,14 @@ solve_diagblk_kernel(const __grid_constant__ SolveParams p, const __grid_constan
 #pragma unroll
       for (int a = 0; a < D; a++)
 #pragma unroll
-        for (int c2 = 0; c2 < D; c2++) {
-          *(cplx*)(yo + a * SL + c2 * SR) = v[a * D + c2];
-          if (wmirror) *(cplx*)(ym + c2 * SL + a * SR) = blk_conj(v[a * D + c2]);
-        }
+        for (int c2 = 0; c2 < D; c2++) *(cplx*)(yo + a * SL + c2 * SR) = v[a * D + c2];
+      if (bl.mirror) {      // (a CTA-uniform branch: predicated-off stores would still take their issue slots)
+#pragma unroll
+        for (int a = 0; a < D; a++)
+#pragma unroll
+          for (int c2 = 0; c2 < D; c2++)
+            if (wmirror) *(cplx*)(ym + c2 * SL + a * SR) = blk_conj(v[a * D + c2]);
+      }
     }
   };
   // G(t) diagonals of one stage; two copies of the loop so that the staged tables are read with shared-memory loads
