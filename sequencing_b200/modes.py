@@ -125,12 +125,18 @@ class Mode(Parameterized):
 
     @property
     def ad(self):
-        return self.a.dag()
+        return self._embedded("ad", qt.create)
 
     @property
     def n(self):
-        a = self.a
-        return a.dag() * a
+        # (the embedded number operator, memoised: a^dag a as a dense N x N product on every access - it sits under
+        # detuning, dephasing and every "n" coupling term - was the largest single host cost of lowering a segment)
+        return self._embedded("n", lambda levels: qt.create(levels) * qt.destroy(levels))      # (a^dag a as the reference forms it: sqrt(k)^2, not k)
+
+    @property
+    def _adada(self):
+        """``a^dag a^dag a a`` (self-Kerr), memoised like the elementary operators."""
+        return self._embedded("adadaa", lambda levels: qt.create(levels) * qt.create(levels) * qt.destroy(levels) * qt.destroy(levels))
 
     @property
     def x(self):
@@ -148,9 +154,7 @@ class Mode(Parameterized):
 
     @property
     def self_kerr(self):
-        a = self.a
-        ad = a.dag()
-        return np.pi * self.kerr * (ad * ad * a * a)
+        return np.pi * self.kerr * self._adada
 
     # -- decoherence ---------------------------------------------------------------------
     @property
@@ -264,7 +268,11 @@ class Mode(Parameterized):
         the expression is evaluated with Python's ``eval`` over a namespace containing only the
         operators in ``OPERATORS`` and numpy (no builtins).
         """
-        namespace = {name: getattr(self, name) for name in self.OPERATORS}
+        # only the operators the expression names are built (each is an N x N Kronecker embedding; building all nine for
+        # every coupling term of every System.H0 access was half of the host cost of lowering a Sequence segment)
+        import re as _re
+        wanted = set(_re.findall(r"[A-Za-z_][A-Za-z0-9_]*", expr))
+        namespace = {name: getattr(self, name) for name in self.OPERATORS if name in wanted}
         namespace.update(np=np, pi=np.pi, sqrt=np.sqrt, exp=np.exp, sin=np.sin, cos=np.cos)
         return eval(expr, {"__builtins__": {}}, namespace)  # noqa: S307
 
