@@ -192,3 +192,18 @@ def test_blk_scaled_shared_table_and_complex_expect(gpu_engine):
     blk = _solve(gpu_engine, mk(), _lib.METHOD_DIAG)
     assert blk.variant.startswith("diagblk")
     _same(blk, _solve(gpu_engine, mk(), _lib.METHOD_GENERIC))
+
+
+def test_blk_without_expectation_operators_and_single_trajectory(gpu_engine):
+    """n_e = 0 (only final states are asked for) and B = 1: the owned-half mode needs no expectation lists at all."""
+    def mk(B):
+        bp = kron_problem((3, 5), 0, B=B, seed=11, exchange=False, store_states=False)
+        bp.E = np.zeros((0, bp.N, bp.N), complex)
+        return bp
+    for B in (1, 4):
+        blk = _solve(gpu_engine, mk(B), _lib.METHOD_DIAG)
+        assert blk.variant.startswith("diagblk") and "no mirror writes" in blk.variant, blk.variant
+        gen = _solve(gpu_engine, mk(B), _lib.METHOD_GENERIC)
+        assert blk.expect.shape[1] == 0
+        assert np.max(np.abs(blk.final_state - gen.final_state)) < 1e-11
+        np.testing.assert_array_equal(blk.stats[:, :3], gen.stats[:, :3])
