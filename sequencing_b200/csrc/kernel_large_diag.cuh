@@ -44,6 +44,62 @@ __global__ void large_diag_gt_kernel(const cplx* __restrict__ g0, const cplx* __
   gt[q] = g;
 }
 
+// one element K_ij of the structured right-hand side from the planar stage state (Yr / Yi: real / imaginary plane, leading
+// dimension NP); i, j < N
+__device__ __forceinline__ cplx large_diag_rhs_elem(const LargeDiagArgs& a, const double* __restrict__ Yr, const double* __restrict__ Yi, int NP,
+                                                    const double* __restrict__ cval, long long i, int j) {
+  const int N = a.N;
+  const cplx y = cmake(Yr[i * NP + j], Yi[i * NP + j]);
+  // static own-element weight
+  const cplx gi = a.gdiag[i], gj = a.gdiag[j];
+  cplx w = cmake(gi.y + gj.y, -(gi.x - gj.x));
+  for (int t = 0; t < a.nLs; t++) {
+    const cplx la = a.lam[(long long)a.ls_a[t] * N + i], lb = a.lam[(long long)a.ls_b[t] * N + j];
+    w.x += la.x * lb.x + la.y * lb.y;
+    w.y += la.y * lb.x - la.x * lb.y;
+  }
+  if (a.g0_tab >= 0) {
+    const cplx vi = a.gt[(long long)a.g0_tab * N + i], vj = a.gt[(long long)a.g0_tab * N + j];
+    w.x += vi.y + vj.y;
+    w.y -= vi.x - vj.x;
+  }
+  for (int t = 0; t < a.nLo; t++) {
+    const double rr = cval[a.lo_r[t]];
+    const cplx la = a.lam[(long long)a.lo_a[t] * N + i], lb = a.lam[(long long)a.lo_b[t] * N + j];
+    w.x += rr * (la.x * lb.x + la.y * lb.y);
+    w.y += rr * (la.y * lb.x - la.x * lb.y);
+  }
+  cplx acc = cmul(w, y);
+  for (int t = 0; t < a.nGo; t++) {
+    const int o = a.go_off[t];
+    const cplx* gv = a.gt + (long long)a.go_tab[t] * N;
+    const long long ii = i + o;
+    if (ii >= 0 && ii < N) {
+      const cplx vi = gv[i];
+      const cplx ya = cmake(Yr[ii * NP + j], Yi[ii * NP + j]);
+      cfma(acc, cmake(vi.y, -vi.x), ya);                       // -i v_d[i] Y[i+o, j]
+    }
+    const int jj = j + o;
+    if (jj >= 0 && jj < N) {
+      const cplx vj = gv[j];
+      const cplx yv = cmake(Yr[i * NP + jj], Yi[i * NP + jj]);
+      cfma(acc, cmake(vj.y, vj.x), yv);                        // +i conj(v_d[j]) Y[i, j+o]
+    }
+  }
+  for (int t = 0; t < a.nLg; t++) {
+    const long long ii = i + a.lg_oa[t];
+    const int jj = j + a.lg_ob[t];
+    if (ii >= 0 && ii < N && jj >= 0 && jj < N) {
+      const int ri = a.lg_r[t];
+      const double rr = ri < 0 ? 1.0 : cval[ri];
+      const cplx la = a.lam[(long long)a.lg_a[t] * N + i], lb = a.lam[(long long)a.lg_b[t] * N + j];
+      const cplx wv = cmake(rr * (la.x * lb.x + la.y * lb.y), rr * (la.y * lb.x - la.x * lb.y));
+      cfma(acc, wv, cmake(Yr[ii * NP + jj], Yi[ii * NP + jj]));
+    }
+  }
+  return acc;
+}
+
 // one thread per element of this rank's row block (padding included: it is written as zero)
 // (K and cval as separate arguments: the device-controlled stepper picks them per attempt; a stays in the constant bank)
 __device__ __forceinline__ void large_diag_rhs_body(const LargeDiagArgs& a, double* __restrict__ Kout, const double* __restrict__ cval) {
@@ -53,58 +109,7 @@ __device__ __forceinline__ void large_diag_rhs_body(const LargeDiagArgs& a, doub
     const int r = (int)(idx / NP), j = (int)(idx - (long long)r * NP);
     const long long i = a.row0 + r;
     cplx acc = cmake(0, 0);
-    if (r < a.Mrows && i < N && j < N) {
-      const double* Yr = a.Y;
-      const double* Yi = a.Y + a.y_plane;
-      const cplx y = cmake(Yr[i * NP + j], Yi[i * NP + j]);
-      // static own-element weight
-      const cplx gi = a.gdiag[i], gj = a.gdiag[j];
-      cplx w = cmake(gi.y + gj.y, -(gi.x - gj.x));
-      for (int t = 0; t < a.nLs; t++) {
-        const cplx la = a.lam[(long long)a.ls_a[t] * N + i], lb = a.lam[(long long)a.ls_b[t] * N + j];
-        w.x += la.x * lb.x + la.y * lb.y;
-        w.y += la.y * lb.x - la.x * lb.y;
-      }
-      if (a.g0_tab >= 0) {
-        const cplx vi = a.gt[(long long)a.g0_tab * N + i], vj = a.gt[(long long)a.g0_tab * N + j];
-        w.x += vi.y + vj.y;
-        w.y -= vi.x - vj.x;
-      }
-      for (int t = 0; t < a.nLo; t++) {
-        const double rr = cval[a.lo_r[t]];
-        const cplx la = a.lam[(long long)a.lo_a[t] * N + i], lb = a.lam[(long long)a.lo_b[t] * N + j];
-        w.x += rr * (la.x * lb.x + la.y * lb.y);
-        w.y += rr * (la.y * lb.x - la.x * lb.y);
-      }
-      acc = cmul(w, y);
-      for (int t = 0; t < a.nGo; t++) {
-        const int o = a.go_off[t];
-        const cplx* gv = a.gt + (long long)a.go_tab[t] * N;
-        const long long ii = i + o;
-        if (ii >= 0 && ii < N) {
-          const cplx vi = gv[i];
-          const cplx ya = cmake(Yr[ii * NP + j], Yi[ii * NP + j]);
-          cfma(acc, cmake(vi.y, -vi.x), ya);                       // -i v_d[i] Y[i+o, j]
-        }
-        const int jj = j + o;
-        if (jj >= 0 && jj < N) {
-          const cplx vj = gv[j];
-          const cplx yv = cmake(Yr[i * NP + jj], Yi[i * NP + jj]);
-          cfma(acc, cmake(vj.y, vj.x), yv);                        // +i conj(v_d[j]) Y[i, j+o]
-        }
-      }
-      for (int t = 0; t < a.nLg; t++) {
-        const long long ii = i + a.lg_oa[t];
-        const int jj = j + a.lg_ob[t];
-        if (ii >= 0 && ii < N && jj >= 0 && jj < N) {
-          const int ri = a.lg_r[t];
-          const double rr = ri < 0 ? 1.0 : cval[ri];
-          const cplx la = a.lam[(long long)a.lg_a[t] * N + i], lb = a.lam[(long long)a.lg_b[t] * N + j];
-          const cplx wv = cmake(rr * (la.x * lb.x + la.y * lb.y), rr * (la.y * lb.x - la.x * lb.y));
-          cfma(acc, wv, cmake(Yr[ii * NP + jj], Yi[ii * NP + jj]));
-        }
-      }
-    }
+    if (r < a.Mrows && i < N && j < N) acc = large_diag_rhs_elem(a, a.Y, a.Y + a.y_plane, NP, cval, i, j);
     Kout[idx] = acc.x;
     Kout[a.k_plane + idx] = acc.y;
   }

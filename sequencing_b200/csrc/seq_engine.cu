@@ -29,6 +29,7 @@
 #include "kernel_ket.cuh"
 #include "kernel_large_diag.cuh"
 #include "kernel_large_dev.cuh"
+#include "kernel_large_herm.cuh"
 
 using namespace seq;
 
@@ -44,7 +45,7 @@ struct seq_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
-  DevBuf ws, gbuf, tab, cprime, pack, stage_in, stage_out, large, sched, spinfo, dflags;
+  DevBuf ws, gbuf, tab, cprime, pack, stage_in, stage_out, large, sched, spinfo, dflags, herm;
   const seq_comm* comm = nullptr;   // set for the duration of seq_engine_solve_sharded
   void* nccl_comm = nullptr;        // native communicator (seq_engine_nccl_init), used when solve_sharded gets comm == NULL
   int nccl_rank = 0, nccl_world = 1;
@@ -516,7 +517,7 @@ int seq_engine_destroy(seq_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   if (e->nccl_comm && g_nccl.lib) { g_nccl.CommDestroy(e->nccl_comm); e->nccl_comm = nullptr; }
-  DevBuf* bufs[] = {&e->ws, &e->gbuf, &e->tab, &e->cprime, &e->pack, &e->stage_in, &e->stage_out, &e->large, &e->sched, &e->spinfo, &e->dflags};
+  DevBuf* bufs[] = {&e->ws, &e->gbuf, &e->tab, &e->cprime, &e->pack, &e->stage_in, &e->stage_out, &e->large, &e->sched, &e->spinfo, &e->dflags, &e->herm};
   for (DevBuf* b : bufs) if (b->ptr) cudaFree(b->ptr);
   if (e->host_err) cudaFreeHost(e->host_err);
   for (int q = 0; q < 2; q++) {
@@ -807,13 +808,59 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
     }
     e->variant = "large/diagonals (device-resident step control)";
   }
+  // ---- Hermitian tiles (kernel_large_herm.cuh): half of rho, stage combination / error estimate fused into the RHS kernel.
+  // SEQ_LARGE_FULL=1 keeps the full-matrix kernels; a non-Hermitian rho0 (checked per trajectory) takes them as well.
+  const bool herm_try = devctl && !getenv("SEQ_LARGE_FULL");
+  LargeHermBufs hb;
+  memset(&hb, 0, sizeof(hb));
+  int h_tiles = 0, NPh = 0;
+  unsigned long long* dchk = nullptr;
+  if (herm_try) {
+    const int nt = (N + LH_T - 1) / LH_T;
+    NPh = nt * LH_T;
+    h_tiles = nt * (nt + 1) / 2;
+    const size_t packed = (size_t)h_tiles * 2 * LH_TE, full = 2 * (size_t)NPh * NPh;
+    rc = reserve(e, e->herm, (2 * full + 9 * packed + 8) * sizeof(double) + (size_t)h_tiles * sizeof(unsigned) + 256);
+    if (rc) return rc;
+    double* hbase = (double*)e->herm.ptr;
+    for (int q = 0; q < 2; q++) { hb.Yfull[q] = hbase; hbase += full; }
+    for (int q = 0; q < 2; q++) { hb.ybuf[q] = hbase; hbase += packed; }
+    for (int q = 0; q < 7; q++) { hb.kbuf[q] = hbase; hbase += packed; }
+    dchk = (unsigned long long*)hbase; hbase += 8;
+    unsigned* dtiles = (unsigned*)hbase;
+    std::vector<unsigned> ht;
+    ht.reserve(h_tiles);
+    for (int ti = 0; ti < nt; ti++)
+      for (int tj = ti; tj < nt; tj++) ht.push_back((unsigned)ti | ((unsigned)tj << 16));
+    CUDA_TRY(e, cudaMemcpyAsync(dtiles, ht.data(), (size_t)h_tiles * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(e, cudaStreamSynchronize(st));
+    hb.tiles = dtiles; hb.yplane = (long long)NPh * NPh; hb.NPh = NPh; hb.N = N;
+  }
 
+  bool any_full = false;
   for (int b = 0; b < B; b++) {
+    bool herm = false;
+    if (herm_try) {      // rho0 -> packed upper tiles + full matrix 0, and is it Hermitian?
+      CUDA_TRY(e, cudaMemsetAsync(dchk, 0, 2 * sizeof(unsigned long long), st));
+      lh_pack_kernel<<<h_tiles, 256, 0, st>>>(p.state0 + (size_t)b * N * N, hb, dchk);
+      e->launches++;
+      double chk[2];
+      CUDA_TRY(e, cudaMemcpyAsync(chk, dchk, sizeof(chk), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(e, cudaStreamSynchronize(st));
+      herm = chk[1] <= 1e-20 * chk[0];
+    }
+    if (!herm) {
     // rho0 -> full stage buffer and this rank's rows
+    any_full = true;
     large_pack_kernel<<<grid_for(yplane, sms), 256, 0, st>>>(p.state0 + (size_t)b * N * N, Yfull, N, NP, rows_full);
     e->launches++;
     CUDA_TRY(e, cudaMemcpyAsync(ycur, Yfull + row0 * NP, mplane * sizeof(double), cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(e, cudaMemcpyAsync(ycur + mplane, Yfull + yplane + row0 * NP, mplane * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    // where the committed state is found as a full planar matrix (outputs, final state)
+    const double* Yc = herm ? hb.Yfull[0] : Yfull;
+    const int NPc = herm ? NPh : NP;
+    const long long rows_c = herm ? (long long)NPh : rows_full, yplane_c = herm ? hb.yplane : yplane;
 
     auto rhs = [&](double t, double* kout) -> int {
       if (n_g > 0) { large_coeff_kernel<<<1, 64, 0, st>>>(p, b, t, cval); e->launches++; }
@@ -877,18 +924,18 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
       for (int j = 0; j < 7; j++) bf.kbuf[j] = kbuf[j];
       bf.Yfull = Yfull; bf.mplane = mplane; bf.yplane = yplane;
       LargeDiagArgs a = la;
-      a.N = N; a.NP = NP; a.m = m; a.Mrows = Mrows; a.row0 = row0; a.y_plane = yplane; a.k_plane = mplane;
-      a.Y = Yfull; a.K = nullptr; a.gt = dgt; a.lam = dlam; a.gdiag = dgdiag; a.cval = nullptr;
+      a.N = N; a.NP = NPc; a.m = m; a.Mrows = Mrows; a.row0 = row0; a.y_plane = yplane_c; a.k_plane = mplane;
+      a.Y = Yc; a.K = nullptr; a.gt = dgt; a.lam = dlam; a.gdiag = dgdiag; a.cval = nullptr;
       const int nDN = dfill.nD * N;
       const int g_elem = grid_for(mplane, sms), g_comb = grid_for(lsz, sms);
       auto outputs = [&]() {
         if (n_e > 0) {
-          ldev_expect_kernel<<<n_e, 256, 0, st>>>(ddev, e_off, e_ij, e_val, Yfull, yplane, NP, p.expect, (long long)b * n_e * d->n_out, d->n_out,
+          ldev_expect_kernel<<<n_e, 256, 0, st>>>(ddev, e_off, e_ij, e_val, Yc, yplane_c, NPc, p.expect, (long long)b * n_e * d->n_out, d->n_out,
                                                   (p.flags & SEQ_FLAG_EXPECT_COMPLEX) ? 1 : 0);
           e->launches++;
         }
         if (p.flags & SEQ_FLAG_STORE_STATES) {
-          ldev_store_kernel<<<grid_for((long long)N * N, sms), 256, 0, st>>>(ddev, Yfull, p.states + (size_t)b * d->n_out * N * N, N, NP, rows_full);
+          ldev_store_kernel<<<grid_for((long long)N * N, sms), 256, 0, st>>>(ddev, Yc, p.states + (size_t)b * d->n_out * N * N, N, NPc, rows_c);
           e->launches++;
         }
       };
@@ -900,6 +947,19 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
       long long guard_attempts = 0;
       while (true) {
         for (int q = 0; q < chunk; q++) {
+          if (herm) {      // stage input of the first stage, then one fused kernel per stage (RHS + next stage input / error sum)
+            lh_first_kernel<<<h_tiles, 256, 0, st>>>(ddev, hb);
+            e->launches++;
+            for (int s_ = 0; s_ < 7; s_++) {
+              ldev_gt_kernel<<<(nDN + 255) / 256, 256, 0, st>>>(ddev, s_, dg0, dgk, n_g, nDN, dgt);
+              lh_stage_kernel<<<h_tiles, 256, 0, st>>>(ddev, hb, s_, a, p.atol, p.rtol);
+              e->launches += 2;
+            }
+            ldev_ctl_kernel<<<1, 32, 0, st>>>(p, b, ddev, 0);
+            e->launches++;
+            outputs();
+            continue;
+          }
           for (int s_ = 0; s_ < 7; s_++) {
             if (s_ > 0) { ldev_combine_kernel<<<g_comb, 256, 0, st>>>(ddev, bf, s_); e->launches++; }
             ldev_gt_kernel<<<(nDN + 255) / 256, 256, 0, st>>>(ddev, s_, dg0, dgk, n_g, nDN, dgt);
@@ -981,7 +1041,7 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
       }
     }
     if (ctl.status == SEQ_STATUS_OK) {
-      large_unpack_kernel<<<grid_for((long long)N * N, sms), 256, 0, st>>>(Yfull, p.final_state + (size_t)b * N * N, N, NP, rows_full);
+      large_unpack_kernel<<<grid_for((long long)N * N, sms), 256, 0, st>>>(Yc, p.final_state + (size_t)b * N * N, N, NPc, rows_c);
       e->launches++;
     } else {
       CUDA_TRY(e, cudaMemsetAsync(p.final_state + (size_t)b * N * N, 0, sizeof(cplx) * N * N, st));
@@ -992,6 +1052,7 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
     CUDA_TRY(e, cudaMemcpyAsync(p.stats + 4 * b, h_stats, sizeof(h_stats), cudaMemcpyHostToDevice, st));
     CUDA_TRY(e, cudaStreamSynchronize(st));   // h_status / h_stats live on this stack frame
   }
+  if (herm_try && !any_full) e->variant = "large/diagonals, Hermitian tiles (device-resident step control, stage combination and error estimate fused into the RHS kernel)";
   CUDA_TRY(e, cudaGetLastError());
   return SEQ_OK;
 }

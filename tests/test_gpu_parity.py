@@ -485,8 +485,19 @@ def test_large_path_structured_rhs_matches_generic_and_zgemm(gpu_engine):
         finally:
             del os.environ["SEQ_LARGE_HOST"]
         assert oh.variant == "large/diagonals"
+        # AUTO integrates the upper 32 x 32 tiles of the Hermitian rho with the stage combination fused into the RHS kernel;
+        # SEQ_LARGE_FULL=1 keeps the full-matrix kernels of the device-controlled stepper
+        assert "Hermitian tiles" in oa.variant
+        os.environ["SEQ_LARGE_FULL"] = "1"
+        try:
+            of = gpu_engine.solve(mk_large())
+        finally:
+            del os.environ["SEQ_LARGE_FULL"]
+        assert of.variant == "large/diagonals (device-resident step control)"
         for k in ("states", "expect", "final_state"):
-            assert np.max(np.abs(getattr(oa, k) - getattr(oh, k))) < 1e-14, k
+            assert np.max(np.abs(getattr(of, k) - getattr(oh, k))) < 1e-14, k
+            assert np.max(np.abs(getattr(oa, k) - getattr(oh, k))) < 1e-13, k
+        np.testing.assert_array_equal(of.stats[:, :3], oh.stats[:, :3])
         np.testing.assert_array_equal(oa.stats[:, :3], oh.stats[:, :3])
         for other in (og, oz):
             assert np.max(np.abs(oa.states - other.states)) < 1e-12, N
@@ -495,6 +506,48 @@ def test_large_path_structured_rhs_matches_generic_and_zgemm(gpu_engine):
     auto = row_sparse_problem(N=120, B=1, n_t=3, w_h=3, w_l=1, n_ch=1, n_c=1, n_e=1, seed=2)
     out = gpu_engine.solve(auto)
     assert out.method in ("large", "sparse")       # too large for the one-CTA kernels' register budget or ELL streams
+
+
+def test_large_path_hermitian_tiles_edges_and_non_hermitian_fallback(gpu_engine):
+    """Hermitian-tile stepper of the large path (kernel_large_herm.cuh): sizes around the 32-wide tile edge and both
+    embedded pairs against the full-matrix stepper; a non-Hermitian rho0 (a direct C-ABI caller may pass one - the
+    host mirror splits it into Hermitian parts) must take the full-matrix kernels and agree with the ZGEMM variant."""
+    import os
+    for N, max_step, atol in ((96, 1.0, 1e-8), (129, 0.0, 1e-8), (161, 0.0, 1e-12)):
+        def mk():
+            bp = row_sparse_problem(N=N, B=2, n_t=5, w_h=5, w_l=1, n_ch=2, n_c=2, n_ctd=1, n_e=2, seed=7 * N, hscale=0.7, store_states=True)
+            bp.max_step, bp.atol, bp.rtol = max_step, atol, atol * 100
+            bp.method = _lib.METHOD_LARGE
+            return bp
+        oa = gpu_engine.solve(mk())
+        os.environ["SEQ_LARGE_FULL"] = "1"
+        try:
+            of = gpu_engine.solve(mk())
+        finally:
+            del os.environ["SEQ_LARGE_FULL"]
+        assert "Hermitian tiles" in oa.variant and "Hermitian" not in of.variant and np.all(oa.status == 0)
+        for k in ("states", "expect", "final_state"):
+            assert np.max(np.abs(getattr(oa, k) - getattr(of, k))) < 1e-13, (N, k)
+        np.testing.assert_array_equal(oa.stats[:, :3], of.stats[:, :3])
+        assert np.max(np.abs(oa.final_state - np.conj(np.swapaxes(oa.final_state, 1, 2)))) < 1e-15      # mirrored tiles are exact conjugates
+    rng = np.random.default_rng(11)
+
+    def mk_nh():
+        bp = row_sparse_problem(N=100, B=2, n_t=4, w_h=5, w_l=1, n_ch=2, n_c=2, n_e=2, seed=5, hscale=0.5, store_states=True)
+        bp.state0[1] = bp.state0[1] + 0.2 * np.triu(rng.normal(size=(100, 100)), 1)      # trajectory 1 is not Hermitian
+        bp.method = _lib.METHOD_LARGE
+        return bp
+    rng = np.random.default_rng(11)
+    onh = gpu_engine.solve(mk_nh())
+    assert onh.variant == "large/diagonals (device-resident step control)"
+    os.environ["SEQ_LARGE_DENSE"] = "1"
+    rng = np.random.default_rng(11)
+    try:
+        oz = gpu_engine.solve(mk_nh())
+    finally:
+        del os.environ["SEQ_LARGE_DENSE"]
+    assert oz.variant == "large/zgemm"
+    assert np.max(np.abs(onh.states - oz.states)) < 1e-12 and np.max(np.abs(onh.expect - oz.expect)) < 1e-12
 
 
 def test_diag_kernel_two_cta_cluster_variant(gpu_engine, plain_diag):
