@@ -171,12 +171,15 @@ __global__ void ldev_err_kernel(LargeDev* __restrict__ dev, const __grid_constan
 }
 
 // Tr(E_e rho) of the committed state from COO lists of the expectation operators (E_ij at (i, j): sum E_ij rho_ji)
-__global__ void ldev_expect_kernel(const LargeDev* __restrict__ dev, const int* __restrict__ e_off, const unsigned* __restrict__ e_ij,
-                                   const cplx* __restrict__ e_val, const double* __restrict__ Y, long long y_plane, int NP, void* __restrict__ expect,
-                                   long long base, int n_out, int complex_out) {
-  __shared__ double red[34];
+struct LargeExpectArgs {
+  const int* e_off; const unsigned* e_ij; const cplx* e_val;
+  const double* Y; long long y_plane; int NP;
+  void* expect; long long base; int n_out, complex_out;
+};
+__device__ __forceinline__ void ldev_expect_body(const LargeDev* __restrict__ dev, const int e, const int* __restrict__ e_off, const unsigned* __restrict__ e_ij,
+                                                 const cplx* __restrict__ e_val, const double* __restrict__ Y, long long y_plane, int NP, void* __restrict__ expect,
+                                                 long long base, int n_out, int complex_out, double* red) {
   if (!dev->emit) return;
-  const int e = blockIdx.x;
   cplx acc = cmake(0, 0);
   for (int q = e_off[e] + threadIdx.x; q < e_off[e + 1]; q += blockDim.x) {
     const unsigned code = e_ij[q];
@@ -189,6 +192,12 @@ __global__ void ldev_expect_kernel(const LargeDev* __restrict__ dev, const int* 
     const long long off = base + (long long)e * n_out + dev->emit_o;
     if (complex_out) ((cplx*)expect)[off] = acc; else ((double*)expect)[off] = acc.x;
   }
+}
+__global__ void ldev_expect_kernel(const LargeDev* __restrict__ dev, const int* __restrict__ e_off, const unsigned* __restrict__ e_ij,
+                                   const cplx* __restrict__ e_val, const double* __restrict__ Y, long long y_plane, int NP, void* __restrict__ expect,
+                                   long long base, int n_out, int complex_out) {
+  __shared__ double red[34];
+  ldev_expect_body(dev, blockIdx.x, e_off, e_ij, e_val, Y, y_plane, NP, expect, base, n_out, complex_out, red);
 }
 
 __global__ void ldev_store_kernel(const LargeDev* __restrict__ dev, const double* __restrict__ src, cplx* __restrict__ states, int N, int NP, long long rows_pad) {

@@ -46,8 +46,22 @@ __global__ void large_diag_gt_kernel(const cplx* __restrict__ g0, const cplx* __
 
 // one element K_ij of the structured right-hand side from the planar stage state (Yr / Yi: real / imaginary plane, leading
 // dimension NP); i, j < N
+// G(t) diagonal `tab` at this element's row / column: from the table in global memory ...
+struct LargeGtGlobal {
+  const cplx* gt; int N; long long i; int j;
+  __device__ __forceinline__ cplx row(int tab) const { return gt[(long long)tab * N + i]; }
+  __device__ __forceinline__ cplx col(int tab) const { return gt[(long long)tab * N + j]; }
+};
+// ... or from the 2 x 32 entries a tile kernel built in shared memory ([tab][row | column][32])
+struct LargeGtTile {
+  const cplx* gts; int r, c;
+  __device__ __forceinline__ cplx row(int tab) const { return gts[tab * 64 + r]; }
+  __device__ __forceinline__ cplx col(int tab) const { return gts[tab * 64 + 32 + c]; }
+};
+
+template <class GT>
 __device__ __forceinline__ cplx large_diag_rhs_elem(const LargeDiagArgs& a, const double* __restrict__ Yr, const double* __restrict__ Yi, int NP,
-                                                    const double* __restrict__ cval, long long i, int j) {
+                                                    const double* __restrict__ cval, long long i, int j, const GT& G) {
   const int N = a.N;
   const cplx y = cmake(Yr[i * NP + j], Yi[i * NP + j]);
   // static own-element weight
@@ -59,7 +73,7 @@ __device__ __forceinline__ cplx large_diag_rhs_elem(const LargeDiagArgs& a, cons
     w.y += la.y * lb.x - la.x * lb.y;
   }
   if (a.g0_tab >= 0) {
-    const cplx vi = a.gt[(long long)a.g0_tab * N + i], vj = a.gt[(long long)a.g0_tab * N + j];
+    const cplx vi = G.row(a.g0_tab), vj = G.col(a.g0_tab);
     w.x += vi.y + vj.y;
     w.y -= vi.x - vj.x;
   }
@@ -72,16 +86,15 @@ __device__ __forceinline__ cplx large_diag_rhs_elem(const LargeDiagArgs& a, cons
   cplx acc = cmul(w, y);
   for (int t = 0; t < a.nGo; t++) {
     const int o = a.go_off[t];
-    const cplx* gv = a.gt + (long long)a.go_tab[t] * N;
     const long long ii = i + o;
     if (ii >= 0 && ii < N) {
-      const cplx vi = gv[i];
+      const cplx vi = G.row(a.go_tab[t]);
       const cplx ya = cmake(Yr[ii * NP + j], Yi[ii * NP + j]);
       cfma(acc, cmake(vi.y, -vi.x), ya);                       // -i v_d[i] Y[i+o, j]
     }
     const int jj = j + o;
     if (jj >= 0 && jj < N) {
-      const cplx vj = gv[j];
+      const cplx vj = G.col(a.go_tab[t]);
       const cplx yv = cmake(Yr[i * NP + jj], Yi[i * NP + jj]);
       cfma(acc, cmake(vj.y, vj.x), yv);                        // +i conj(v_d[j]) Y[i, j+o]
     }
@@ -109,7 +122,7 @@ __device__ __forceinline__ void large_diag_rhs_body(const LargeDiagArgs& a, doub
     const int r = (int)(idx / NP), j = (int)(idx - (long long)r * NP);
     const long long i = a.row0 + r;
     cplx acc = cmake(0, 0);
-    if (r < a.Mrows && i < N && j < N) acc = large_diag_rhs_elem(a, a.Y, a.Y + a.y_plane, NP, cval, i, j);
+    if (r < a.Mrows && i < N && j < N) acc = large_diag_rhs_elem(a, a.Y, a.Y + a.y_plane, NP, cval, i, j, LargeGtGlobal{a.gt, N, i, j});
     Kout[idx] = acc.x;
     Kout[a.k_plane + idx] = acc.y;
   }

@@ -29,6 +29,8 @@ struct LargeHermBufs {
   const unsigned* tiles;    // ti | tj << 16 of every upper tile
   long long yplane;         // NPh * NPh
   int NPh, N;
+  const cplx *g0, *gk;      // G diagonals: static part [nD][N] and time-dependent terms [n_g][nD][N] (diag_fill_kernel's tables)
+  int n_g, nD;
 };
 
 // v[q]: element (row w + 8 q, column lane) of tile (ti, tj) -> the tile and (ti != tj) its conjugate-transposed mirror
@@ -94,11 +96,20 @@ __global__ void __launch_bounds__(256) lh_pack_kernel(const cplx* __restrict__ s
   }
 }
 
-// input of the attempt's first stage -> full matrix st0 & 1: y itself (st0 = 0, k1 not known yet) or y + h a_10 k1
-__global__ void __launch_bounds__(256) lh_first_kernel(const LargeDev* __restrict__ dev, const __grid_constant__ LargeHermBufs bf) {
+// input of the attempt's first stage, y + h a_10 k1 -> full matrix 1.  (st0 = 0 - k1 not known yet, the first attempt of a
+// trajectory - needs nothing: the stage input is y itself, which lh_pack_kernel left in matrix 0.)
+// Blocks behind the tiles: expectation values of the committed state (matrix 0, which this kernel does not write), so
+// that an output costs no launch of its own.
+__global__ void __launch_bounds__(256) lh_first_kernel(const LargeDev* __restrict__ dev, const __grid_constant__ LargeHermBufs bf, int n_tiles,
+                                                       const __grid_constant__ LargeExpectArgs ex) {
   __shared__ double sm[2][LH_T][LH_T + 1];
+  if ((int)blockIdx.x >= n_tiles) {
+    ldev_expect_body(dev, (int)blockIdx.x - n_tiles, ex.e_off, ex.e_ij, ex.e_val, ex.Y, ex.y_plane, ex.NP, ex.expect, ex.base, ex.n_out, ex.complex_out, &sm[0][0][0]);
+    return;
+  }
   if (!dev->active) return;
   const int st0 = dev->st0;
+  if (st0 == 0) return;
   const unsigned code = bf.tiles[blockIdx.x];
   const int ti = code & 0xffffu, tj = code >> 16;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -110,13 +121,9 @@ __global__ void __launch_bounds__(256) lh_first_kernel(const LargeDev* __restric
 #pragma unroll
   for (int q = 0; q < 4; q++) {
     const int idx = (w + 8 * q) * LH_T + lane;
-    v[q] = cmake(y[idx], y[LH_TE + idx]);
-    if (st0) {
-      v[q].x = fma(h, fma(a10, k0[idx], 0.0), v[q].x);
-      v[q].y = fma(h, fma(a10, k0[LH_TE + idx], 0.0), v[q].y);
-    }
+    v[q] = cmake(fma(h, fma(a10, k0[idx], 0.0), y[idx]), fma(h, fma(a10, k0[LH_TE + idx], 0.0), y[LH_TE + idx]));
   }
-  lh_write_tile(bf.Yfull[st0 & 1], bf.yplane, bf.NPh, ti, tj, v, sm);
+  lh_write_tile(bf.Yfull[1], bf.yplane, bf.NPh, ti, tj, v, sm);
 }
 
 // stage st of the attempt on one upper tile: right-hand side, then the next stage input (or, last stage, the error sum)
@@ -124,6 +131,7 @@ __global__ void __launch_bounds__(256) lh_stage_kernel(LargeDev* __restrict__ de
                                                        const __grid_constant__ LargeDiagArgs a, double atol, double rtol) {
   __shared__ double sm[2][LH_T][LH_T + 1];
   __shared__ double red[34];
+  __shared__ cplx gts[DIAG_MAX_GD * 2 * LH_T];
   if (!dev->active || st < dev->st0 || st >= dev->S) return;
   const int pair = dev->ctl.pair, S = dev->S, N = bf.N, NP = bf.NPh;
   const bool last = st == S - 1;
@@ -137,11 +145,29 @@ __global__ void __launch_bounds__(256) lh_stage_kernel(LargeDev* __restrict__ de
   const double* cval = dev->cval + st * LDEV_MAXG;
   const int j = tj * LH_T + lane;
 
+  // G(t) diagonals of this stage time at the tile's 32 rows and 32 columns: g0 + sum_m c_m(t) gk_m
+  for (int q = threadIdx.x; q < bf.nD * 2 * LH_T; q += blockDim.x) {
+    const int d = q / (2 * LH_T), r = q % LH_T;
+    const int pos = (((q / LH_T) & 1) ? tj : ti) * LH_T + r;
+    cplx g = cmake(0, 0);
+    if (pos < N) {
+      g = bf.g0[(long long)d * N + pos];
+      for (int m = 0; m < bf.n_g; m++) {
+        const cplx gm = bf.gk[((long long)m * bf.nD + d) * N + pos];
+        const double c = cval[m];
+        g.x = fma(c, gm.x, g.x);
+        g.y = fma(c, gm.y, g.y);
+      }
+    }
+    gts[q] = g;
+  }
+  __syncthreads();
+
   cplx kv[4];
 #pragma unroll
   for (int q = 0; q < 4; q++) {
-    const int i = ti * LH_T + w + 8 * q;
-    kv[q] = (i < N && j < N) ? large_diag_rhs_elem(a, Yr, Yi, NP, cval, i, j) : cmake(0, 0);
+    const int r = w + 8 * q, i = ti * LH_T + r;
+    kv[q] = (i < N && j < N) ? large_diag_rhs_elem(a, Yr, Yi, NP, cval, i, j, LargeGtTile{gts, r, lane}) : cmake(0, 0);
   }
   {
     double* kd = bf.kbuf[dev->kmap[st]] + tbase;

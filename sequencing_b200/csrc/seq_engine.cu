@@ -835,6 +835,7 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
     CUDA_TRY(e, cudaMemcpyAsync(dtiles, ht.data(), (size_t)h_tiles * sizeof(unsigned), cudaMemcpyHostToDevice, st));
     CUDA_TRY(e, cudaStreamSynchronize(st));
     hb.tiles = dtiles; hb.yplane = (long long)NPh * NPh; hb.NPh = NPh; hb.N = N;
+    hb.g0 = dg0; hb.gk = dgk; hb.n_g = n_g; hb.nD = dfill.nD;
   }
 
   bool any_full = false;
@@ -941,23 +942,32 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
       };
       ldev_ctl_kernel<<<1, 32, 0, st>>>(p, b, ddev, 1);
       e->launches++;
-      outputs();
+      // (Hermitian tiles: the expectation values of a committed state ride in the next attempt's first kernel)
+      LargeExpectArgs exa;
+      exa.e_off = e_off; exa.e_ij = e_ij; exa.e_val = e_val; exa.Y = Yc; exa.y_plane = yplane_c; exa.NP = NPc;
+      exa.expect = p.expect; exa.base = (long long)b * n_e * d->n_out; exa.n_out = d->n_out; exa.complex_out = (p.flags & SEQ_FLAG_EXPECT_COMPLEX) ? 1 : 0;
+      auto store_h = [&]() {
+        if (p.flags & SEQ_FLAG_STORE_STATES) {
+          ldev_store_kernel<<<grid_for((long long)N * N, sms), 256, 0, st>>>(ddev, Yc, p.states + (size_t)b * d->n_out * N * N, N, NPc, rows_c);
+          e->launches++;
+        }
+      };
+      if (herm) store_h(); else outputs();
       LargeDev* hdev = (LargeDev*)e->host_err;
       const int chunk = 32;
       long long guard_attempts = 0;
       while (true) {
         for (int q = 0; q < chunk; q++) {
           if (herm) {      // stage input of the first stage, then one fused kernel per stage (RHS + next stage input / error sum)
-            lh_first_kernel<<<h_tiles, 256, 0, st>>>(ddev, hb);
+            lh_first_kernel<<<h_tiles + n_e, 256, 0, st>>>(ddev, hb, h_tiles, exa);
             e->launches++;
             for (int s_ = 0; s_ < 7; s_++) {
-              ldev_gt_kernel<<<(nDN + 255) / 256, 256, 0, st>>>(ddev, s_, dg0, dgk, n_g, nDN, dgt);
               lh_stage_kernel<<<h_tiles, 256, 0, st>>>(ddev, hb, s_, a, p.atol, p.rtol);
-              e->launches += 2;
+              e->launches++;
             }
             ldev_ctl_kernel<<<1, 32, 0, st>>>(p, b, ddev, 0);
             e->launches++;
-            outputs();
+            store_h();
             continue;
           }
           for (int s_ = 0; s_ < 7; s_++) {
@@ -974,7 +984,14 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
         }
         CUDA_TRY(e, cudaMemcpyAsync(hdev, ddev, offsetof(LargeDev, cval), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(e, cudaStreamSynchronize(st));
-        if (!hdev->active) break;
+        if (!hdev->active) {
+          if (herm && n_e > 0) {      // the last committed state's expectation values, had the chunk ended with its step
+            ldev_expect_kernel<<<n_e, 256, 0, st>>>(ddev, e_off, e_ij, e_val, Yc, yplane_c, NPc, p.expect, (long long)b * n_e * d->n_out, d->n_out,
+                                                    (p.flags & SEQ_FLAG_EXPECT_COMPLEX) ? 1 : 0);
+            e->launches++;
+          }
+          break;
+        }
         guard_attempts += chunk;
         if (guard_attempts > 100000000LL) return fail(e, SEQ_ERR_CUDA, "large path: the device step controller does not terminate");
       }
