@@ -171,11 +171,6 @@ __global__ void ldev_err_kernel(LargeDev* __restrict__ dev, const __grid_constan
 }
 
 // Tr(E_e rho) of the committed state from COO lists of the expectation operators (E_ij at (i, j): sum E_ij rho_ji)
-struct LargeExpectArgs {
-  const int* e_off; const unsigned* e_ij; const cplx* e_val;
-  const double* Y; long long y_plane; int NP;
-  void* expect; long long base; int n_out, complex_out;
-};
 __device__ __forceinline__ void ldev_expect_body(const LargeDev* __restrict__ dev, const int e, const int* __restrict__ e_off, const unsigned* __restrict__ e_ij,
                                                  const cplx* __restrict__ e_val, const double* __restrict__ Y, long long y_plane, int NP, void* __restrict__ expect,
                                                  long long base, int n_out, int complex_out, double* red) {

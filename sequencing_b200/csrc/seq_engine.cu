@@ -814,16 +814,23 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
   LargeHermBufs hb;
   memset(&hb, 0, sizeof(hb));
   int h_tiles = 0, NPh = 0;
+  size_t h_smem = 0;
   unsigned long long* dchk = nullptr;
   if (herm_try) {
     const int nt = (N + LH_T - 1) / LH_T;
     NPh = nt * LH_T;
     h_tiles = nt * (nt + 1) / 2;
-    const size_t packed = (size_t)h_tiles * 2 * LH_TE, full = 2 * (size_t)NPh * NPh;
-    rc = reserve(e, e->herm, (2 * full + 9 * packed + 8) * sizeof(double) + (size_t)h_tiles * sizeof(unsigned) + 256);
+    // zero guard rows around the full matrices: gathers are not bounds checked (their coefficients are zero outside)
+    int guard = 0;
+    for (int t = 0; t < la.nGo; t++) guard = std::max(guard, abs(la.go_off[t]));
+    for (int t = 0; t < la.nLg; t++) guard = std::max(guard, std::max(abs(la.lg_oa[t]), abs(la.lg_ob[t])));
+    guard += 2;
+    const size_t packed = (size_t)h_tiles * LH_TE, full = ((size_t)NPh + 2 * (size_t)guard) * NPh;      // complex elements
+    rc = reserve(e, e->herm, (2 * full + 9 * packed + 8) * sizeof(cplx) + (size_t)h_tiles * sizeof(unsigned) + 256);
     if (rc) return rc;
-    double* hbase = (double*)e->herm.ptr;
-    for (int q = 0; q < 2; q++) { hb.Yfull[q] = hbase; hbase += full; }
+    cplx* hbase = (cplx*)e->herm.ptr;
+    CUDA_TRY(e, cudaMemsetAsync(hbase, 0, 2 * full * sizeof(cplx), st));
+    for (int q = 0; q < 2; q++) { hb.Yfull[q] = hbase + (size_t)guard * NPh; hbase += full; }
     for (int q = 0; q < 2; q++) { hb.ybuf[q] = hbase; hbase += packed; }
     for (int q = 0; q < 7; q++) { hb.kbuf[q] = hbase; hbase += packed; }
     dchk = (unsigned long long*)hbase; hbase += 8;
@@ -834,10 +841,12 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
       for (int tj = ti; tj < nt; tj++) ht.push_back((unsigned)ti | ((unsigned)tj << 16));
     CUDA_TRY(e, cudaMemcpyAsync(dtiles, ht.data(), (size_t)h_tiles * sizeof(unsigned), cudaMemcpyHostToDevice, st));
     CUDA_TRY(e, cudaStreamSynchronize(st));
-    hb.tiles = dtiles; hb.yplane = (long long)NPh * NPh; hb.NPh = NPh; hb.N = N;
-    hb.g0 = dg0; hb.gk = dgk; hb.n_g = n_g; hb.nD = dfill.nD;
+    hb.tiles = dtiles; hb.NPh = NPh; hb.N = N;
+    hb.g0 = dg0; hb.gk = dgk; hb.lam = dlam; hb.gdiag = dgdiag; hb.n_g = n_g; hb.nD = dfill.nD; hb.nT = dfill.nT;
+    h_smem = lh_stage_smem(dfill.nD, dfill.nT);
+    if (cudaFuncSetAttribute(lh_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h_smem) != cudaSuccess)
+      return fail(e, SEQ_ERR_CUDA, "large path: %zu bytes of shared memory per tile refused", h_smem);
   }
-
   bool any_full = false;
   for (int b = 0; b < B; b++) {
     bool herm = false;
@@ -858,10 +867,6 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
     CUDA_TRY(e, cudaMemcpyAsync(ycur, Yfull + row0 * NP, mplane * sizeof(double), cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(e, cudaMemcpyAsync(ycur + mplane, Yfull + yplane + row0 * NP, mplane * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
-    // where the committed state is found as a full planar matrix (outputs, final state)
-    const double* Yc = herm ? hb.Yfull[0] : Yfull;
-    const int NPc = herm ? NPh : NP;
-    const long long rows_c = herm ? (long long)NPh : rows_full, yplane_c = herm ? hb.yplane : yplane;
 
     auto rhs = [&](double t, double* kout) -> int {
       if (n_g > 0) { large_coeff_kernel<<<1, 64, 0, st>>>(p, b, t, cval); e->launches++; }
@@ -925,30 +930,30 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
       for (int j = 0; j < 7; j++) bf.kbuf[j] = kbuf[j];
       bf.Yfull = Yfull; bf.mplane = mplane; bf.yplane = yplane;
       LargeDiagArgs a = la;
-      a.N = N; a.NP = NPc; a.m = m; a.Mrows = Mrows; a.row0 = row0; a.y_plane = yplane_c; a.k_plane = mplane;
-      a.Y = Yc; a.K = nullptr; a.gt = dgt; a.lam = dlam; a.gdiag = dgdiag; a.cval = nullptr;
+      a.N = N; a.NP = NP; a.m = m; a.Mrows = Mrows; a.row0 = row0; a.y_plane = yplane; a.k_plane = mplane;
+      a.Y = Yfull; a.K = nullptr; a.gt = dgt; a.lam = dlam; a.gdiag = dgdiag; a.cval = nullptr;
       const int nDN = dfill.nD * N;
       const int g_elem = grid_for(mplane, sms), g_comb = grid_for(lsz, sms);
       auto outputs = [&]() {
         if (n_e > 0) {
-          ldev_expect_kernel<<<n_e, 256, 0, st>>>(ddev, e_off, e_ij, e_val, Yc, yplane_c, NPc, p.expect, (long long)b * n_e * d->n_out, d->n_out,
+          ldev_expect_kernel<<<n_e, 256, 0, st>>>(ddev, e_off, e_ij, e_val, Yfull, yplane, NP, p.expect, (long long)b * n_e * d->n_out, d->n_out,
                                                   (p.flags & SEQ_FLAG_EXPECT_COMPLEX) ? 1 : 0);
           e->launches++;
         }
         if (p.flags & SEQ_FLAG_STORE_STATES) {
-          ldev_store_kernel<<<grid_for((long long)N * N, sms), 256, 0, st>>>(ddev, Yc, p.states + (size_t)b * d->n_out * N * N, N, NPc, rows_c);
+          ldev_store_kernel<<<grid_for((long long)N * N, sms), 256, 0, st>>>(ddev, Yfull, p.states + (size_t)b * d->n_out * N * N, N, NP, rows_full);
           e->launches++;
         }
       };
       ldev_ctl_kernel<<<1, 32, 0, st>>>(p, b, ddev, 1);
       e->launches++;
       // (Hermitian tiles: the expectation values of a committed state ride in the next attempt's first kernel)
-      LargeExpectArgs exa;
-      exa.e_off = e_off; exa.e_ij = e_ij; exa.e_val = e_val; exa.Y = Yc; exa.y_plane = yplane_c; exa.NP = NPc;
+      LargeHermExpect exa;
+      exa.e_off = e_off; exa.e_ij = e_ij; exa.e_val = e_val;
       exa.expect = p.expect; exa.base = (long long)b * n_e * d->n_out; exa.n_out = d->n_out; exa.complex_out = (p.flags & SEQ_FLAG_EXPECT_COMPLEX) ? 1 : 0;
       auto store_h = [&]() {
         if (p.flags & SEQ_FLAG_STORE_STATES) {
-          ldev_store_kernel<<<grid_for((long long)N * N, sms), 256, 0, st>>>(ddev, Yc, p.states + (size_t)b * d->n_out * N * N, N, NPc, rows_c);
+          lh_unpack_kernel<<<grid_for((long long)N * N, sms), 256, 0, st>>>(ddev, hb.Yfull[0], p.states + (size_t)b * d->n_out * N * N, (long long)N * N, N, NPh);
           e->launches++;
         }
       };
@@ -962,7 +967,7 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
             lh_first_kernel<<<h_tiles + n_e, 256, 0, st>>>(ddev, hb, h_tiles, exa);
             e->launches++;
             for (int s_ = 0; s_ < 7; s_++) {
-              lh_stage_kernel<<<h_tiles, 256, 0, st>>>(ddev, hb, s_, a, p.atol, p.rtol);
+              lh_stage_kernel<<<h_tiles, 256, h_smem, st>>>(ddev, hb, s_, a, p.atol, p.rtol);
               e->launches++;
             }
             ldev_ctl_kernel<<<1, 32, 0, st>>>(p, b, ddev, 0);
@@ -986,8 +991,7 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
         CUDA_TRY(e, cudaStreamSynchronize(st));
         if (!hdev->active) {
           if (herm && n_e > 0) {      // the last committed state's expectation values, had the chunk ended with its step
-            ldev_expect_kernel<<<n_e, 256, 0, st>>>(ddev, e_off, e_ij, e_val, Yc, yplane_c, NPc, p.expect, (long long)b * n_e * d->n_out, d->n_out,
-                                                    (p.flags & SEQ_FLAG_EXPECT_COMPLEX) ? 1 : 0);
+            lh_expect_kernel<<<n_e, 256, 0, st>>>(ddev, hb, exa);
             e->launches++;
           }
           break;
@@ -1058,7 +1062,8 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
       }
     }
     if (ctl.status == SEQ_STATUS_OK) {
-      large_unpack_kernel<<<grid_for((long long)N * N, sms), 256, 0, st>>>(Yc, p.final_state + (size_t)b * N * N, N, NPc, rows_c);
+      if (herm) lh_unpack_kernel<<<grid_for((long long)N * N, sms), 256, 0, st>>>(nullptr, hb.Yfull[0], p.final_state + (size_t)b * N * N, 0, N, NPh);
+      else large_unpack_kernel<<<grid_for((long long)N * N, sms), 256, 0, st>>>(Yfull, p.final_state + (size_t)b * N * N, N, NP, rows_full);
       e->launches++;
     } else {
       CUDA_TRY(e, cudaMemsetAsync(p.final_state + (size_t)b * N * N, 0, sizeof(cplx) * N * N, st));
