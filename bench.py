@@ -604,6 +604,9 @@ def ours(args):
         kname = ("large_diag_rhs_kernel" if structured_large else "zgemm_dmma_kernel") if out_h.method == "large" else f"solve_{out_h.method}_kernel"
         if out_h.variant.startswith("diagblk"):
             kname = "solve_diagblk_kernel"
+        herm_large = structured_large and "Hermitian tiles" in out_h.variant
+        if herm_large:
+            kname = "lh_stage_kernel"
         peak_scale = world if rows_mode else 1     # rows mode: the algorithmic flops of the ONE system are spread over all GPUs
         if out_h.method == "small":
             # N <= 6: below one DMMA tile -> the HBM roofline, FP64-FMA ceiling noted
@@ -637,6 +640,18 @@ def ours(args):
                 roof["hbm"] = {"bound": "hbm", "achieved": gb, "peak": peak_h * peak_scale, "unit": "GB/s", "frac": gb / (peak_h * peak_scale),
                                "bytes_per_rhs": 32.0 * s["N"] ** 2, "peak_source": src_h,
                                "note": "whole stepper time (RHS + stage combinations + error norm + outputs) against the RHS kernel's compulsory bytes"}
+                if herm_large:
+                    # what the Hermitian-tile stepper moves by construction (kernel_large_herm.cuh): h = one packed half vector;
+                    # a 4(3) step streams 37 h (stage input 4 h, fused stages 7 + 8 + 10 + 8 h), a 5(4) step 59 h
+                    nt = (s["N"] + 31) // 32
+                    h_b = 16.0 * 1024 * nt * (nt + 1) / 2
+                    rhs_all, att_all = float(np.sum(stats[:, 2])), float(np.sum(stats[:, 0]) + np.sum(stats[:, 1]))
+                    f5 = min(1.0, max(0.0, (rhs_all / max(att_all, 1.0) - 4.0) / 2.0))
+                    per_rhs = h_b * ((1.0 - f5) * 37.0 / 4.0 + f5 * 59.0 / 6.0)
+                    roof["hbm"].update({"executed_bytes_per_rhs_model": per_rhs, "executed_GBps_model": per_rhs * rhs_all / (k_ms * 1e-3) / 1e9,
+                                        "executed_frac_model": per_rhs * rhs_all / (k_ms * 1e-3) / 1e9 / (peak_h * peak_scale),
+                                        "model": "packed half vectors of 16 B x 1024 x tiles(ti<=tj): stage input 4 h, fused stage kernels 7/8/10/8 h (4(3) pair) or "
+                                                 "7/8/9/10/12/9 h (5(4) pair); ncu dram__bytes of the four stage kernels of a 4(3) step agrees (profiles/r02_c5_herm_stage_ncu_summary.json)"})
             if sw:
                 # The kernel that ran is a structure-exploiting FP64-FMA kernel: `frac` is what it EXECUTES against the
                 # peak of the pipe it uses; the dense-equivalent figure (SURVEY.md 8(d) algorithmic flops against the DMMA
@@ -669,6 +684,11 @@ def ours(args):
                                      "= algorithmic dense flops 8 N^3 (1 + 2 n_c) per RHS (SURVEY.md 8(d)) / time / DMMA peak: how much faster "
                                      "than a dense tensor-core evaluation at 100 % of its peak - not a utilisation.  `dense_kernel` is the "
                                      "tensor-core kernel timed on the same inputs.  ncu pipe utilisation of this kernel: profiles/"})
+                if structured_large:
+                    # the large path's structured stepper is HBM-bound (a few FP64 multiply-adds per 16-byte element): the top-level
+                    # roofline is the HBM one - SURVEY.md 8(d)'s 32 N^2 bytes per RHS against the WHOLE stepper's time; the FP64 figures stay as extras
+                    roof.update({"bound": "hbm", "achieved": roof["hbm"]["achieved"], "peak": roof["hbm"]["peak"], "unit": "GB/s", "frac": roof["hbm"]["frac"],
+                                 "peak_source": roof["hbm"]["peak_source"]})
                 if world == 1 and not args.no_dense and not rows_mode:
                     # the dense tensor-core formulation on the same workload (a quarter of the batch), for the DMMA roofline
                     import copy as _copy

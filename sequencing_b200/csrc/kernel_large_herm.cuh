@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(256) lh_first_kernel(const LargeDev* __restric
 }
 
 // stage st of the attempt on one upper tile: right-hand side, then the next stage input (or, last stage, the error sum)
-__global__ void __launch_bounds__(256, 3) lh_stage_kernel(LargeDev* __restrict__ dev, const __grid_constant__ LargeHermBufs bf, int st,
+template <int MINB, int UNR>
+__global__ void __launch_bounds__(256, MINB) lh_stage_kernel(LargeDev* __restrict__ dev, const __grid_constant__ LargeHermBufs bf, int st,
                                                           const __grid_constant__ LargeDiagArgs a, double atol, double rtol) {
   extern __shared__ __align__(16) unsigned char lh_smem[];
   if (!dev->active || st < dev->st0 || st >= dev->S) return;
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(256, 3) lh_stage_kernel(LargeDev* __restrict__
 #pragma unroll
     for (int q = 0; q < 4; q++) kv[q] = cmul(wt[q], yv[q]);
   }
+#pragma unroll UNR
   for (int t = 0; t < a.nGo; t++) {
     const int o = a.go_off[t];
     const cplx* gv = gts + a.go_tab[t] * 64;

@@ -815,6 +815,8 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
   memset(&hb, 0, sizeof(hb));
   int h_tiles = 0, NPh = 0;
   size_t h_smem = 0;
+  int h_variant = 0;
+  void (*h_stage)(LargeDev*, const LargeHermBufs, int, const LargeDiagArgs, double, double) = nullptr;
   unsigned long long* dchk = nullptr;
   if (herm_try) {
     const int nt = (N + LH_T - 1) / LH_T;
@@ -844,7 +846,12 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
     hb.tiles = dtiles; hb.NPh = NPh; hb.N = N;
     hb.g0 = dg0; hb.gk = dgk; hb.lam = dlam; hb.gdiag = dgdiag; hb.n_g = n_g; hb.nD = dfill.nD; hb.nT = dfill.nT;
     h_smem = lh_stage_smem(dfill.nD, dfill.nT);
-    if (cudaFuncSetAttribute(lh_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h_smem) != cudaSuccess)
+    {
+      const char* v = getenv("SEQ_LH_VARIANT");      // experiments: resident CTAs per SM / unrolling of the gather loop
+      h_variant = v ? atoi(v) : 0;
+      h_stage = h_variant == 1 ? lh_stage_kernel<3, 1> : h_variant == 2 ? lh_stage_kernel<2, 2> : lh_stage_kernel<4, 1>;      // (measured at C5: 0.480 / 0.501 / 0.493 ms per 5(4) step for 4 / 3 / 2 x unrolled)
+    }
+    if (cudaFuncSetAttribute(h_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h_smem) != cudaSuccess)
       return fail(e, SEQ_ERR_CUDA, "large path: %zu bytes of shared memory per tile refused", h_smem);
   }
   bool any_full = false;
@@ -967,7 +974,7 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
             lh_first_kernel<<<h_tiles + n_e, 256, 0, st>>>(ddev, hb, h_tiles, exa);
             e->launches++;
             for (int s_ = 0; s_ < 7; s_++) {
-              lh_stage_kernel<<<h_tiles, 256, h_smem, st>>>(ddev, hb, s_, a, p.atol, p.rtol);
+              h_stage<<<h_tiles, 256, h_smem, st>>>(ddev, hb, s_, a, p.atol, p.rtol);
               e->launches++;
             }
             ldev_ctl_kernel<<<1, 32, 0, st>>>(p, b, ddev, 0);
