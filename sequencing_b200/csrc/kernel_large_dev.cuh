@@ -34,9 +34,31 @@ struct LargeDevBufs {
   long long mplane, yplane;      // doubles per plane of a row-block vector / of the full stage buffer
 };
 
+// Programmatic dependent launch (the attempt's kernels are launched with programmaticStreamSerialization): a kernel's CTAs
+// become resident while the previous kernel drains; nothing written by an earlier kernel is read before this wait.  The
+// dependents are released right after it, so a kernel two launches back has always completed.  (No-ops without the attribute.)
+__device__ __forceinline__ void lh_grid_dependency_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// launch with programmatic stream serialization (see lh_grid_dependency_wait)
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(bool pdl, void (*k)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k, KArgs(args)...);
+}
+
 // One warp.  `first`: nothing has been evaluated yet (initial call).
 __global__ void ldev_ctl_kernel(const __grid_constant__ SolveParams p, int b, LargeDev* __restrict__ dev, int first) {
   const int lane = threadIdx.x;
+  lh_grid_dependency_wait();
   StepCtl ctl = dev->ctl;
   double c_htry = dev->htry, c_target = dev->target;
   int c_o = dev->o, c_nst = dev->nst;

@@ -43,6 +43,7 @@ struct LargeHermBufs {
   const cplx *g0, *gk;      // G diagonals: static part [nD][N] and time-dependent terms [n_g][nD][N] (diag_fill_kernel's tables)
   const cplx *lam, *gdiag;  // collapse diagonals [nT][N], static main diagonal of G0 [N]
   int n_g, nD, nT;
+  int dbg;                  // timing experiments (SEQ_LH_DBG; results are wrong): 1 no mirror write, 2 no tile write, 4 no k store
 };
 
 static inline size_t lh_stage_smem(int nD, int nT) { return ((size_t)LH_T * (LH_T + 1) + (size_t)(nD + nT + 1) * 2 * LH_T) * sizeof(cplx) + 40 * sizeof(double); }
@@ -144,6 +145,7 @@ __global__ void lh_unpack_kernel(const LargeDev* __restrict__ dev, const cplx* _
 __global__ void __launch_bounds__(256) lh_first_kernel(const LargeDev* __restrict__ dev, const __grid_constant__ LargeHermBufs bf, int n_tiles,
                                                        const __grid_constant__ LargeHermExpect ex) {
   __shared__ cplx sm[LH_T * (LH_T + 1)];
+  lh_grid_dependency_wait();
   if ((int)blockIdx.x >= n_tiles) {
     lh_expect_body(dev, (int)blockIdx.x - n_tiles, ex, bf.Yfull[0], bf.NPh, (double*)sm);
     return;
@@ -172,6 +174,7 @@ template <int MINB, int UNR>
 __global__ void __launch_bounds__(256, MINB) lh_stage_kernel(LargeDev* __restrict__ dev, const __grid_constant__ LargeHermBufs bf, int st,
                                                           const __grid_constant__ LargeDiagArgs a, double atol, double rtol) {
   extern __shared__ __align__(16) unsigned char lh_smem[];
+  lh_grid_dependency_wait();
   if (!dev->active || st < dev->st0 || st >= dev->S) return;
   cplx* sm = (cplx*)lh_smem;                               // transpose buffer 32 x 33
   cplx* gts = sm + LH_T * (LH_T + 1);                      // [nD][rows 32 | columns 32]: G(t) diagonals of this stage time
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(256, MINB) lh_stage_kernel(LargeDev* __restric
     const int d = q / (2 * LH_T), r = q % LH_T;
     const int pos = (((q / LH_T) & 1) ? tj : ti) * LH_T + r;
     cplx g = cmake(0, 0);
-    if (pos < N) {
+    if (pos < N && !(bf.dbg & 32)) {
       if (d < bf.nD) {      // g0 + sum_m c_m(t) gk_m
         g = bf.g0[(long long)d * N + pos];
         for (int m = 0; m < bf.n_g; m++) {
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(256, MINB) lh_stage_kernel(LargeDev* __restric
     for (int q = 0; q < 4; q++) kv[q] = cmul(wt[q], yv[q]);
   }
 #pragma unroll UNR
-  for (int t = 0; t < a.nGo; t++) {
+  for (int t = 0; t < ((bf.dbg & 64) ? 0 : a.nGo); t++) {
     const int o = a.go_off[t];
     const cplx* gv = gts + a.go_tab[t] * 64;
     const cplx vj = gv[cj];
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(256, MINB) lh_stage_kernel(LargeDev* __restric
       cfma(kv[q], cjv, yb);
     }
   }
-  for (int t = 0; t < a.nLg; t++) {
+  for (int t = 0; t < ((bf.dbg & 64) ? 0 : a.nLg); t++) {
     const int ri = a.lg_r[t];
     const double rr = ri < 0 ? 1.0 : cval[ri];
     const cplx lb = lams[a.lg_b[t] * 64 + cj];
@@ -300,6 +303,7 @@ __global__ void __launch_bounds__(256, MINB) lh_stage_kernel(LargeDev* __restric
   }
   {
     cplx* kd = bf.kbuf[dev->kmap[st]] + tbase;
+    if (!(bf.dbg & 4))
 #pragma unroll
     for (int q = 0; q < 4; q++) kd[(w + 8 * q) * LH_T + lane] = kv[q];
   }
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(256, MINB) lh_stage_kernel(LargeDev* __restric
     cplx acc[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) acc[q] = cmake(0, 0);
-    for (int jj = 0; jj < st; jj++) {
+    for (int jj = 0; jj < ((bf.dbg & 128) ? 0 : st); jj++) {
       const double aj = RK_A[pair][st + 1][jj];
       if (aj == 0.0) continue;
       const cplx* kj = bf.kbuf[dev->kmap[jj]] + tbase;
@@ -333,6 +337,9 @@ __global__ void __launch_bounds__(256, MINB) lh_stage_kernel(LargeDev* __restric
 #pragma unroll
       for (int q = 0; q < 4; q++) yn[(w + 8 * q) * LH_T + lane] = v[q];
     }
+    if (bf.dbg & 3) {
+      if (!(bf.dbg & 2)) lh_write_tile(bf.Yfull[(st + 1) & 1], NP, ti, ti, v, sm);      // own tile only (written where the diagonal tile would go: timing only)
+    } else
     lh_write_tile(bf.Yfull[(st + 1) & 1], NP, ti, tj, v, sm);
   } else {
     // error estimate h sum_jj e_jj k_jj, weighted by atol + rtol max(|y|, |y_new|); the stage input of the last stage

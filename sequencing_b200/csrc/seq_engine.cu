@@ -30,6 +30,7 @@
 #include "kernel_large_diag.cuh"
 #include "kernel_large_dev.cuh"
 #include "kernel_large_herm.cuh"
+#include "kernel_large_hermq.cuh"
 
 using namespace seq;
 
@@ -814,20 +815,53 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
   LargeHermBufs hb;
   memset(&hb, 0, sizeof(hb));
   int h_tiles = 0, NPh = 0;
-  size_t h_smem = 0;
-  int h_variant = 0;
+  size_t h_smem = 0, hq_smem_t = 0;      // dynamic shared memory of the stage kernel / of the q-local pack and stage-input kernels
   void (*h_stage)(LargeDev*, const LargeHermBufs, int, const LargeDiagArgs, double, double) = nullptr;
+  // q-local variant (kernel_large_hermq.cuh): the outermost tensor factor inside a thread
+  LargeQLocal lq;
+  bool use_q = false;
+  const bool h_pdl = !getenv("SEQ_LH_NOPDL");
+  void (*hq_stage)(LargeDev*, const LargeHermBufs, int, const LargeDiagArgs, const LargeQLocal, double, double) = nullptr;
+  void (*hq_first)(const LargeDev*, const LargeHermBufs, int, int, const LargeHermExpect) = nullptr;
+  void (*hq_pack)(const cplx*, const LargeHermBufs, int, unsigned long long*) = nullptr;
   unsigned long long* dchk = nullptr;
   if (herm_try) {
+    use_q = !getenv("SEQ_LH_NOQ") && lhq_plan(N, la, &lq);
     const int nt = (N + LH_T - 1) / LH_T;
     NPh = nt * LH_T;
-    h_tiles = nt * (nt + 1) / 2;
+    std::vector<unsigned> ht;
+    size_t packed;      // complex elements of a packed vector
+    if (use_q) {
+      const int nxt = (lq.L + LQ_T - 1) / LQ_T;
+      for (int xi = 0; xi < nxt; xi++)
+        for (int xj = xi; xj < nxt; xj++) ht.push_back((unsigned)xi | ((unsigned)xj << 16));
+      packed = ht.size() * (size_t)lq.Q * lq.Q * LQ_TE;
+      if (lq.Q == 2) { hq_stage = lhq_stage_kernel<2>; hq_first = lhq_first_kernel<2>; hq_pack = lhq_pack_kernel<2>; h_smem = lhq_stage_smem<2>(dfill.nD, dfill.nT); }
+      else if (lq.Q == 3) { hq_stage = lhq_stage_kernel<3>; hq_first = lhq_first_kernel<3>; hq_pack = lhq_pack_kernel<3>; h_smem = lhq_stage_smem<3>(dfill.nD, dfill.nT); }
+      else { hq_stage = lhq_stage_kernel<4>; hq_first = lhq_first_kernel<4>; hq_pack = lhq_pack_kernel<4>; h_smem = lhq_stage_smem<4>(dfill.nD, dfill.nT); }
+      hq_smem_t = (size_t)lq.Q * lq.Q * LQ_T * (LQ_T + 1) * sizeof(cplx);
+      if (cudaFuncSetAttribute(hq_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h_smem) != cudaSuccess ||
+          cudaFuncSetAttribute(hq_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hq_smem_t) != cudaSuccess ||
+          cudaFuncSetAttribute(hq_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hq_smem_t) != cudaSuccess)
+        return fail(e, SEQ_ERR_CUDA, "large path: %zu bytes of shared memory per tile refused", h_smem);
+    } else {
+      for (int ti = 0; ti < nt; ti++)
+        for (int tj = ti; tj < nt; tj++) ht.push_back((unsigned)ti | ((unsigned)tj << 16));
+      packed = ht.size() * (size_t)LH_TE;
+      h_smem = lh_stage_smem(dfill.nD, dfill.nT);
+      const char* v = getenv("SEQ_LH_VARIANT");      // experiments: resident CTAs per SM / unrolling of the gather loop
+      const int h_variant = v ? atoi(v) : 0;
+      h_stage = h_variant == 1 ? lh_stage_kernel<3, 1> : h_variant == 2 ? lh_stage_kernel<2, 2> : lh_stage_kernel<4, 1>;      // (measured at C5: 0.480 / 0.501 / 0.493 ms per 5(4) step for 4 / 3 / 2 x unrolled)
+      if (cudaFuncSetAttribute(h_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h_smem) != cudaSuccess)
+        return fail(e, SEQ_ERR_CUDA, "large path: %zu bytes of shared memory per tile refused", h_smem);
+    }
+    h_tiles = (int)ht.size();
     // zero guard rows around the full matrices: gathers are not bounds checked (their coefficients are zero outside)
     int guard = 0;
     for (int t = 0; t < la.nGo; t++) guard = std::max(guard, abs(la.go_off[t]));
     for (int t = 0; t < la.nLg; t++) guard = std::max(guard, std::max(abs(la.lg_oa[t]), abs(la.lg_ob[t])));
-    guard += 2;
-    const size_t packed = (size_t)h_tiles * LH_TE, full = ((size_t)NPh + 2 * (size_t)guard) * NPh;      // complex elements
+    guard += 2 + LQ_T;      // (+ the positions x >= L of the last x tile, which the q-local kernels read but never write)
+    const size_t full = ((size_t)NPh + 2 * (size_t)guard) * NPh;      // complex elements
     rc = reserve(e, e->herm, (2 * full + 9 * packed + 8) * sizeof(cplx) + (size_t)h_tiles * sizeof(unsigned) + 256);
     if (rc) return rc;
     cplx* hbase = (cplx*)e->herm.ptr;
@@ -837,29 +871,23 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
     for (int q = 0; q < 7; q++) { hb.kbuf[q] = hbase; hbase += packed; }
     dchk = (unsigned long long*)hbase; hbase += 8;
     unsigned* dtiles = (unsigned*)hbase;
-    std::vector<unsigned> ht;
-    ht.reserve(h_tiles);
-    for (int ti = 0; ti < nt; ti++)
-      for (int tj = ti; tj < nt; tj++) ht.push_back((unsigned)ti | ((unsigned)tj << 16));
     CUDA_TRY(e, cudaMemcpyAsync(dtiles, ht.data(), (size_t)h_tiles * sizeof(unsigned), cudaMemcpyHostToDevice, st));
     CUDA_TRY(e, cudaStreamSynchronize(st));
     hb.tiles = dtiles; hb.NPh = NPh; hb.N = N;
     hb.g0 = dg0; hb.gk = dgk; hb.lam = dlam; hb.gdiag = dgdiag; hb.n_g = n_g; hb.nD = dfill.nD; hb.nT = dfill.nT;
-    h_smem = lh_stage_smem(dfill.nD, dfill.nT);
-    {
-      const char* v = getenv("SEQ_LH_VARIANT");      // experiments: resident CTAs per SM / unrolling of the gather loop
-      h_variant = v ? atoi(v) : 0;
-      h_stage = h_variant == 1 ? lh_stage_kernel<3, 1> : h_variant == 2 ? lh_stage_kernel<2, 2> : lh_stage_kernel<4, 1>;      // (measured at C5: 0.480 / 0.501 / 0.493 ms per 5(4) step for 4 / 3 / 2 x unrolled)
+    if (const char* dv = getenv("SEQ_LH_DBG")) {      // timing experiments only (wrong results)
+      hb.dbg = atoi(dv);
+      if (hb.dbg & 8) { for (int t = 0; t < la.nGo; t++) la.go_off[t] = 0; for (int t = 0; t < la.nLg; t++) la.lg_oa[t] = la.lg_ob[t] = 0; }
+      if (hb.dbg & 16) { for (int t = 0; t < la.nGo; t++) la.go_off[t] = (la.go_off[t] > 0) - (la.go_off[t] < 0); for (int t = 0; t < la.nLg; t++) la.lg_oa[t] = la.lg_ob[t] = 1; }
     }
-    if (cudaFuncSetAttribute(h_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h_smem) != cudaSuccess)
-      return fail(e, SEQ_ERR_CUDA, "large path: %zu bytes of shared memory per tile refused", h_smem);
   }
   bool any_full = false;
   for (int b = 0; b < B; b++) {
     bool herm = false;
     if (herm_try) {      // rho0 -> packed upper tiles + full matrix 0, and is it Hermitian?
       CUDA_TRY(e, cudaMemsetAsync(dchk, 0, 2 * sizeof(unsigned long long), st));
-      lh_pack_kernel<<<h_tiles, 256, 0, st>>>(p.state0 + (size_t)b * N * N, hb, dchk);
+      if (use_q) hq_pack<<<h_tiles, 256, hq_smem_t, st>>>(p.state0 + (size_t)b * N * N, hb, lq.L, dchk);
+      else lh_pack_kernel<<<h_tiles, 256, 0, st>>>(p.state0 + (size_t)b * N * N, hb, dchk);
       e->launches++;
       double chk[2];
       CUDA_TRY(e, cudaMemcpyAsync(chk, dchk, sizeof(chk), cudaMemcpyDeviceToHost, st));
@@ -971,13 +999,15 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
       while (true) {
         for (int q = 0; q < chunk; q++) {
           if (herm) {      // stage input of the first stage, then one fused kernel per stage (RHS + next stage input / error sum)
-            lh_first_kernel<<<h_tiles + n_e, 256, 0, st>>>(ddev, hb, h_tiles, exa);
+            if (use_q) launch_pdl(h_pdl, hq_first, h_tiles + n_e, 256, hq_smem_t, st, ddev, hb, lq.L, h_tiles, exa);
+            else launch_pdl(h_pdl, lh_first_kernel, h_tiles + n_e, 256, 0, st, ddev, hb, h_tiles, exa);
             e->launches++;
             for (int s_ = 0; s_ < 7; s_++) {
-              h_stage<<<h_tiles, 256, h_smem, st>>>(ddev, hb, s_, a, p.atol, p.rtol);
+              if (use_q) launch_pdl(h_pdl, hq_stage, h_tiles, 256, h_smem, st, ddev, hb, s_, a, lq, p.atol, p.rtol);
+              else launch_pdl(h_pdl, h_stage, h_tiles, 256, h_smem, st, ddev, hb, s_, a, p.atol, p.rtol);
               e->launches++;
             }
-            ldev_ctl_kernel<<<1, 32, 0, st>>>(p, b, ddev, 0);
+            launch_pdl(h_pdl, ldev_ctl_kernel, 1, 32, 0, st, p, b, ddev, 0);
             e->launches++;
             store_h();
             continue;
@@ -1081,7 +1111,12 @@ static int solve_large(seq_engine* e, const seq_solve_desc* d, const SolveParams
     CUDA_TRY(e, cudaMemcpyAsync(p.stats + 4 * b, h_stats, sizeof(h_stats), cudaMemcpyHostToDevice, st));
     CUDA_TRY(e, cudaStreamSynchronize(st));   // h_status / h_stats live on this stack frame
   }
-  if (herm_try && !any_full) e->variant = "large/diagonals, Hermitian tiles (device-resident step control, stage combination and error estimate fused into the RHS kernel)";
+  if (herm_try && !any_full) {
+    char vb[256];
+    if (use_q) snprintf(vb, sizeof(vb), "large/diagonals, Hermitian tiles, outer factor of dimension %d inside a thread (device-resident step control, stage combination and error estimate fused into the RHS kernel)", lq.Q);
+    else snprintf(vb, sizeof(vb), "large/diagonals, Hermitian tiles (device-resident step control, stage combination and error estimate fused into the RHS kernel)");
+    e->variant = vb;
+  }
   CUDA_TRY(e, cudaGetLastError());
   return SEQ_OK;
 }

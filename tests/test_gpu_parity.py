@@ -550,6 +550,66 @@ def test_large_path_hermitian_tiles_edges_and_non_hermitian_fallback(gpu_engine)
     assert np.max(np.abs(onh.states - oz.states)) < 1e-12 and np.max(np.abs(onh.expect - oz.expect)) < 1e-12
 
 
+def _banded_problem(N, L, seed, n_t=5, B=2, max_step=1.0, mult=2):
+    """Diagonal-structured random operators whose offsets contain multiples of L = N / Q next to small ones - the offset
+    pattern of a tensor product with a small first factor, at RANDOM values (nothing vanishes at the block edges, so a
+    kernel that assumed Kronecker structure instead of reading the offsets would get this wrong)."""
+    bp = random_problem(N=N, B=B, n_t=n_t, n_ch=2, n_c=3, n_ctd=1, n_e=2, seed=seed, hscale=0.6, store_states=True)
+    i, j = np.indices((N, N))
+
+    def band(m, offs):
+        keep = np.zeros((N, N), bool)
+        for o in offs:
+            keep |= (j - i) == o
+        return m * keep * np.sqrt(N) * 0.5
+
+    bp.H0 = band(bp.H0, (0, 1, -1, 3, -3, L, -L))
+    bp.Hk = np.stack([band(bp.Hk[0], (L, -L, mult * L, -mult * L)), band(bp.Hk[1], (0, 1, -1))])
+    bp.Lc = np.stack([band(bp.Lc[0], (L,)), band(bp.Lc[1], (1,)), band(bp.Lc[2], (0, -L))])
+    bp.Ltd = np.stack([band(bp.Ltd[0], (L + 1,))])
+    bp.max_step = max_step
+    bp.method = _lib.METHOD_LARGE
+    return bp
+
+
+def test_large_path_outer_factor_inside_a_thread(gpu_engine):
+    """kernel_large_hermq.cuh: offsets that are multiples of L = N / Q (Q = 2, 3, 4) are evaluated on the thread's own
+    Q x Q elements.  Against the full-matrix stepper and the 32 x 32 Hermitian tiles, on random banded operators with
+    x tiles that end inside a tile (L not a multiple of 16) and on a small cousin of C5 (3 x 5 x 5)."""
+    import os
+    from sequencing_b200 import workloads
+
+    def solve_with(mk, env):
+        for k in env:
+            os.environ[k] = "1"
+        try:
+            return gpu_engine.solve(mk())
+        finally:
+            for k in env:
+                del os.environ[k]
+    # (N, L, max_step, second multiple): Q = 2 | Q = 3 with offsets +-2L | Q = 2 with a partial last x tile (the largest
+    # divisor offset, 66, wins over 33) | Q = 4 with offsets +-3L
+    cases = [(lambda N=N, L=L, ms=ms, mu=mu: _banded_problem(N, L, seed=N + L, max_step=ms, mult=mu))
+             for N, L, ms, mu in ((96, 48, 1.0, 2), (150, 50, 0.0, 2), (132, 33, 1.0, 2), (100, 25, 0.0, 3))]
+
+    def cousin():
+        bp = workloads.c5_transmon_two_cavities(cavity_levels=5, n_ops=2, sigma=3)
+        bp.method = _lib.METHOD_LARGE
+        return bp
+    cases.append(cousin)
+    for mk in cases:
+        oq = solve_with(mk, ())
+        of = solve_with(mk, ("SEQ_LARGE_FULL",))
+        ot = solve_with(mk, ("SEQ_LH_NOQ",))
+        N = oq.final_state.shape[-1]
+        assert "outer factor of dimension" in oq.variant and np.all(oq.status == 0), oq.variant
+        assert "Hermitian tiles" in ot.variant and "outer factor" not in ot.variant and "Hermitian" not in of.variant
+        for k in ("expect", "final_state") + (("states",) if oq.states is not None and of.states is not None else ()):
+            assert np.max(np.abs(getattr(oq, k) - getattr(of, k))) < 1e-12, (N, k)
+            assert np.max(np.abs(getattr(oq, k) - getattr(ot, k))) < 1e-12, (N, k)
+        np.testing.assert_array_equal(oq.stats[:, :3], of.stats[:, :3])
+
+
 def test_diag_kernel_two_cta_cluster_variant(gpu_engine, plain_diag):
     """The diagonal kernel's cluster variant (SEQ_DIAG_CL=2: one trajectory on two CTAs, the stage matrix written into
     both CTAs' shared memory through DSMEM stores, cluster barriers per RHS) against the FP64-FMA kernel, with one and
