@@ -606,7 +606,7 @@ def ours(args):
             kname = "solve_diagblk_kernel"
         herm_large = structured_large and "Hermitian tiles" in out_h.variant
         if herm_large:
-            kname = "lh_stage_kernel"
+            kname = "lhq_stage_kernel" if "outer factor of dimension" in out_h.variant else "lh_stage_kernel"
         peak_scale = world if rows_mode else 1     # rows mode: the algorithmic flops of the ONE system are spread over all GPUs
         if out_h.method == "small":
             # N <= 6: below one DMMA tile -> the HBM roofline, FP64-FMA ceiling noted
@@ -645,13 +645,17 @@ def ours(args):
                     # a 4(3) step streams 37 h (stage input 4 h, fused stages 7 + 8 + 10 + 8 h), a 5(4) step 59 h
                     nt = (s["N"] + 31) // 32
                     h_b = 16.0 * 1024 * nt * (nt + 1) / 2
+                    if "outer factor of dimension" in out_h.variant:      # 16 x 16 tiles of the x-space, Q x Q elements per pair (kernel_large_hermq.cuh)
+                        q_loc = int(out_h.variant.split("outer factor of dimension")[1].split()[0])
+                        nxt = (s["N"] // q_loc + 15) // 16
+                        h_b = 16.0 * 256 * q_loc * q_loc * nxt * (nxt + 1) / 2
                     rhs_all, att_all = float(np.sum(stats[:, 2])), float(np.sum(stats[:, 0]) + np.sum(stats[:, 1]))
                     f5 = min(1.0, max(0.0, (rhs_all / max(att_all, 1.0) - 4.0) / 2.0))
                     per_rhs = h_b * ((1.0 - f5) * 37.0 / 4.0 + f5 * 59.0 / 6.0)
                     roof["hbm"].update({"executed_bytes_per_rhs_model": per_rhs, "executed_GBps_model": per_rhs * rhs_all / (k_ms * 1e-3) / 1e9,
                                         "executed_frac_model": per_rhs * rhs_all / (k_ms * 1e-3) / 1e9 / (peak_h * peak_scale),
                                         "model": "packed half vectors of 16 B x 1024 x tiles(ti<=tj): stage input 4 h, fused stage kernels 7/8/10/8 h (4(3) pair) or "
-                                                 "7/8/9/10/12/9 h (5(4) pair); ncu dram__bytes of the four stage kernels of a 4(3) step agrees (profiles/r02_c5_herm_stage_ncu_summary.json)"})
+                                                 "7/8/9/10/12/9 h (5(4) pair); ncu dram__bytes of the four stage kernels of a 4(3) step (32 x 32 tile variant) agrees (profiles/r02_c5_herm_stage_ncu_summary.json)"})
             if sw:
                 # The kernel that ran is a structure-exploiting FP64-FMA kernel: `frac` is what it EXECUTES against the
                 # peak of the pipe it uses; the dense-equivalent figure (SURVEY.md 8(d) algorithmic flops against the DMMA
