@@ -79,10 +79,7 @@ class CompiledPulseSequence(object):
 
     def _assemble(self, c_ops):
         if "H0" not in self.hc.channels:
-            H0 = sum(self.system.H0())
-            if isinstance(H0, int) and H0 == 0:
-                H0 = 0 * self.system.I()
-            self.hc.add_channel("H0", H=H0, time_dependent=False)
+            self.hc.add_channel("H0", H=self.system.H0_sum(), time_dependent=False)
         c_ops.extend(self.system.c_ops())
         H, C_ops, times = self.build_hamiltonian()
         c_ops.extend(C_ops)

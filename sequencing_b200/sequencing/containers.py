@@ -265,6 +265,37 @@ def run_sequences(sequences, init_states, e_ops=None, options=None):
         sq._t = 0
     times = [0]
     snaps = [(cur.clone(), as_ket)]
+    with system.frozen():      # one system state for the whole batch: static operators are built (and hashed) once
+        cur, as_ket, ket_dims, dm_dims = _run_items(sequences, distinct, n_items, system, eng, cur, as_ket, ket_dims, dm_dims, N, B, options, times, snaps)
+    n_snap = len(snaps)
+    ex = np.zeros((n_snap, B, len(e_ops)), dtype=complex)
+    if e_ops:
+        te = torch.from_numpy(np.ascontiguousarray(np.stack([op.full() for op in e_ops]), dtype=np.complex128)).to(eng.device)
+        for q, (st, k_) in enumerate(snaps):
+            exq = torch.empty((B, len(e_ops)), dtype=torch.complex128, device=eng.device)
+            eng._check(eng.lib.seq_engine_expect(eng.handle, te.data_ptr(), st.data_ptr(), exq.data_ptr(), N, B, len(e_ops), int(k_)))
+            ex[q] = exq.cpu().numpy()
+    host = [(st.cpu().numpy(), k_) for st, k_ in snaps]
+    times = np.array(times)
+    num_collapse = len(system.c_ops(clean=True))
+    results = []
+    for b in range(B):
+        states = [given[b]]
+        for q in range(1, n_snap):
+            arr, k_ = host[q]
+            states.append(qt.Qobj(arr[b].reshape(-1, 1), dims=ket_dims) if k_ else qt.Qobj(arr[b], dims=dm_dims))
+        expect = []
+        for m, op in enumerate(e_ops):
+            row = ex[:, b, m]
+            expect.append(np.array(row.real if op.isherm else row))
+        results.append(SequenceResult(times=times, states=states, expect=expect, num_collapse=num_collapse))
+    return results
+
+
+def _run_items(sequences, distinct, n_items, system, eng, cur, as_ket, ket_dims, dm_dims, N, B, options, times, snaps):
+    """Item k of every sequence of the batch, k = 0, 1, ...: see ``run_sequences``."""
+    from .. import solver
+    torch = eng.torch
     for k in range(n_items):
         items = {id(sq): sq._validate(sq[k]) for sq in distinct}
         first = items[id(sequences[0])]
@@ -314,29 +345,7 @@ def run_sequences(sequences, init_states, e_ops=None, options=None):
             cur = out["final_state"]
             times.append(sequences[0]._tmax)
         snaps.append((cur.clone(), as_ket))
-    n_snap = len(snaps)
-    ex = np.zeros((n_snap, B, len(e_ops)), dtype=complex)
-    if e_ops:
-        te = torch.from_numpy(np.ascontiguousarray(np.stack([op.full() for op in e_ops]), dtype=np.complex128)).to(eng.device)
-        for q, (st, k_) in enumerate(snaps):
-            exq = torch.empty((B, len(e_ops)), dtype=torch.complex128, device=eng.device)
-            eng._check(eng.lib.seq_engine_expect(eng.handle, te.data_ptr(), st.data_ptr(), exq.data_ptr(), N, B, len(e_ops), int(k_)))
-            ex[q] = exq.cpu().numpy()
-    host = [(st.cpu().numpy(), k_) for st, k_ in snaps]
-    times = np.array(times)
-    num_collapse = len(system.c_ops(clean=True))
-    results = []
-    for b in range(B):
-        states = [given[b]]
-        for q in range(1, n_snap):
-            arr, k_ = host[q]
-            states.append(qt.Qobj(arr[b].reshape(-1, 1), dims=ket_dims) if k_ else qt.Qobj(arr[b], dims=dm_dims))
-        expect = []
-        for m, op in enumerate(e_ops):
-            row = ex[:, b, m]
-            expect.append(np.array(row.real if op.isherm else row))
-        results.append(SequenceResult(times=times, states=states, expect=expect, num_collapse=num_collapse))
-    return results
+    return cur, as_ket, ket_dims, dm_dims
 
 
 class SequenceResult(object):

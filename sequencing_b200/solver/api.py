@@ -127,12 +127,21 @@ class _Lowered:
     state_herm: bool = True
     e_herm: Optional[List[bool]] = None
 
-    def signature(self):
-        ops = (self.H0, *self.Hk, *self.Lc, *self.Ltd, *self.E)
+    src: tuple = ()      # the Qobj operators this problem was lowered from (static H terms, drive terms, collapse terms, e_ops)
+
+    def signature(self, digest=None):
+        """Grouping key of a deferred solve: shapes, grid, options and the CONTENT of every operator.  ``digest`` (a
+        per-block cache, ``_Deferred._digest``) hashes each source operator once per object instead of once per solve -
+        B sequences of one system share their static operators as objects (``System.frozen``)."""
+        if digest is not None and self.src:
+            content = tuple(digest(q) for q in self.src)
+        else:
+            ops = (self.H0, *self.Hk, *self.Lc, *self.Ltd, *self.E)
+            content = hash(b"".join(np.ascontiguousarray(o).tobytes() for o in ops))
         return (
             self.H0.shape[0], self.is_ket, self.n_t, self.t0, self.dt, self.out_idx.tobytes(),
             len(self.Hk), len(self.Lc), len(self.Ltd), len(self.E), tuple(self.e_real),
-            self.store_states, self.options._key(), hash(b"".join(np.ascontiguousarray(o).tobytes() for o in ops)),
+            self.store_states, self.options._key(), content,
         )
 
 
@@ -186,12 +195,14 @@ def _lower(H, rho0, tlist, c_ops, e_ops, options) -> _Lowered:
     N = rho0.shape[0]
     H0 = np.zeros((N, N), dtype=complex)
     Hk, coeff = [], []
+    src_static, src_td = [], []
     for term in H:
         if _is_td(term):
+            src_td.append(term[0])
             c = np.asarray(term[1])
             if c.shape != (n_t,):
                 raise ValueError(f"coefficient array of length {c.shape} does not match the {n_t}-point time grid")
-            op = term[0].full()
+            op = term[0]._a      # (read only from here on: stacked into the batch arrays by _to_batch)
             if np.iscomplexobj(c) and np.any(c.imag):
                 # spline is linear: c H = Re(c) H + Im(c) (iH)
                 Hk += [op, 1j * op]
@@ -200,7 +211,8 @@ def _lower(H, rho0, tlist, c_ops, e_ops, options) -> _Lowered:
                 Hk.append(op)
                 coeff.append(np.ascontiguousarray(c.real, dtype=float))
         elif isinstance(term, qt.Qobj):
-            H0 = H0 + term.full()
+            H0 = H0 + term._a
+            src_static.append(term)
         elif isinstance(term, (int, float, complex)) and term == 0:
             continue
         else:
@@ -211,10 +223,10 @@ def _lower(H, rho0, tlist, c_ops, e_ops, options) -> _Lowered:
             c = np.asarray(term[1])
             if c.shape != (n_t,):
                 raise ValueError("collapse coefficient array does not match the time grid")
-            Ltd.append(term[0].full())
+            Ltd.append(term[0]._a)
             rate.append(np.ascontiguousarray((np.conj(c) * c).real, dtype=float))
         elif isinstance(term, qt.Qobj):
-            Lc.append(term.full())
+            Lc.append(term._a)
         else:
             raise TypeError(f"unsupported collapse operator of type {type(term)}")
 
@@ -226,8 +238,8 @@ def _lower(H, rho0, tlist, c_ops, e_ops, options) -> _Lowered:
         dm = qt.ket2dm(rho0) if rho0.isket else rho0
         state0 = dm.full()
         dims = dm.dims
-    state_herm = True if is_ket else bool(np.allclose(state0, state0.conj().T, atol=1e-12))
-    E = [e.full() for e in e_ops]
+    state_herm = True if is_ket else bool(np.array_equal(state0, state0.conj().T) or np.allclose(state0, state0.conj().T, atol=1e-12))
+    E = [e._a for e in e_ops]
     e_real = [bool(e.isherm and state_herm) for e in e_ops]
 
     # outputs must sit on coefficient-grid samples (true for every call the reference makes:
@@ -240,9 +252,12 @@ def _lower(H, rho0, tlist, c_ops, e_ops, options) -> _Lowered:
     if np.any(np.diff(out_idx) <= 0) and out_idx.size > 1:
         raise ValueError("tlist must be strictly increasing")
     store_states = bool(options.store_states) or not e_ops
+    # (static and time-dependent terms are marked apart: the same operators split differently are different problems)
+    src = (*src_static, None, *src_td, None, *[t for t in c_ops if isinstance(t, qt.Qobj)], None,
+           *[t[0] for t in c_ops if _is_td(t)], None, *e_ops)
     return _Lowered(H0, Hk, coeff, Lc, Ltd, rate, state0, is_ket, E, e_real, t0, dt, n_t,
                     out_idx.astype(np.int32), tlist, dims, options, store_states, state_herm,
-                    [bool(e.isherm) for e in e_ops])
+                    [bool(e.isherm) for e in e_ops], src)
 
 
 def _stack(ops, N):
@@ -312,10 +327,24 @@ class _Deferral:
         self.combos.append((res, self.add(part_p), self.add(part_q)))
         return res
 
+    def _digest(self, q):
+        """Content hash of a source operator, computed once per object inside this block (the cache keeps the array
+        alive, so an id is never reused)."""
+        if q is None:
+            return None
+        cache = self.__dict__.setdefault("_digests", {})
+        a = q._a
+        hit = cache.get(id(a))
+        if hit is None:
+            hit = (a, hash(np.ascontiguousarray(a).tobytes()))
+            cache[id(a)] = hit
+        return hit[1]
+
     def groups(self):
         groups = {}
         for i, it in enumerate(self.items):
-            groups.setdefault(it.signature(), []).append(i)
+            groups.setdefault(it.signature(self._digest), []).append(i)
+        self.__dict__.pop("_digests", None)
         return list(groups.values())
 
     def batch_problems(self):

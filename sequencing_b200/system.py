@@ -21,6 +21,9 @@ from .modes import Mode, sort_modes
 from .parameters import DictParameter, ListParameter, Parameterized
 
 
+_EVAL_CACHE = None      # set inside ``System.frozen()``
+
+
 class CouplingTerm(object):
     """``strength * prod_i mode_i.operator_expr(expr_i)`` (+ h.c. if ``add_hc``).
 
@@ -206,8 +209,45 @@ class System(Parameterized):
         )
         self.cross_kerrs[key] = chi
 
+    # -- evaluation cache for loops over many sequences of one system state ------------------------
+    @contextmanager
+    def frozen(self):
+        """Inside the block no parameter of any system or mode changes (``run_sequences`` lowers B sequences whose
+        captured segments each carry a deep copy of the system, ``main.py:226-233``): ``H0()``, ``c_ops()`` and
+        ``couplings()`` are evaluated once per system STATE - keyed by a fingerprint of every parameter, coupling term
+        and tensor space, so that equal copies share one evaluation - and handed out again as the same ``Qobj`` objects."""
+        global _EVAL_CACHE
+        outer = _EVAL_CACHE
+        _EVAL_CACHE = {"fp": {}, "vals": {}} if outer is None else outer
+        try:
+            yield self
+        finally:
+            _EVAL_CACHE = outer
+
+    def _fingerprint(self):
+        couplings = [(sorted(key), [([(m.name, e) for m, e in t.terms], t.strength.hex(), t.add_hc) for t in terms])
+                     for key, terms in self.coupling_terms.items()]
+        spaces = [(m.name, m.levels, [(x.name, x.levels) for x in m.space]) for m in self.modes]
+        return repr((self.as_dict(), couplings, [m.name for m in self.active_modes], spaces, self._dt))
+
+    def _cached(self, what, modes, clean, build):
+        cache = _EVAL_CACHE
+        if cache is None:
+            return build()
+        fp = cache["fp"].get(id(self))
+        if fp is None:
+            fp = (self, self._fingerprint())      # (the reference keeps the id alive)
+            cache["fp"][id(self)] = fp
+        key = (fp[1], what, tuple(mode.name for mode in modes), bool(clean))
+        if key not in cache["vals"]:
+            cache["vals"][key] = build()
+        return list(cache["vals"][key])
+
     def couplings(self, modes=None, clean=True):
         modes = self.active_modes if modes is None else modes
+        return self._cached("couplings", modes, clean, lambda: self._couplings(modes, clean))
+
+    def _couplings(self, modes, clean):
         names = {mode.name for mode in modes}
         found = []
         with self.use_modes(modes):
@@ -219,15 +259,30 @@ class System(Parameterized):
     def H0(self, modes=None, clean=True):
         """Static Hamiltonian as a list: detunings, self-Kerrs, then couplings."""
         modes = self.active_modes if modes is None else modes
-        parts = [m.detuning for m in modes] + [m.self_kerr for m in modes]
-        parts += self.couplings(modes=modes, clean=clean)
-        return [h for h in parts if h.data.nnz] if clean else parts
+
+        def build():
+            parts = [m.detuning for m in modes] + [m.self_kerr for m in modes]
+            parts += self.couplings(modes=modes, clean=clean)
+            return [h for h in parts if h.data.nnz] if clean else parts
+        return self._cached("H0", modes, clean, build)
+
+    def H0_sum(self):
+        """``sum(H0())`` as one operator (the static channel of a compiled sequence, ``basic.py:437-443``)."""
+        def build():
+            H0 = sum(self.H0())
+            if isinstance(H0, int) and H0 == 0:
+                H0 = 0 * self.I()
+            return [H0]
+        return self._cached("H0_sum", self.active_modes, True, build)[0]
 
     def c_ops(self, modes=None, clean=True):
         """Static collapse operators: all decays, then excitations, then dephasings."""
         modes = self.active_modes if modes is None else modes
-        ops = [m.decay for m in modes] + [m.excitation for m in modes] + [m.dephasing for m in modes]
-        return [c for c in ops if c.data.nnz] if clean else ops
+
+        def build():
+            ops = [m.decay for m in modes] + [m.excitation for m in modes] + [m.dephasing for m in modes]
+            return [c for c in ops if c.data.nnz] if clean else ops
+        return self._cached("c_ops", modes, clean, build)
 
     # -- (de)serialisation: cross_kerrs has frozenset keys ----------------------------------
     def as_dict(self, json_friendly=False):

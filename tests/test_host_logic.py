@@ -218,6 +218,37 @@ def test_deferred_solves_group_into_batches(oracle_engine):
     assert results[0].num_expect == 1 and results[0].solver == "mesolve"
 
 
+def test_frozen_system_evaluation_cache_and_signature_digests(qc_system):
+    """``System.frozen()`` (what ``run_sequences`` lowers a batch under): equal system STATES - also deep copies, which
+    every captured segment carries (``main.py:226-233``) - share one evaluation of H0 / c_ops as the same objects; a
+    different state gets its own; outside the block nothing is cached.  The deferred-solve signature hashes each source
+    operator once per object and still groups by CONTENT (equal operators of different identity share a batch, a changed
+    operator does not)."""
+    import copy
+    system = qc_system
+    twin = copy.deepcopy(system)
+    ref_h0 = [h.full() for h in system.H0()]
+    with system.frozen():
+        a, b = system.H0(), twin.H0()
+        assert all(x is y for x, y in zip(a, b)) and len(a) == len(b) == len(ref_h0)
+        assert all(x is y for x, y in zip(system.c_ops(), twin.c_ops()))
+        assert system.H0_sum() is twin.H0_sum()
+        other = copy.deepcopy(system)
+        other.modes[0].kerr = other.modes[0].kerr * 1.5
+        assert other.H0_sum() is not system.H0_sum()
+        assert not np.allclose(other.H0_sum().full(), system.H0_sum().full())
+    assert all(np.array_equal(x.full(), y) for x, y in zip(a, ref_h0))
+    assert system.H0_sum() is not system.H0_sum()      # (no cache outside the block)
+    # signatures: same content, different identity -> one group; different content -> two
+    psi = system.fock()
+    with deferred_solves(execute=False) as d:
+        for sysk in (system, twin, other):
+            H = [sum(sysk.H0())]
+            api.mesolve(H, psi, np.arange(4.0), sysk.c_ops(), [])
+    groups = sorted(len(g) for g in d.groups())
+    assert groups == [1, 2]
+
+
 def test_product_path_fails_loudly_without_cuda():
     import torch
     if torch.cuda.is_available():
