@@ -156,7 +156,7 @@ def tune_rabi(system, init_state, e_ops=None, mode_name="qubit", pulse_name=None
         e_pop = [float(v) for v in np.real(out.expect[:, 0, -1])]
     else:
         results = []
-        with deferred_solves():
+        with deferred_solves(), system.frozen():      # (the loop varies pulse parameters only: H0 / c_ops are built once)
             for amp in prog(amps):
                 seq = get_sequence(system)
                 with qubit.pulse_scale(amp, pulse_name=pulse_name):
@@ -275,7 +275,7 @@ def tune_drag(system, init_state, e_ops=None, mode_name="qubit", pulse_name=None
         XpY9, YpX9 = [float(v) for v in pops[:len(drags)]], [float(v) for v in pops[len(drags):]]
     else:
         res_xy, res_yx = [], []
-        with deferred_solves():
+        with deferred_solves(), system.frozen():      # (the loop varies pulse parameters only: H0 / c_ops are built once)
             for drag in prog(drags):
                 pulse.drag = drag
                 seq = get_sequence(system)
@@ -325,7 +325,7 @@ def tune_displacement(system, init_state, e_ops=None, mode_name="cavity", pulse_
     amps = np.linspace(*amp_range)
     prog = tqdm if progbar else (lambda x, **kw: x)
     results = []
-    with deferred_solves():
+    with deferred_solves(), system.frozen():      # (the loop varies pulse parameters only: H0 / c_ops are built once)
         for amp in prog(amps):
             seq = get_sequence(system)
             with cavity.pulse_scale(amp):

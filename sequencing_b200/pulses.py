@@ -182,6 +182,18 @@ def slepian_pulse(tau=None, width=10, drag=0, dt=1):
     return i_wave, drag * np.gradient(i_wave) / dt
 
 
+_PARAMETER_NAMES = {}
+
+
+def _parameter_names(func):
+    """Parameter names of a waveform function (``inspect.signature`` once per function: a sweep calls every pulse per point)."""
+    key = getattr(func, "__func__", func)
+    names = _PARAMETER_NAMES.get(key)
+    if names is None:
+        names = _PARAMETER_NAMES[key] = frozenset(inspect.signature(func).parameters)
+    return names
+
+
 @attr.s
 class Pulse(Parameterized):
     """Parameterised complex waveform generator: ``pulse_func`` shapes, ``array_pulse`` modulates."""
@@ -196,8 +208,8 @@ class Pulse(Parameterized):
     scale_noise = BoolParameter(False)
 
     def __call__(self, **kwargs):
-        shape_names = inspect.signature(self.pulse_func).parameters
-        mod_names = inspect.signature(array_pulse).parameters
+        shape_names = _parameter_names(self.pulse_func)
+        mod_names = _parameter_names(array_pulse)
         params = self.as_dict()
         # parameters feed the shape function first (so ``dt`` goes there), overrides passed
         # as keyword arguments feed the modulation first -- same precedence as pulses.py:276-287

@@ -90,7 +90,10 @@ class Qobj:
     @property
     def isherm(self) -> bool:
         a = self._a
-        return a.shape[0] == a.shape[1] and bool(np.allclose(a, a.conj().T, atol=1e-12, rtol=0))
+        if a.shape[0] != a.shape[1]:
+            return False
+        at = a.conj().T
+        return bool(np.array_equal(a, at) or np.allclose(a, at, atol=1e-12, rtol=0))      # (exact test first: most operators are exactly Hermitian)
 
     def full(self, order="C", squeeze=False):
         out = np.array(self._a, order=order)

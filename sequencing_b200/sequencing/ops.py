@@ -117,12 +117,14 @@ def capture_operation(func):
     filled with the global sequence's start time.
     """
 
+    t0_param = inspect.signature(func).parameters.get("t0")
+    fill_t0 = t0_param is not None and t0_param.default is None
+
     @wraps(func)
     def wrapper(*args, **kwargs):
         sequence = get_sequence()
         if sequence.system is not None:
-            t0_param = inspect.signature(func).parameters.get("t0")
-            if t0_param is not None and t0_param.default is None and kwargs.get("t0") is None:
+            if fill_t0 and kwargs.get("t0") is None:
                 kwargs["t0"] = sequence.t0
         capture = kwargs.pop("capture", True)
         produced = func(*args, **kwargs)
