@@ -33,6 +33,14 @@ namespace seq {
 
 #define LH_T 32
 #define LH_TE (LH_T * LH_T)
+// packed streams (state, stage derivatives) pass through once per kernel: streaming loads / stores keep L1 / L2 for the gathers
+#ifdef SEQ_LQ_PLAIN_STREAMS
+#define LQ_LD(p) (*(p))
+#define LQ_ST(p, v) (*(p) = (v))
+#else
+#define LQ_LD(p) __ldcs(p)
+#define LQ_ST(p, v) __stcs((p), (v))
+#endif
 
 struct LargeHermBufs {
   cplx* ybuf[2];            // packed state / new state
@@ -163,7 +171,7 @@ __global__ void __launch_bounds__(256) lh_first_kernel(const LargeDev* __restric
 #pragma unroll
   for (int q = 0; q < 4; q++) {
     const int idx = (w + 8 * q) * LH_T + lane;
-    const cplx yv = y[idx], kv = k0[idx];
+    const cplx yv = LQ_LD(y + idx), kv = LQ_LD(k0 + idx);
     v[q] = cmake(fma(h, fma(a10, kv.x, 0.0), yv.x), fma(h, fma(a10, kv.y, 0.0), yv.y));
   }
   lh_write_tile(bf.Yfull[1], bf.NPh, ti, tj, v, sm);
@@ -305,7 +313,7 @@ __global__ void __launch_bounds__(256, MINB) lh_stage_kernel(LargeDev* __restric
     cplx* kd = bf.kbuf[dev->kmap[st]] + tbase;
     if (!(bf.dbg & 4))
 #pragma unroll
-    for (int q = 0; q < 4; q++) kd[(w + 8 * q) * LH_T + lane] = kv[q];
+    for (int q = 0; q < 4; q++) LQ_ST(kd + (w + 8 * q) * LH_T + lane, kv[q]);
   }
   if (!last) {
     // Y_{st+1} = y + h sum_{jj <= st} a_{st+1,jj} k_jj   (zero coefficients skipped: fma(0, k, acc) = acc)
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(256, MINB) lh_stage_kernel(LargeDev* __restric
       const cplx* kj = bf.kbuf[dev->kmap[jj]] + tbase;
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        const cplx kq = kj[(w + 8 * q) * LH_T + lane];
+        const cplx kq = LQ_LD(kj + (w + 8 * q) * LH_T + lane);
         acc[q].x = fma(aj, kq.x, acc[q].x);
         acc[q].y = fma(aj, kq.y, acc[q].y);
       }
@@ -327,7 +335,7 @@ __global__ void __launch_bounds__(256, MINB) lh_stage_kernel(LargeDev* __restric
     cplx v[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      const cplx yq = y[(w + 8 * q) * LH_T + lane];
+      const cplx yq = LQ_LD(y + (w + 8 * q) * LH_T + lane);
       acc[q].x = fma(as, kv[q].x, acc[q].x);
       acc[q].y = fma(as, kv[q].y, acc[q].y);
       v[q] = cmake(fma(h, acc[q].x, yq.x), fma(h, acc[q].y, yq.y));
@@ -335,7 +343,7 @@ __global__ void __launch_bounds__(256, MINB) lh_stage_kernel(LargeDev* __restric
     if (st == S - 2) {      // the propagated solution: the new state if the step is accepted
       cplx* yn = bf.ybuf[dev->ycur ^ 1] + tbase;
 #pragma unroll
-      for (int q = 0; q < 4; q++) yn[(w + 8 * q) * LH_T + lane] = v[q];
+      for (int q = 0; q < 4; q++) LQ_ST(yn + (w + 8 * q) * LH_T + lane, v[q]);
     }
     if (bf.dbg & 3) {
       if (!(bf.dbg & 2)) lh_write_tile(bf.Yfull[(st + 1) & 1], NP, ti, ti, v, sm);      // own tile only (written where the diagonal tile would go: timing only)
@@ -353,7 +361,7 @@ __global__ void __launch_bounds__(256, MINB) lh_stage_kernel(LargeDev* __restric
       const cplx* kj = bf.kbuf[dev->kmap[jj]] + tbase;
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        const cplx kq = kj[(w + 8 * q) * LH_T + lane];
+        const cplx kq = LQ_LD(kj + (w + 8 * q) * LH_T + lane);
         er[q].x = fma(ej, kq.x, er[q].x);
         er[q].y = fma(ej, kq.y, er[q].y);
       }
@@ -369,7 +377,7 @@ __global__ void __launch_bounds__(256, MINB) lh_stage_kernel(LargeDev* __restric
       const int r = w + 8 * q;
       if (ti * LH_T + r < N && j < N) {
         const double ex = fma(el, kv[q].x, er[q].x) * h, ey = fma(el, kv[q].y, er[q].y) * h;
-        const cplx yq = y[r * LH_T + lane], nq = p0[q * rs];
+        const cplx yq = LQ_LD(y + r * LH_T + lane), nq = p0[q * rs];
         const double s = atol + rtol * sqrt(fmax(fmax(yq.x * yq.x + yq.y * yq.y, nq.x * nq.x + nq.y * nq.y), m2floor));
         es = fma(ex * ex + ey * ey, 1.0 / (s * s), es);
       }

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) lhq_first_kernel(const LargeDev* __restri
   cplx v[Q * Q];
 #pragma unroll
   for (int e = 0; e < Q * Q; e++) {
-    const cplx yv = y[e * LQ_TE], kv = k0[e * LQ_TE];
+    const cplx yv = LQ_LD(y + e * LQ_TE), kv = LQ_LD(k0 + e * LQ_TE);
     v[e] = cmake(fma(h, fma(a10, kv.x, 0.0), yv.x), fma(h, fma(a10, kv.y, 0.0), yv.y));
   }
   lhq_write<Q>(bf.Yfull[1], bf.NPh, L, xi, xj, v, sm);
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(256, (Q > 3 ? 1 : 2)) lhq_stage_kernel(LargeDe
   {
     cplx* kd = bf.kbuf[dev->kmap[st]] + tbase;
 #pragma unroll
-    for (int e = 0; e < E; e++) kd[e * LQ_TE] = kv[e];
+    for (int e = 0; e < E; e++) LQ_ST(kd + e * LQ_TE, kv[e]);
   }
   const cplx* y = bf.ybuf[dev->ycur] + tbase;
   if (!last) {
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(256, (Q > 3 ? 1 : 2)) lhq_stage_kernel(LargeDe
       const cplx* kj = bf.kbuf[dev->kmap[jj]] + tbase;
 #pragma unroll
       for (int e = 0; e < E; e++) {
-        const cplx kq = kj[e * LQ_TE];
+        const cplx kq = LQ_LD(kj + e * LQ_TE);
         acc[e].x = fma(aj, kq.x, acc[e].x);
         acc[e].y = fma(aj, kq.y, acc[e].y);
       }
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(256, (Q > 3 ? 1 : 2)) lhq_stage_kernel(LargeDe
     const double as = RK_A[pair][st + 1][st];
 #pragma unroll
     for (int e = 0; e < E; e++) {
-      const cplx yq = y[e * LQ_TE];
+      const cplx yq = LQ_LD(y + e * LQ_TE);
       acc[e].x = fma(as, kv[e].x, acc[e].x);
       acc[e].y = fma(as, kv[e].y, acc[e].y);
       acc[e] = cmake(fma(h, acc[e].x, yq.x), fma(h, acc[e].y, yq.y));
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256, (Q > 3 ? 1 : 2)) lhq_stage_kernel(LargeDe
     if (st == S - 2) {      // the propagated solution: the new state if the step is accepted
       cplx* yn = bf.ybuf[dev->ycur ^ 1] + tbase;
 #pragma unroll
-      for (int e = 0; e < E; e++) yn[e * LQ_TE] = acc[e];
+      for (int e = 0; e < E; e++) LQ_ST(yn + e * LQ_TE, acc[e]);
     }
     lhq_write<Q>(bf.Yfull[(st + 1) & 1], NP, L, xi, xj, acc, sm);
   } else {
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(256, (Q > 3 ? 1 : 2)) lhq_stage_kernel(LargeDe
       const cplx* kj = bf.kbuf[dev->kmap[jj]] + tbase;
 #pragma unroll
       for (int e = 0; e < E; e++) {
-        const cplx kq = kj[e * LQ_TE];
+        const cplx kq = LQ_LD(kj + e * LQ_TE);
         er[e].x = fma(ej, kq.x, er[e].x);
         er[e].y = fma(ej, kq.y, er[e].y);
       }
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(256, (Q > 3 ? 1 : 2)) lhq_stage_kernel(LargeDe
 #pragma unroll
       for (int e = 0; e < E; e++) {
         const double ex = fma(el, kv[e].x, er[e].x) * h, ey = fma(el, kv[e].y, er[e].y) * h;
-        const cplx yq = y[e * LQ_TE];
+        const cplx yq = LQ_LD(y + e * LQ_TE);
         const double s = atol + rtol * sqrt(fmax(fmax(yq.x * yq.x + yq.y * yq.y, yv[e].x * yv[e].x + yv[e].y * yv[e].y), m2floor));
         es = fma(ex * ex + ey * ey, 1.0 / (s * s), es);
       }
