@@ -493,7 +493,7 @@ int seq_engine_nccl_destroy(seq_engine* e) {
 int seq_engine_abi_version(void) { return SEQ_ENGINE_ABI_VERSION; }
 
 const char* seq_engine_build_info(void) {
-  return "seq_engine abi=3 arch=sm_100a kernels=diagblk(operators by diagonals, one tensor factor inside a thread, fma),diag(operators by diagonals, fma, rho upper triangle in registers),ketdiag(kets by diagonals),sparse(ELL operator rows, fma),generic(fma),dmma(8x8x4 resident),dmma_stream(8x8x4 blocked),small(thread-per-trajectory real superoperator),large(structured RHS with device-resident step control | stream-K DMMA ZGEMM; row-sharded over hooks or native NCCL) built " __DATE__;
+  return "seq_engine abi=3 arch=sm_100a kernels=diagblk(operators by diagonals, one tensor factor inside a thread, fma),diag(operators by diagonals, fma, rho upper triangle in registers),ketdiag(kets by diagonals),sparse(ELL operator rows, fma),generic(fma),dmma(8x8x4 resident),dmma_stream(8x8x4 blocked),small(thread-per-trajectory real superoperator),large(Hermitian tiles with fused stage kernels, outer tensor factor inside a thread, device-resident step control | full-matrix structured RHS | stream-K DMMA ZGEMM; row-sharded over hooks or native NCCL) built " __DATE__;
 }
 
 int seq_engine_create(int device, void* stream, seq_engine** out) {
