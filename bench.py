@@ -722,6 +722,31 @@ def ours(args):
                 parity["engine_kernel"] = kname
             except Exception as exc:
                 parity = {"error": repr(exc)}
+        if world == 1 and herm_large and parity is None:
+            # C5: the oracle's N^2 x N^2 Liouvillian does not exist at N = 1875 (tests/test_c5_large.py holds the sparse-operator CPU
+            # truth); what a bench run can check is the benched kernels against the full-matrix stepper of the same path on the
+            # sequence's first operation - same steps, same numbers
+            try:
+                import sequencing_b200.workloads as _w
+                outs = {}
+                for mode in ("herm", "full"):
+                    one = _w.c5_transmon_two_cavities(n_ops=1)
+                    one.method = seqlib.METHOD_LARGE
+                    if mode == "full":
+                        os.environ["SEQ_LARGE_FULL"] = "1"
+                    try:
+                        outs[mode] = eng.solve(one)
+                    finally:
+                        os.environ.pop("SEQ_LARGE_FULL", None)
+                parity = {"what": "Hermitian-tile stepper vs the full-matrix stepper of the large path, first operation of the C5 sequence (GPU vs GPU; "
+                                  "the CPU truth at N = 1875 is tests/test_c5_large.py)",
+                          "variants": [outs["herm"].variant, outs["full"].variant],
+                          "max_abs_final_state": float(np.max(np.abs(outs["herm"].final_state - outs["full"].final_state))),
+                          "max_abs_expect": float(np.max(np.abs(outs["herm"].expect - outs["full"].expect))),
+                          "same_steps": bool(np.array_equal(outs["herm"].stats[:, :3], outs["full"].stats[:, :3])),
+                          "engine_kernel": kname}
+            except Exception as exc:
+                parity = {"error": repr(exc)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if (rows_mode or strong) else "weak", "vs_baseline": None,
